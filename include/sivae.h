@@ -1,0 +1,177 @@
+/*
+ * sivae.h -- C ABI of libsivae.so: hand-written sm_100a kernels for the training hot path of
+ * M-hayatooo/Soft-intro-VAE-for-3D-MRI (encoder/decoder forward+backward and the introspective loss).
+ *
+ * The reference has no FFI / plugin layer: every operation below is an *implicit library call*
+ * the reference makes through torch.nn (cuDNN / ATen).  Each entry point cites the reference
+ * call site (path:line relative to the reference checkout) whose computation it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless marked "host".
+ *   - activations are NDHWC ("channels-last-3d") bf16: x[n][d][h][w][c]; 1-channel model inputs /
+ *     outputs / latents are fp32 [n][d][h][w] (identical bytes to the reference's NCDHW with C=1).
+ *   - C (channels) of bf16 activations must be a multiple of 8; the tcgen05 convolutions require
+ *     Cin, Cout in {64, 128, 256} (the headline network; other widths are channel-padded by the host).
+ *   - the caller owns every buffer including workspaces; no allocation, no host sync inside.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *   - return value: 0 on success, negative on error; sivae_last_error() gives the message
+ *     (thread-local).
+ */
+#ifndef SIVAE_H_
+#define SIVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIVAE_ABI_VERSION 1
+
+/* resample modes of the fused BN/activation pass */
+#define SIVAE_RESAMPLE_NONE 0
+#define SIVAE_RESAMPLE_AVGPOOL2 1 /* nn.AvgPool3d(kernel_size=2)           models/models.py:20 */
+#define SIVAE_RESAMPLE_UPSAMPLE2 2 /* nn.Upsample(scale_factor=2), nearest  models/models.py:58 */
+
+const char* sivae_last_error(void);
+int sivae_abi_version(void);
+/* 0 if the current device is compute capability 10.x, negative otherwise. */
+int sivae_device_check(void);
+/* number of kernels launched by this library since load (diagnostic for bench.py "gpu_launches"). */
+long long sivae_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3x3x3 convolutions, stride 1, pad 1, no bias (nn.Conv3d in BuildingBlock / UpsampleBuildingkBlock,
+ * models/models.py:17,21,55,59) and their autograd (lossE.backward(), utils/my_trainer.py:287,323).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fp32 [Cout][Cin][3][3][3] (torch layout) -> two bf16 packs:
+ *   wf[tap][Cout][Cin]            forward operand
+ *   wd[26-tap][Cin][Cout]         data-gradient operand (spatially flipped, channel-transposed)
+ * either output may be NULL. */
+int sivae_pack_conv3_weights(const float* w, int Cout, int Cin, void* wf_bf16, void* wd_bf16, void* stream);
+
+/* y[n,d,h,w,co] = sum_{tap,ci} x[n,d+kd-1,h+kh-1,w+kw-1,ci] * wpack[tap][co][ci]   (zero padding)
+ * Implicit GEMM on tcgen05 (TMA-staged NDHWC tiles, fp32 accumulation in TMEM, bf16 store).
+ * Forward uses wf; the data gradient is the same call on dy with wd (Cin/Cout swapped). */
+int sivae_conv3_igemm(const void* x_bf16, const void* wpack_bf16, void* y_bf16,
+                      int N, int D, int H, int W, int Cin, int Cout, void* stream);
+
+/* dw[co][ci][tap] = sum_{n,d,h,w} dy[n,d,h,w,co] * x[n,d+kd-1,h+kh-1,w+kw-1,ci]   (fp32, torch layout)
+ * Split-K tcgen05 GEMM over voxels + deterministic second-stage reduction. */
+size_t sivae_conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
+int sivae_conv3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw,
+                      void* workspace, size_t workspace_bytes,
+                      int N, int D, int H, int W, int Cin, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm3d (train mode) + (Leaky)ReLU + residual + AvgPool/Upsample + Dropout, fused
+ * (nn.BatchNorm3d models/models.py:18,22,56,60,93,119; LeakyReLU :15,19,94,121; residual :39-41;
+ *  AvgPool3d :20; Upsample :58; Dropout :95,122).
+ * ---------------------------------------------------------------------------------------------- */
+
+size_t sivae_bn_workspace_bytes(int C);
+
+/* Batch statistics of y (bf16 [nvox][C]) and the affine coefficients of the normalisation:
+ *   mean[c], invstd[c] = 1/sqrt(var_biased+eps), scale[c] = gamma*invstd, shift[c] = beta-mean*scale
+ * Updates running_mean/running_var (momentum, unbiased variance) and num_batches_tracked (int64)
+ * in place when they are non-NULL, exactly as torch's native_batch_norm in training mode. */
+int sivae_bn_train_coeffs(const void* y_bf16, long long nvox, int C,
+                          const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches_tracked,
+                          float momentum, float eps,
+                          float* mean, float* invstd, float* scale, float* shift,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = resample( dropout( act( y*scale[c]+shift[c] (+ res) ) ) )
+ *   act(t) = t>0 ? t : slope*t        (slope 0.2 = LeakyReLU(0.2), slope 0 = ReLU)
+ *   dropout: keep-mask (uint8 NDHWC, 0/1) if mask != NULL, else Philox(seed) if p > 0, else none;
+ *            kept values are scaled by 1/(1-p).
+ * y, res: [N][D][H][W][C] bf16; out: [N][D'][H'][W'][C] with D' = D/2, D or 2D per `resample`. */
+int sivae_bn_act_fwd(const void* y_bf16, const float* scale, const float* shift, const void* res_bf16,
+                     void* out_bf16, int N, int D, int H, int W, int C, float slope, int resample,
+                     const uint8_t* mask, float p, unsigned long long seed, void* stream);
+
+/* Backward of sivae_bn_train_coeffs + sivae_bn_act_fwd given g = dLoss/d(out) (bf16, out's shape):
+ *   dconv = gradient w.r.t. y (bf16), dres = gradient w.r.t. res (bf16, may be NULL),
+ *   dgamma, dbeta fp32 [C] (may be NULL).  Full train-mode BN backward:
+ *   dy = gamma*invstd*(dt - mean(dt) - xhat*mean(dt*xhat)).                                       */
+int sivae_bn_act_bwd(const void* g_bf16, const void* y_bf16, const void* res_bf16,
+                     const float* mean, const float* invstd, const float* gamma, const float* beta,
+                     void* dconv_bf16, void* dres_bf16, float* dgamma, float* dbeta,
+                     int N, int D, int H, int W, int C, float slope, int resample,
+                     const uint8_t* mask, float p, unsigned long long seed,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Thin convolutions with a single channel on one side (direct, HBM-bound; no tensor cores):
+ *   encoder stem Conv3d(1,in_ch,3)        models/models.py:92
+ *   decoder tail Conv3d(in_ch,1,3)+ReLU+Dropout(.35)   models/models.py:137-140
+ *   mu / var heads Conv3d(C,1,1)          models/models.py:216-217
+ *   decoder stem Conv3d(1,C,1)            models/models.py:118
+ * T is the tap count: 27 (3x3x3, pad 1) or 1 (1x1x1).  Weights are the torch tensors as they lie in
+ * memory: both [C][1][k][k][k] and [1][C][k][k][k] are w[c][t].  flip=1 uses tap 26-t (transposed conv).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y[v][c] (+)= bias[c] + sum_t w[c][t] * x1[v + delta(t)]           x1 fp32 [N][D][H][W], y bf16 NDHWC */
+int sivae_c1_to_cn(const float* x1, const float* w, const float* bias, void* y_bf16,
+                   int N, int D, int H, int W, int C, int T, int flip, int accumulate, void* stream);
+
+/* y[v] = act( bias[0] + sum_{t,c} w[c][t] * x[v + delta(t)][c] )     x bf16 NDHWC, y fp32 [N][D][H][W]
+ *   act = 0: identity; act = 1: ReLU followed by dropout (mask / Philox(seed) / p as above).        */
+int sivae_cn_to_c1(const void* x_bf16, const float* w, const float* bias, float* y,
+                   int N, int D, int H, int W, int C, int T, int flip, int act,
+                   const uint8_t* mask, float p, unsigned long long seed, void* stream);
+
+/* dw[c][t] = sum_v xc[v][c] * x1[v + delta(t)];  sum_c[c] = sum_v xc[v][c];  sum_1[0] = sum_v x1[v]
+ * (sum_c, sum_1 may be NULL).  Deterministic two-stage reduction. */
+size_t sivae_wgrad_c1_workspace_bytes(int N, int D, int H, int W, int C, int T);
+int sivae_wgrad_c1(const void* xc_bf16, const float* x1, float* dw, float* sum_c, float* sum_1,
+                   int N, int D, int H, int W, int C, int T, int flip,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* backward of ReLU+Dropout on the decoder output: dy[i] = out[i] > 0 ? g[i]/(1-p) : 0 */
+int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n, float p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent / loss kernels (fp32, coalesced float4 + warp-shuffle reductions)
+ *   reparameterize           models/models.py:263-271
+ *   calc_kl                  utils/my_trainer.py:38-48   (= lossf.kld_loss, models/lossf.py:14-18)
+ *   calc_reconstruction_loss utils/my_trainer.py:62-78   (= lossf.mse_loss, models/lossf.py:5-12)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* z = mu + eps*exp(0.5*logvar), three separately rounded fp32 operations (bit-equal to torch).
+ * eps == NULL -> the scalar eps_const is used (validation path, eps = 0.1). */
+int sivae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float eps_const,
+                      float* z, long long n, void* stream);
+/* dmu (+)= dz ; dlogvar (+)= dz*eps*0.5*exp(0.5*logvar).  accumulate=1 adds into dmu/dlogvar. */
+int sivae_reparam_bwd(const float* dz, const float* logvar, const float* eps, float eps_const,
+                      float* dmu, float* dlogvar, long long n, int accumulate, void* stream);
+
+/* kl[b] = -0.5 * sum_j (1 + logvar - mu^2 - exp(logvar))     mu, logvar: [B][n] */
+int sivae_kl_persample_fwd(const float* mu, const float* logvar, float* kl, int B, long long n, void* stream);
+/* dmu (+)= g[b]*mu ; dlogvar (+)= g[b]*0.5*(exp(logvar)-1) */
+int sivae_kl_persample_bwd(const float* mu, const float* logvar, const float* g, float* dmu, float* dlogvar,
+                           int B, long long n, int accumulate, void* stream);
+
+/* r[b] = sum_j (x[b][j]-y[b][j])^2 */
+size_t sivae_mse_workspace_bytes(int B, long long n);
+int sivae_mse_persample_fwd(const float* x, const float* y, float* r, int B, long long n,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* dx = 2*(x-y)*g[b], dy = -dx; either output may be NULL (Q13: both operands can need a gradient). */
+int sivae_mse_persample_bwd(const float* x, const float* y, const float* g, float* dx, float* dy,
+                            int B, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout helpers at the module boundary (used by parity tests and for non-unit channel inputs)
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 NCDHW -> bf16 NDHWC and back */
+int sivae_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst_bf16, int N, int C, long long vox, void* stream);
+int sivae_ndhwc_bf16_to_ncdhw_f32(const void* src_bf16, float* dst, int N, int C, long long vox, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIVAE_H_ */

@@ -1,0 +1,458 @@
+// pointwise.cu -- HBM-bound kernels around the tensor-core convolutions (all NDHWC bf16, 16-byte vectors):
+//   * BatchNorm3d (train) statistics / coefficients           models/models.py:18,22,56,60,93,119
+//   * fused BN-apply + (Leaky)ReLU + residual + AvgPool3d(2) / Upsample(2) + Dropout, forward and backward
+//                                                              models/models.py:15-22,39-41,53-60,94-95,121-122
+// One thread owns a fixed group of 8 channels (one 16-byte vector) and walks voxels, so per-channel
+// reductions need no atomics: registers -> shared-memory tree -> per-block partials -> fp64 finalize.
+#include "sivae_common.cuh"
+
+namespace sivae {
+
+static constexpr int kBnThreads = 256;
+static constexpr int kBnMaxBlocks = 148 * 8;
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void ldf8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// keep-scale of dropout for the 8 channels of voxel-linear element base `e0` (= voxel*C + c0)
+__device__ __forceinline__ void drop8(const uint8_t* mask, float p, unsigned long long seed, long long e0,
+                                      float (&ks)[8]) {
+  if (mask == nullptr && p <= 0.f) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = 1.f;
+    return;
+  }
+  const float inv = 1.f / (1.f - p);
+  if (mask != nullptr) {
+    const uint2 m = *reinterpret_cast<const uint2*>(mask + e0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = (((k < 4 ? m.x : m.y) >> ((k & 3) * 8)) & 0xffu) ? inv : 0.f;
+  } else {
+    // e0 is a multiple of 8: two Philox blocks cover the 8 elements
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const unsigned long long b = (unsigned long long)e0 >> 2;
+    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u), key);
+    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(b + 1), (uint32_t)((b + 1) >> 32), 0u, 0u), key);
+    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = ((float)(w[k] >> 8) * (1.0f / 16777216.0f) >= p) ? inv : 0.f;
+  }
+}
+
+// Block-level reduction of per-thread (s1[8], s2[8]) for threads sharing a channel chunk; result to
+// partial[(blockIdx.x*2 + {0,1})*C + c].
+__device__ __forceinline__ void block_reduce_channels(const float (&s1)[8], const float (&s2)[8], int C, int cpc,
+                                                      float* __restrict__ partial) {
+  __shared__ float sh[kBnThreads][17];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sh[threadIdx.x][k] = s1[k];
+    sh[threadIdx.x][8 + k] = s2[k];
+  }
+  __syncthreads();
+  const int lanes_v = kBnThreads / cpc;
+  for (int j = threadIdx.x; j < C; j += kBnThreads) {
+    const int chunk = j >> 3, k = j & 7;
+    float a = 0.f, b = 0.f;
+    for (int lv = 0; lv < lanes_v; ++lv) {
+      a += sh[lv * cpc + chunk][k];
+      b += sh[lv * cpc + chunk][8 + k];
+    }
+    partial[((long long)blockIdx.x * 2 + 0) * C + j] = a;
+    partial[((long long)blockIdx.x * 2 + 1) * C + j] = b;
+  }
+}
+
+// ---- BN statistics ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long nvox,
+                                                              int C, float* __restrict__ partial) {
+  const int cpc = C >> 3;
+  const int chunk = threadIdx.x % cpc;
+  const int lanes_v = kBnThreads / cpc;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long v = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v < nvox; v += (long long)gridDim.x * lanes_v) {
+    float f[8];
+    ld8(y + v * C + chunk * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += f[k];
+      s2[k] += f[k] * f[k];
+    }
+  }
+  block_reduce_channels(s1, s2, C, cpc, partial);
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long nvox,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* running_mean, float* running_var, long long* nbt, float momentum,
+                                         float eps, float* mean_o, float* invstd_o, float* scale_o, float* shift_o) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += (double)partial[((long long)i * 2 + 0) * C + c];
+    b += (double)partial[((long long)i * 2 + 1) * C + c];
+  }
+  const double n = (double)nvox;
+  const double mean = a / n;
+  double var = b / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  mean_o[c] = (float)mean;
+  invstd_o[c] = invstd;
+  scale_o[c] = g * invstd;
+  shift_o[c] = bt - (float)mean * g * invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unb = nvox > 1 ? var * n / (n - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// ---- fused forward ------------------------------------------------------------------------------
+// activated value of one input-voxel channel chunk
+__device__ __forceinline__ void act_chunk(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
+                                          const float (&sc)[8], const float (&sh)[8], long long e0, float slope,
+                                          const uint8_t* mask, float p, unsigned long long seed, float (&a)[8]) {
+  float f[8], ks[8];
+  ld8(y + e0, f);
+  if (res != nullptr) {
+    float r[8];
+    ld8(res + e0, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]) + r[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+  }
+  drop8(mask, p, seed, e0, ks);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = (f[k] > 0.f ? f[k] : slope * f[k]) * ks[k];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ y,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift,
+                                                         const __nv_bfloat16* __restrict__ res,
+                                                         __nv_bfloat16* __restrict__ out, int N, int D, int H, int W,
+                                                         int C, float slope, const uint8_t* __restrict__ mask, float p,
+                                                         unsigned long long seed) {
+  const int cpc = C >> 3;
+  const long long nvox_in = (long long)N * D * H * W;
+  const long long items = (MODE == SIVAE_RESAMPLE_AVGPOOL2 ? nvox_in / 8 : nvox_in) * cpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i % cpc);
+    const long long v = i / cpc;
+    float sc[8], sh[8];
+    ldf8(scale + chunk * 8, sc);
+    ldf8(shift + chunk * 8, sh);
+    if (MODE == SIVAE_RESAMPLE_NONE) {
+      float a[8];
+      act_chunk(y, res, sc, sh, v * C + chunk * 8, slope, mask, p, seed, a);
+      st8(out + v * C + chunk * 8, a);
+    } else if (MODE == SIVAE_RESAMPLE_AVGPOOL2) {
+      const int Wo = W / 2, Ho = H / 2, Do = D / 2;
+      const int wo = (int)(v % Wo);
+      const int ho = (int)((v / Wo) % Ho);
+      const int dd = (int)((v / ((long long)Wo * Ho)) % Do);
+      const long long n = v / ((long long)Wo * Ho * Do);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long vi = ((n * D + (2 * dd + (q >> 2))) * H + (2 * ho + ((q >> 1) & 1))) * W + (2 * wo + (q & 1));
+        float a[8];
+        act_chunk(y, res, sc, sh, vi * C + chunk * 8, slope, mask, p, seed, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += a[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= 0.125f;
+      st8(out + v * C + chunk * 8, acc);
+    } else {
+      const int w = (int)(v % W);
+      const int h = (int)((v / W) % H);
+      const int d = (int)((v / ((long long)W * H)) % D);
+      const long long n = v / ((long long)W * H * D);
+      float a[8];
+      act_chunk(y, res, sc, sh, v * C + chunk * 8, slope, mask, p, seed, a);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long vo =
+            ((n * (2 * D) + (2 * d + (q >> 2))) * (2 * H) + (2 * h + ((q >> 1) & 1))) * (2 * W) + (2 * w + (q & 1));
+        st8(out + vo * C + chunk * 8, a);
+      }
+    }
+  }
+}
+
+// ---- fused backward -----------------------------------------------------------------------------
+// dt (gradient at the BN output, after activation/dropout/resample backward) and xhat for one input voxel chunk
+template <int MODE>
+__device__ __forceinline__ void bwd_chunk(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                          const __nv_bfloat16* __restrict__ res, const float (&mean)[8],
+                                          const float (&invstd)[8], const float (&gam)[8], const float (&bet)[8],
+                                          long long v, int chunk, int N, int D, int H, int W, int C, float slope,
+                                          const uint8_t* mask, float p, unsigned long long seed, float (&dt)[8],
+                                          float (&xh)[8]) {
+  const long long e0 = v * C + chunk * 8;
+  float f[8], gp[8], ks[8];
+  ld8(y + e0, f);
+  if (MODE == SIVAE_RESAMPLE_NONE) {
+    ld8(g + e0, gp);
+  } else {
+    const int w = (int)(v % W);
+    const int h = (int)((v / W) % H);
+    const int d = (int)((v / ((long long)W * H)) % D);
+    const long long n = v / ((long long)W * H * D);
+    if (MODE == SIVAE_RESAMPLE_AVGPOOL2) {
+      const long long vo = ((n * (D / 2) + d / 2) * (H / 2) + h / 2) * (W / 2) + w / 2;
+      ld8(g + vo * C + chunk * 8, gp);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k] *= 0.125f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long vo =
+            ((n * (2 * D) + (2 * d + (q >> 2))) * (2 * H) + (2 * h + ((q >> 1) & 1))) * (2 * W) + (2 * w + (q & 1));
+        float t[8];
+        ld8(g + vo * C + chunk * 8, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gp[k] += t[k];
+      }
+    }
+  }
+  drop8(mask, p, seed, e0, ks);
+  float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (res != nullptr) ld8(res + e0, r);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    xh[k] = (f[k] - mean[k]) * invstd[k];
+    const float t = fmaf(xh[k], gam[k], bet[k]) + r[k];
+    dt[k] = gp[k] * ks[k] * (t > 0.f ? 1.f : slope);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                         const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int N, int D, int H, int W, int C, float slope,
+                         const uint8_t* __restrict__ mask, float p, unsigned long long seed,
+                         float* __restrict__ partial) {
+  const int cpc = C >> 3;
+  const int chunk = threadIdx.x % cpc;
+  const int lanes_v = kBnThreads / cpc;
+  const long long nvox = (long long)N * D * H * W;
+  float mu[8], is[8], ga[8], be[8];
+  ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long v = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v < nvox; v += (long long)gridDim.x * lanes_v) {
+    float dt[8], xh[8];
+    bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += dt[k];
+      s2[k] += dt[k] * xh[k];
+    }
+  }
+  block_reduce_channels(s1, s2, C, cpc, partial);
+}
+
+// coef[0][c] = sum(dt)/n, coef[1][c] = sum(dt*xhat)/n ; dgamma = sum(dt*xhat), dbeta = sum(dt)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long nvox,
+                                       float* __restrict__ coef, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += (double)partial[((long long)i * 2 + 0) * C + c];
+    b += (double)partial[((long long)i * 2 + 1) * C + c];
+  }
+  coef[c] = (float)(a / (double)nvox);
+  coef[C + c] = (float)(b / (double)nvox);
+  if (dbeta) dbeta[c] = (float)a;
+  if (dgamma) dgamma[c] = (float)b;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                        const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ coef,
+                        __nv_bfloat16* __restrict__ dconv, __nv_bfloat16* __restrict__ dres, int N, int D, int H, int W,
+                        int C, float slope, const uint8_t* __restrict__ mask, float p, unsigned long long seed) {
+  const int cpc = C >> 3;
+  const long long items = (long long)N * D * H * W * cpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i % cpc);
+    const long long v = i / cpc;
+    float mu[8], is[8], ga[8], be[8], c1[8], c2[8], dt[8], xh[8], o[8];
+    ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+    ldf8(coef + chunk * 8, c1); ldf8(coef + C + chunk * 8, c2);
+    bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
+    st8(dconv + v * C + chunk * 8, o);
+    if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
+  }
+}
+
+// ---- layout helpers -----------------------------------------------------------------------------
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C,
+                                      long long vox) {
+  const long long total = (long long)N * C * vox;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long v = (i / C) % vox;
+    const long long n = i / ((long long)C * vox);
+    dst[i] = __float2bfloat16_rn(src[(n * C + c) * vox + v]);
+  }
+}
+__global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int N, int C,
+                                      long long vox) {
+  const long long total = (long long)N * C * vox;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % vox;
+    const int c = (int)((i / vox) % C);
+    const long long n = i / ((long long)C * vox);
+    dst[i] = __bfloat162float(src[(n * vox + v) * C + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long items, int threads) {
+  long long b = (items + threads - 1) / threads;
+  if (b > 148ll * 16) b = 148ll * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static bool channels_ok(int C) { return C >= 8 && (C % 8) == 0 && (kBnThreads % (C / 8)) == 0; }
+
+size_t bn_workspace_bytes(int C) { return ((size_t)kBnMaxBlocks * 2 * C + 2 * (size_t)C) * sizeof(float); }
+
+static int reduce_blocks(long long nvox, int C) {
+  const int lanes_v = kBnThreads / (C / 8);
+  long long b = (nvox + lanes_v - 1) / lanes_v;
+  if (b > kBnMaxBlocks) b = kBnMaxBlocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, const float* beta, float* rm, float* rv,
+                    long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+  SIVAE_CHECK(channels_ok(C), "bn_train_coeffs: unsupported channel count %d", C);
+  SIVAE_CHECK(nvox > 0, "bn_train_coeffs: empty tensor");
+  SIVAE_CHECK(ws && ws_bytes >= bn_workspace_bytes(C), "bn_train_coeffs: workspace too small");
+  const int blocks = reduce_blocks(nvox, C);
+  bn_stats_kernel<<<blocks, kBnThreads, 0, st>>>((const __nv_bfloat16*)y, nvox, C, (float*)ws);
+  SIVAE_LAUNCH_OK("bn_stats_kernel");
+  bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>((const float*)ws, blocks, C, nvox, gamma, beta, rm, rv, nbt,
+                                                         momentum, eps, mean, invstd, scale, shift);
+  SIVAE_LAUNCH_OK("bn_stats_finalize_kernel");
+  return 0;
+}
+
+static int check_resample(const char* who, int D, int H, int W, int resample) {
+  SIVAE_CHECK(resample >= 0 && resample <= 2, "%s: bad resample mode %d", who, resample);
+  if (resample == SIVAE_RESAMPLE_AVGPOOL2)
+    SIVAE_CHECK(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "%s: AvgPool3d(2) needs even extents (%d,%d,%d)", who, D, H, W);
+  return 0;
+}
+
+int bn_act_fwd(const void* y, const float* scale, const float* shift, const void* res, void* out, int N, int D, int H,
+               int W, int C, float slope, int resample, const uint8_t* mask, float p, unsigned long long seed,
+               cudaStream_t st) {
+  SIVAE_CHECK(C >= 8 && C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
+  SIVAE_CHECK(p >= 0.f && p < 1.f, "bn_act_fwd: dropout p=%f out of range", p);
+  if (check_resample("bn_act_fwd", D, H, W, resample)) return -2;
+  const long long nvox = (long long)N * D * H * W;
+  SIVAE_CHECK(nvox > 0, "bn_act_fwd: empty tensor");
+  const long long items = (resample == SIVAE_RESAMPLE_AVGPOOL2 ? nvox / 8 : nvox) * (C / 8);
+  const int blocks = grid_for(items, 256);
+  const __nv_bfloat16 *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
+  __nv_bfloat16* oo = (__nv_bfloat16*)out;
+  if (resample == 0)
+    bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+  else if (resample == 1)
+    bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+  else
+    bn_act_fwd_kernel<2><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+  SIVAE_LAUNCH_OK("bn_act_fwd_kernel");
+  return 0;
+}
+
+int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean, const float* invstd,
+               const float* gamma, const float* beta, void* dconv, void* dres, float* dgamma, float* dbeta, int N,
+               int D, int H, int W, int C, float slope, int resample, const uint8_t* mask, float p,
+               unsigned long long seed, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SIVAE_CHECK(channels_ok(C), "bn_act_bwd: unsupported channel count %d", C);
+  if (check_resample("bn_act_bwd", D, H, W, resample)) return -2;
+  SIVAE_CHECK(ws && ws_bytes >= bn_workspace_bytes(C), "bn_act_bwd: workspace too small");
+  const long long nvox = (long long)N * D * H * W;
+  SIVAE_CHECK(nvox > 0, "bn_act_bwd: empty tensor");
+  const int blocks = reduce_blocks(nvox, C);
+  float* partial = (float*)ws;
+  float* coef = partial + (size_t)kBnMaxBlocks * 2 * C;
+  const __nv_bfloat16 *gg = (const __nv_bfloat16*)g, *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
+#define SIVAE_BWD_REDUCE(M)                                                                                      \
+  bn_act_bwd_reduce_kernel<M><<<blocks, kBnThreads, 0, st>>>(gg, yy, rr, mean, invstd, gamma, beta, N, D, H, W, C, \
+                                                             slope, mask, p, seed, partial)
+  if (resample == 0) SIVAE_BWD_REDUCE(0);
+  else if (resample == 1) SIVAE_BWD_REDUCE(1);
+  else SIVAE_BWD_REDUCE(2);
+#undef SIVAE_BWD_REDUCE
+  SIVAE_LAUNCH_OK("bn_act_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, blocks, C, nvox, coef, dgamma, dbeta);
+  SIVAE_LAUNCH_OK("bn_bwd_finalize_kernel");
+  const int ablocks = grid_for(nvox * (C / 8), 256);
+#define SIVAE_BWD_APPLY(M)                                                                                      \
+  bn_act_bwd_apply_kernel<M><<<ablocks, 256, 0, st>>>(gg, yy, rr, mean, invstd, gamma, beta, coef,               \
+                                                      (__nv_bfloat16*)dconv, (__nv_bfloat16*)dres, N, D, H, W, C, \
+                                                      slope, mask, p, seed)
+  if (resample == 0) SIVAE_BWD_APPLY(0);
+  else if (resample == 1) SIVAE_BWD_APPLY(1);
+  else SIVAE_BWD_APPLY(2);
+#undef SIVAE_BWD_APPLY
+  SIVAE_LAUNCH_OK("bn_act_bwd_apply_kernel");
+  return 0;
+}
+
+int ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, long long vox, cudaStream_t st) {
+  const long long total = (long long)N * C * vox;
+  SIVAE_CHECK(total > 0, "layout: empty tensor");
+  ncdhw_to_ndhwc_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, N, C, vox);
+  SIVAE_LAUNCH_OK("ncdhw_to_ndhwc_kernel");
+  return 0;
+}
+int ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, long long vox, cudaStream_t st) {
+  const long long total = (long long)N * C * vox;
+  SIVAE_CHECK(total > 0, "layout: empty tensor");
+  ndhwc_to_ncdhw_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)src, dst, N, C, vox);
+  SIVAE_LAUNCH_OK("ndhwc_to_ncdhw_kernel");
+  return 0;
+}
+
+}  // namespace sivae
