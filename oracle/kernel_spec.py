@@ -1,0 +1,213 @@
+"""Executable specification of every function in ``soft-intro-vae-for-3d-mri_b200/kernels.py``
+(TEST INFRASTRUCTURE ONLY -- plain torch, device-agnostic, never on the product path).
+
+Two uses:
+  * ``-m gpu`` tests compare each CUDA kernel (called through the C ABI) with the function of the
+    same name here, on the same inputs;
+  * ``-m "not gpu"`` tests monkeypatch these functions over ``kernels.*`` so the whole autograd
+    wiring of the drop-in modules can be checked against ``oracle/sivae_oracle.py`` on a CPU, in
+    fp32 ("exact" mode: activations keep whatever dtype they come in with; the CUDA path uses bf16).
+
+Math is done in fp32 and rounded to the activation dtype exactly where the kernels round.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_UPSAMPLE2 = 0, 1, 2
+
+# dtype of activations created from fp32 inputs (c1_to_cn).  bf16 mirrors the CUDA path; the CPU
+# wiring tests set this to float32 to separate wiring errors from rounding.
+ACT_DTYPE = torch.bfloat16
+
+
+def _ncdhw(x):  # [N,D,H,W,C] -> [N,C,D,H,W] fp32
+    return x.float().permute(0, 4, 1, 2, 3)
+
+
+def _ndhwc(x, dtype):  # [N,C,D,H,W] -> [N,D,H,W,C]
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(dtype)
+
+
+def launch_count():
+    return 0
+
+
+def device_check():
+    return None
+
+
+def pack_conv3_weights(w):
+    co, ci = w.shape[:2]
+    w27 = w.reshape(co, ci, 27)
+    wf = w27.permute(2, 0, 1).contiguous().to(ACT_DTYPE)                 # [27,Co,Ci]
+    wd = w27.flip(2).permute(2, 1, 0).contiguous().to(ACT_DTYPE)         # [27,Ci,Co], tap flipped
+    return wf, wd
+
+
+def conv3_igemm(x, wpack):
+    co, ci = wpack.shape[1], wpack.shape[2]
+    w = wpack.float().permute(1, 2, 0).reshape(co, ci, 3, 3, 3)
+    y = F.conv3d(_ncdhw(x), w, None, 1, 1)
+    return _ndhwc(y, x.dtype)
+
+
+def conv3_wgrad(x, dy):
+    xi, g = _ncdhw(x), _ncdhw(dy)
+    co, ci = g.shape[1], xi.shape[1]
+    return torch.nn.grad.conv3d_weight(xi, (co, ci, 3, 3, 3), g, stride=1, padding=1)
+
+
+def bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps):
+    c = y.shape[-1]
+    f = y.float().reshape(-1, c)
+    n = f.shape[0]
+    mean = f.mean(0)
+    var = f.var(0, unbiased=False)
+    invstd = torch.rsqrt(var + eps)
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mean)
+    if running_var is not None:
+        running_var.mul_(1 - momentum).add_(momentum * var * (n / max(n - 1, 1)))
+    if num_batches_tracked is not None:
+        num_batches_tracked += 1
+    return mean, invstd, scale, shift
+
+
+def _keep_scale(y, mask, p):
+    if mask is not None:
+        return mask.float() * (1.0 / (1.0 - p))
+    if p > 0.0:
+        raise NotImplementedError("Philox dropout is only checked statistically; pass an explicit mask")
+    return None
+
+
+def _resample(a, resample):  # a: [N,D,H,W,C] fp32
+    if resample == RESAMPLE_AVGPOOL2:
+        return F.avg_pool3d(a.permute(0, 4, 1, 2, 3), 2).permute(0, 2, 3, 4, 1)
+    if resample == RESAMPLE_UPSAMPLE2:
+        return a.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    return a
+
+
+def _resample_T(g, resample):  # transpose of _resample; g fp32 in output space
+    if resample == RESAMPLE_AVGPOOL2:
+        return g.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.125
+    if resample == RESAMPLE_UPSAMPLE2:
+        return F.avg_pool3d(g.permute(0, 4, 1, 2, 3), 2).permute(0, 2, 3, 4, 1) * 8.0
+    return g
+
+
+def bn_act_fwd(y, scale, shift, res, slope, resample, mask=None, p=0.0, seed=0):
+    t = y.float() * scale + shift
+    if res is not None:
+        t = t + res.float()
+    a = torch.where(t > 0, t, slope * t)
+    ks = _keep_scale(y, mask, p)
+    if ks is not None:
+        a = a * ks
+    return _resample(a, resample).contiguous().to(y.dtype)
+
+
+def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope, resample, mask=None, p=0.0, seed=0,
+               need_dres=False, need_affine=True):
+    c = y.shape[-1]
+    xh = (y.float() - mean) * invstd
+    t = xh * gamma + beta
+    if res is not None:
+        t = t + res.float()
+    gp = _resample_T(g.float(), resample)
+    ks = _keep_scale(y, mask, p)
+    if ks is not None:
+        gp = gp * ks
+    dt = gp * torch.where(t > 0, torch.ones_like(t), torch.full_like(t, slope))
+    n = y.numel() // c
+    s1 = dt.reshape(-1, c).sum(0)
+    s2 = (dt * xh).reshape(-1, c).sum(0)
+    dconv = gamma * invstd * (dt - s1 / n - xh * (s2 / n))
+    return (dconv.to(y.dtype), dt.to(y.dtype) if need_dres else None,
+            s2 if need_affine else None, s1 if need_affine else None)
+
+
+def _w5(w, flip):  # [C,T] -> conv kernel taps [C,k,k,k]
+    c, t = w.shape
+    k = 3 if t == 27 else 1
+    w = w.flip(1) if flip else w
+    return w.reshape(c, k, k, k), k
+
+
+def c1_to_cn(x1, w, bias, flip=False, out=None):
+    w5, k = _w5(w, flip)
+    y = F.conv3d(x1.float().unsqueeze(1), w5.unsqueeze(1), bias, 1, k // 2)      # [N,C,D,H,W]
+    y = y.permute(0, 2, 3, 4, 1)
+    if out is not None:
+        out.copy_((out.float() + y).to(out.dtype))
+        return out
+    return y.contiguous().to(ACT_DTYPE)
+
+
+def cn_to_c1(x, w, bias, flip=False, act=0, mask=None, p=0.0, seed=0):
+    w5, k = _w5(w, flip)
+    y = F.conv3d(_ncdhw(x), w5.unsqueeze(0), bias, 1, k // 2)[:, 0]             # [N,D,H,W]
+    if act == 1:
+        y = F.relu(y)
+        if mask is not None:
+            y = y * mask.float() * (1.0 / (1.0 - p))
+        elif p > 0.0:
+            raise NotImplementedError("Philox dropout is only checked statistically; pass an explicit mask")
+    return y.contiguous()
+
+
+def wgrad_c1(xc, x1, taps, flip=False):
+    k = 3 if taps == 27 else 1
+    xi = x1.float().unsqueeze(1)                                                   # [N,1,D,H,W]
+    gc = _ncdhw(xc)                                                                # [N,C,D,H,W]
+    c = gc.shape[1]
+    # dw[c,t] = sum_v xc[v,c] * x1[v+delta(t)]  == weight gradient of conv3d(x1 -> C) with output grad xc
+    dw = torch.nn.grad.conv3d_weight(xi, (c, 1, k, k, k), gc, stride=1, padding=k // 2).reshape(c, taps)
+    if flip:
+        dw = dw.flip(1)
+    return dw.contiguous(), gc.sum((0, 2, 3, 4)), x1.float().sum().reshape(1)
+
+
+def relu_drop_bwd(g, out, p):
+    return torch.where(out > 0, g * (1.0 / (1.0 - p)), torch.zeros_like(g))
+
+
+def reparam_fwd(mu, logvar, eps):
+    return mu + eps * torch.exp(0.5 * logvar)
+
+
+def reparam_bwd(dz, logvar, eps):
+    return dz.clone(), dz * eps * torch.exp(0.5 * logvar) * 0.5
+
+
+def kl_persample_fwd(mu, logvar):
+    return -0.5 * torch.sum(1 + logvar - mu * mu - logvar.exp(), dim=1)
+
+
+def kl_persample_bwd(mu, logvar, g):
+    return g[:, None] * mu, g[:, None] * 0.5 * (logvar.exp() - 1.0)
+
+
+def mse_persample_fwd(x, y):
+    return ((x - y) ** 2).sum(1)
+
+
+def mse_persample_bwd(x, y, g, need_dx, need_dy):
+    d = 2.0 * (x - y) * g[:, None]
+    return (d if need_dx else None), (-d if need_dy else None)
+
+
+def to_ndhwc_bf16(x):
+    return _ndhwc(x, ACT_DTYPE)
+
+
+def to_ncdhw_f32(x):
+    return _ncdhw(x).contiguous()
+
+
+ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F",)]

@@ -1,0 +1,335 @@
+"""Autograd wiring of the fused units on top of ``kernels`` (one C-ABI call per line).
+
+Units (all activations NDHWC, one-channel tensors fp32 [N,D,H,W]):
+  conv_bn_act       Conv3d(3, bias=False) -> BatchNorm3d -> (Leaky)ReLU [+res] -> AvgPool/Upsample
+                    (reference: BuildingBlock / UpsampleBuildingkBlock, models/models.py:8-80)
+  stem_bn_act       Conv3d(1, C, k, bias) -> BatchNorm3d -> (Leaky)ReLU -> Dropout
+                    (encoder stem models.py:91-96, k=3; decoder stem :117-123, k=1)
+  tail_relu_drop    Conv3d(C, 1, 3, bias) -> ReLU -> Dropout          (models.py:136-141)
+  heads             mu / var 1x1 Conv3d(C, 1)                          (models.py:216-223)
+  reparameterize, kl_persample, mse_persample                          (models.py:263-271,
+                    utils/my_trainer.py:38-78)
+Backward follows SURVEY.md appendix B; parameter gradients are only computed when the parameter
+requires grad (the trainer freezes encoder / decoder per phase, utils/my_trainer.py:242-245,291-294).
+"""
+from __future__ import annotations
+
+import itertools
+import weakref
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# dropout state: every dropout call gets a fresh 64-bit Philox key; backward reuses the same key
+# ----------------------------------------------------------------------------------------------
+class _DropoutState:
+    def __init__(self):
+        self.base_seed = 0x5EED5EED
+        self.counter = itertools.count(1)
+        self.mask_feed = None  # optional iterator of explicit uint8 NDHWC keep-masks (parity tests)
+
+    def next(self):
+        """-> (mask or None, seed)"""
+        seed = (self.base_seed * 0x9E3779B97F4A7C15 + next(self.counter) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        mask = next(self.mask_feed) if self.mask_feed is not None else None
+        return mask, seed
+
+
+dropout_state = _DropoutState()
+
+
+def manual_seed(seed: int):
+    """Re-key the in-kernel Philox dropout streams (independent of torch's generator)."""
+    dropout_state.base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    dropout_state.counter = itertools.count(1)
+
+
+class BnState:
+    """Non-differentiable BatchNorm state handed to the fused units."""
+
+    __slots__ = ("running_mean", "running_var", "num_batches_tracked", "training", "momentum", "eps")
+
+    def __init__(self, running_mean, running_var, num_batches_tracked, training, momentum=BN_MOMENTUM, eps=BN_EPS):
+        self.running_mean, self.running_var, self.num_batches_tracked = running_mean, running_var, num_batches_tracked
+        self.training, self.momentum, self.eps = training, momentum, eps
+
+
+def _bn_coeffs(y, gamma, beta, bn: BnState):
+    """-> (mean, invstd, scale, shift).  Train: batch statistics (+ running-stat update).  Eval: running stats."""
+    if bn.training:
+        return K.bn_train_coeffs(y, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                 bn.momentum, bn.eps)
+    invstd = torch.rsqrt(bn.running_var + bn.eps)
+    scale = gamma * invstd
+    return bn.running_mean, invstd, scale, beta - bn.running_mean * scale
+
+
+# Weight packs are cached per live tensor object and validated by (storage pointer, version): optimiser
+# steps bump ``_version``; the trainer's per-epoch ``model.to('cpu')`` / ``.to(device)`` round trip
+# re-allocates storage; temporaries (channel-padded weights) die and fail the weakref test.
+_pack_cache = {}
+
+
+def _packed(weight: torch.Tensor):
+    key = id(weight)
+    hit = _pack_cache.get(key)
+    if hit is not None:
+        ref, ptr, ver, packs = hit
+        if ref() is weight and ptr == weight.data_ptr() and ver == weight._version:
+            return packs
+    if len(_pack_cache) > 512:
+        for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
+            del _pack_cache[k]
+    packs = K.pack_conv3_weights(weight.detach().contiguous())
+    _pack_cache[key] = (weakref.ref(weight), weight.data_ptr(), weight._version, packs)
+    return packs
+
+
+class _ConvBnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int):
+        wf, wd = _packed(weight)
+        y = K.conv3_igemm(x, wf)
+        mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
+        out = K.bn_act_fwd(y, scale, shift, res, slope, resample)
+        ctx.save_for_backward(x, y, res, mean, invstd, gamma, beta, wd)
+        ctx.cfg = (slope, resample, bn.training)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, res, mean, invstd, gamma, beta, wd = ctx.saved_tensors
+        slope, resample, training = ctx.cfg
+        if not training:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference hot path")
+        need_x, need_w, need_g, need_b, need_res = ctx.needs_input_grad[:5]
+        dconv, dres, dgamma, dbeta = K.bn_act_bwd(g.contiguous(), y, res, mean, invstd, gamma, beta, slope, resample,
+                                                  need_dres=bool(need_res and res is not None),
+                                                  need_affine=bool(need_g or need_b))
+        dx = K.conv3_igemm(dconv, wd) if need_x else None
+        dw = K.conv3_wgrad(x, dconv) if need_w else None
+        return dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), dres, None, None, None
+
+
+def conv_bn_act(x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int = K.RESAMPLE_NONE):
+    return _ConvBnAct.apply(x, weight, gamma, beta, res, bn, slope, resample)
+
+
+class _StemBnAct(torch.autograd.Function):
+    """x1 fp32 [N,D,H,W] -> NDHWC [N,D,H,W,C]; weight fp32 [C,T] (T = 27 or 1), bias [C]."""
+
+    @staticmethod
+    def forward(ctx, x1, weight, bias, gamma, beta, bn: BnState, slope: float, p: float):
+        y = K.c1_to_cn(x1, weight, bias)
+        mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
+        mask, seed = (None, 0)
+        p_eff = p if bn.training else 0.0
+        if p_eff > 0.0:
+            mask, seed = dropout_state.next()
+        out = K.bn_act_fwd(y, scale, shift, None, slope, K.RESAMPLE_NONE, mask, p_eff, seed)
+        ctx.save_for_backward(x1, y, mean, invstd, gamma, beta, weight, mask)
+        ctx.cfg = (slope, p_eff, seed, bn.training)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, y, mean, invstd, gamma, beta, weight, mask = ctx.saved_tensors
+        slope, p, seed, training = ctx.cfg
+        if not training:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference hot path")
+        need_x, need_w, need_bias, need_g, need_b = ctx.needs_input_grad[:5]
+        dconv, _, dgamma, dbeta = K.bn_act_bwd(g.contiguous(), y, None, mean, invstd, gamma, beta, slope,
+                                               K.RESAMPLE_NONE, mask, p, seed, need_dres=False,
+                                               need_affine=bool(need_g or need_b))
+        dw = dbias = dx = None
+        if need_w or need_bias:
+            dw, dbias, _ = K.wgrad_c1(dconv, x1, weight.shape[1], flip=False)
+        if need_x:
+            dx = K.cn_to_c1(dconv, weight, None, flip=True, act=0)
+        return (dx, dw if need_w else None, dbias if need_bias else None, dgamma if need_g else None,
+                dbeta if need_b else None, None, None, None)
+
+
+def stem_bn_act(x1, weight, bias, gamma, beta, bn: BnState, slope: float, p: float):
+    return _StemBnAct.apply(x1, weight, bias, gamma, beta, bn, slope, p)
+
+
+class _TailReluDrop(torch.autograd.Function):
+    """a NDHWC [N,D,H,W,C] -> fp32 [N,D,H,W]; weight fp32 [C,27], bias [1]."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, p: float, training: bool):
+        mask, seed = (None, 0)
+        p_eff = p if training else 0.0
+        if p_eff > 0.0:
+            mask, seed = dropout_state.next()
+        out = K.cn_to_c1(a, weight, bias, flip=False, act=1, mask=mask, p=p_eff, seed=seed)
+        ctx.save_for_backward(a, weight, out)
+        ctx.p = p_eff
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, weight, out = ctx.saved_tensors
+        need_a, need_w, need_b = ctx.needs_input_grad[:3]
+        dy = K.relu_drop_bwd(g.contiguous(), out, ctx.p)
+        da = K.c1_to_cn(dy, weight, None, flip=True) if need_a else None
+        dw = db = None
+        if need_w or need_b:
+            dw, _, db = K.wgrad_c1(a, dy, weight.shape[1], flip=True)
+        return da, (dw if need_w else None), (db if need_b else None), None, None
+
+
+def tail_relu_drop(a, weight, bias, p: float, training: bool):
+    return _TailReluDrop.apply(a, weight, bias, p, training)
+
+
+class _Heads(torch.autograd.Function):
+    """h NDHWC [N,d,h,w,C] -> (mu, logvar) fp32 [N,d,h,w]; weights fp32 [C,1], biases [1]."""
+
+    @staticmethod
+    def forward(ctx, h, w_mu, b_mu, w_var, b_var):
+        mu = K.cn_to_c1(h, w_mu, b_mu)
+        lv = K.cn_to_c1(h, w_var, b_var)
+        ctx.save_for_backward(h, w_mu, w_var)
+        return mu, lv
+
+    @staticmethod
+    def backward(ctx, dmu, dlv):
+        h, w_mu, w_var = ctx.saved_tensors
+        need_h, need_wm, need_bm, need_wv, need_bv = ctx.needs_input_grad
+        dmu, dlv = dmu.contiguous(), dlv.contiguous()
+        dh = None
+        if need_h:
+            dh = K.c1_to_cn(dmu, w_mu, None)
+            dh = K.c1_to_cn(dlv, w_var, None, out=dh)
+        dwm = dbm = dwv = dbv = None
+        if need_wm or need_bm:
+            dwm, _, dbm = K.wgrad_c1(h, dmu, 1)
+        if need_wv or need_bv:
+            dwv, _, dbv = K.wgrad_c1(h, dlv, 1)
+        return (dh, dwm if need_wm else None, dbm if need_bm else None, dwv if need_wv else None,
+                dbv if need_bv else None)
+
+
+def heads(h, w_mu, b_mu, w_var, b_var):
+    return _Heads.apply(h, w_mu, b_mu, w_var, b_var)
+
+
+class _Reparam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar = mu.contiguous(), logvar.contiguous()
+        z = K.reparam_fwd(mu, logvar, eps)
+        if isinstance(eps, torch.Tensor):
+            ctx.save_for_backward(logvar, eps)
+            ctx.eps_const = None
+        else:
+            ctx.save_for_backward(logvar)
+            ctx.eps_const = float(eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        if ctx.eps_const is None:
+            logvar, eps = ctx.saved_tensors
+        else:
+            (logvar,) = ctx.saved_tensors
+            eps = ctx.eps_const
+        dmu, dlv = K.reparam_bwd(dz.contiguous(), logvar, eps)
+        return dmu, dlv, None
+
+
+def reparameterize(mu, logvar, eps):
+    """z = mu + eps*exp(0.5*logvar); eps is a tensor (train) or a python float (validation, 0.1)."""
+    return _Reparam.apply(mu, logvar, eps)
+
+
+class _KlPerSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        ctx.shape = mu.shape
+        mu2, lv2 = mu.reshape(mu.shape[0], -1).contiguous(), logvar.reshape(mu.shape[0], -1).contiguous()
+        ctx.save_for_backward(mu2, lv2)
+        return K.kl_persample_fwd(mu2, lv2)
+
+    @staticmethod
+    def backward(ctx, g):
+        mu2, lv2 = ctx.saved_tensors
+        dmu, dlv = K.kl_persample_bwd(mu2, lv2, g.contiguous())
+        return dmu.reshape(ctx.shape), dlv.reshape(ctx.shape)
+
+
+def kl_persample(mu, logvar):
+    """[B] vector  -0.5*sum(1 + logvar - mu^2 - exp(logvar))."""
+    return _KlPerSample.apply(mu, logvar)
+
+
+class _MsePerSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.shape = x.shape
+        x2, y2 = x.reshape(x.shape[0], -1).contiguous(), y.reshape(y.shape[0], -1).contiguous()
+        ctx.save_for_backward(x2, y2)
+        return K.mse_persample_fwd(x2, y2)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, y2 = ctx.saved_tensors
+        need_x, need_y = ctx.needs_input_grad
+        dx, dy = K.mse_persample_bwd(x2, y2, g.contiguous(), bool(need_x), bool(need_y))
+        return (dx.reshape(ctx.shape) if need_x else None), (dy.reshape(ctx.shape) if need_y else None)
+
+
+def mse_persample(x, y):
+    """[B] vector  sum_voxels (x - y)^2; gradients flow to both operands when both need them."""
+    return _MsePerSample.apply(x, y)
+
+
+class _Head1(torch.autograd.Function):
+    """Single 1x1 head (ResNetEncoder.conv, models/models.py:105-108): NDHWC -> fp32 [N,d,h,w]."""
+
+    @staticmethod
+    def forward(ctx, h, w, b):
+        ctx.save_for_backward(h, w)
+        return K.cn_to_c1(h, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w = ctx.saved_tensors
+        need_h, need_w, need_b = ctx.needs_input_grad
+        dy = dy.contiguous()
+        dh = K.c1_to_cn(dy, w, None) if need_h else None
+        dw = db = None
+        if need_w or need_b:
+            dw, _, db = K.wgrad_c1(h, dy, 1)
+        return dh, (dw if need_w else None), (db if need_b else None)
+
+
+def head1(h, w, b):
+    return _Head1.apply(h, w, b)
+
+
+# ----------------------------------------------------------------------------------------------
+# reparameterisation noise: torch's generator by default (randn_like, as the reference), or an
+# injected sequence of eps tensors for parity tests
+# ----------------------------------------------------------------------------------------------
+class _NoiseState:
+    def __init__(self):
+        self.eps_feed = None
+
+
+noise_state = _NoiseState()
+
+
+def draw_eps(like: torch.Tensor) -> torch.Tensor:
+    if noise_state.eps_feed is not None:
+        return next(noise_state.eps_feed).to(like.device, like.dtype).reshape(like.shape)
+    return torch.randn_like(like)

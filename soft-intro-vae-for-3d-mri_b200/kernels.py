@@ -1,0 +1,380 @@
+"""Tensor-level bindings of libsivae.so (the C ABI declared in include/sivae.h).
+
+Every function here is one call into the shared library (one or a few kernel launches on the
+current torch CUDA stream).  There is NO fallback: if the library is missing, fails to load,
+or a tensor is not on a CUDA device, the call raises.  torch is used only for device memory
+(``torch.empty``) and the stream handle.
+
+Layout conventions: activations are NDHWC bf16 tensors of shape [N, D, H, W, C]; one-channel model
+inputs / outputs / latents are fp32 [N, D, H, W].
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsivae.so")
+
+RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_UPSAMPLE2 = 0, 1, 2
+
+_lib = None
+_vp, _i, _ll, _f, _sz, _u64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                               ctypes.c_size_t, ctypes.c_ulonglong)
+
+# name -> (restype, argtypes); mirrors include/sivae.h one to one
+_SIGNATURES = {
+    "sivae_last_error": (ctypes.c_char_p, []),
+    "sivae_abi_version": (_i, []),
+    "sivae_device_check": (_i, []),
+    "sivae_launch_count": (_ll, []),
+    "sivae_pack_conv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "sivae_conv3_igemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_conv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "sivae_conv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_bn_workspace_bytes": (_sz, [_i]),
+    "sivae_bn_train_coeffs": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sivae_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _f, _u64, _vp]),
+    "sivae_bn_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i,
+                              _vp, _f, _u64, _vp, _sz, _vp]),
+    "sivae_c1_to_cn": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_cn_to_c1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp]),
+    "sivae_wgrad_c1_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "sivae_wgrad_c1": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sivae_relu_drop_bwd": (_i, [_vp, _vp, _vp, _ll, _f, _vp]),
+    "sivae_reparam_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _ll, _vp]),
+    "sivae_reparam_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
+    "sivae_kl_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
+    "sivae_kl_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
+    "sivae_mse_workspace_bytes": (_sz, [_i, _ll]),
+    "sivae_mse_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _sz, _vp]),
+    "sivae_mse_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
+    "sivae_ncdhw_f32_to_ndhwc_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
+    "sivae_ndhwc_bf16_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class SivaeError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libsivae.so and declare the prototypes.  Raises SivaeError when it is absent
+    (build it with ``python __graft_entry__.py`` or ``make -C .../csrc``)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise SivaeError(f"{p} not found: the CUDA extension is not built (run `python __graft_entry__.py`); "
+                         "there is no CPU or PyTorch fallback for the hot path")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sivae_abi_version() != 1:
+        raise SivaeError("libsivae.so ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _L():
+    return _lib if _lib is not None else load_library()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise SivaeError(f"{what} failed ({rc}): {_L().sivae_last_error().decode()}")
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise SivaeError(f"{name}: expected a CUDA tensor (no CPU fallback exists for the hot path)")
+    if t.dtype != dtype:
+        raise SivaeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise SivaeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def launch_count() -> int:
+    return int(_L().sivae_launch_count())
+
+
+def device_check():
+    _check(_L().sivae_device_check(), "sivae_device_check")
+
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
+    """Per-(device, stream, tag) scratch buffer, grown on demand (caller-owned workspace of the C ABI)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------------------------
+# 3x3x3 convolutions on tcgen05
+# ----------------------------------------------------------------------------------------------
+def pack_conv3_weights(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [Co,Ci,3,3,3] -> (wf bf16 [27,Co,Ci], wd bf16 [27,Ci,Co] flipped+transposed)."""
+    _req(w, torch.float32, "weight")
+    co, ci = w.shape[0], w.shape[1]
+    wf = torch.empty(27, co, ci, dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty(27, ci, co, dtype=torch.bfloat16, device=w.device)
+    _check(_L().sivae_pack_conv3_weights(_p(w), co, ci, _p(wf), _p(wd), _stream(w)), "sivae_pack_conv3_weights")
+    return wf, wd
+
+
+def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
+    """y[n,d,h,w,co] = sum_{tap,ci} x[n,d+kd-1,h+kh-1,w+kw-1,ci] * wpack[tap,co,ci]."""
+    _req(x, torch.bfloat16, "x")
+    _req(wpack, torch.bfloat16, "wpack")
+    n, d, h, w, ci = x.shape
+    co = wpack.shape[1]
+    assert wpack.shape == (27, co, ci), (wpack.shape, ci)
+    y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
+    _check(_L().sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)), "sivae_conv3_igemm")
+    return y
+
+
+def conv3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dw[co,ci,kd,kh,kw] = sum_v dy[v,co] * x[v+tap,ci]   (fp32, torch weight layout)."""
+    _req(x, torch.bfloat16, "x")
+    _req(dy, torch.bfloat16, "dy")
+    n, d, h, w, ci = x.shape
+    co = dy.shape[-1]
+    assert dy.shape[:4] == x.shape[:4]
+    lib = _L()
+    nbytes = lib.sivae_conv3_wgrad_workspace_bytes(n, d, h, w, ci, co)
+    ws = _workspace(x.device, nbytes, "wgrad")
+    dw = torch.empty(co, ci, 3, 3, 3, dtype=torch.float32, device=x.device)
+    _check(lib.sivae_conv3_wgrad(_p(x), _p(dy), _p(dw), _p(ws), ws.numel(), n, d, h, w, ci, co, _stream(x)),
+           "sivae_conv3_wgrad")
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------
+# BatchNorm (train) + activation + residual + resample + dropout
+# ----------------------------------------------------------------------------------------------
+def bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float, eps: float):
+    """-> (mean, invstd, scale, shift), each fp32 [C]; running stats are updated in place."""
+    _req(y, torch.bfloat16, "y")
+    c = y.shape[-1]
+    nvox = y.numel() // c
+    lib = _L()
+    ws = _workspace(y.device, lib.sivae_bn_workspace_bytes(c), "bn")
+    coef = torch.empty(4, c, dtype=torch.float32, device=y.device)
+    if num_batches_tracked is not None:
+        _req(num_batches_tracked, torch.int64, "num_batches_tracked")
+    _check(lib.sivae_bn_train_coeffs(_p(y), nvox, c, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                     _p(num_batches_tracked), momentum, eps, _p(coef[0]), _p(coef[1]), _p(coef[2]),
+                                     _p(coef[3]), _p(ws), ws.numel(), _stream(y)), "sivae_bn_train_coeffs")
+    return coef[0], coef[1], coef[2], coef[3]
+
+
+def _resampled_shape(shape, resample):
+    n, d, h, w, c = shape
+    if resample == RESAMPLE_AVGPOOL2:
+        return (n, d // 2, h // 2, w // 2, c)
+    if resample == RESAMPLE_UPSAMPLE2:
+        return (n, 2 * d, 2 * h, 2 * w, c)
+    return (n, d, h, w, c)
+
+
+def bn_act_fwd(y, scale, shift, res, slope: float, resample: int, mask=None, p: float = 0.0, seed: int = 0):
+    """out = resample(dropout(act(y*scale+shift (+res))))."""
+    _req(y, torch.bfloat16, "y")
+    n, d, h, w, c = y.shape
+    if res is not None:
+        _req(res, torch.bfloat16, "res")
+        assert res.shape == y.shape
+    if mask is not None:
+        _req(mask, torch.uint8, "mask")
+        assert mask.shape == y.shape
+    out = torch.empty(_resampled_shape(y.shape, resample), dtype=torch.bfloat16, device=y.device)
+    _check(_L().sivae_bn_act_fwd(_p(y), _p(scale), _p(shift), _p(res), _p(out), n, d, h, w, c, slope, resample,
+                                 _p(mask), p, seed, _stream(y)), "sivae_bn_act_fwd")
+    return out
+
+
+def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int, mask=None, p: float = 0.0,
+               seed: int = 0, need_dres: bool = False, need_affine: bool = True):
+    """-> (dconv bf16 like y, dres bf16 or None, dgamma fp32 [C] or None, dbeta fp32 [C] or None)."""
+    _req(g, torch.bfloat16, "g")
+    _req(y, torch.bfloat16, "y")
+    n, d, h, w, c = y.shape
+    assert tuple(g.shape) == _resampled_shape(y.shape, resample), (g.shape, y.shape, resample)
+    lib = _L()
+    ws = _workspace(y.device, lib.sivae_bn_workspace_bytes(c), "bn")
+    dconv = torch.empty_like(y)
+    dres = torch.empty_like(y) if need_dres else None
+    aff = torch.empty(2, c, dtype=torch.float32, device=y.device) if need_affine else None
+    _check(lib.sivae_bn_act_bwd(_p(g), _p(y), _p(res), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dconv), _p(dres),
+                                _p(aff[0]) if need_affine else None, _p(aff[1]) if need_affine else None,
+                                n, d, h, w, c, slope, resample, _p(mask), p, seed, _p(ws), ws.numel(), _stream(y)),
+           "sivae_bn_act_bwd")
+    return dconv, dres, (aff[0] if need_affine else None), (aff[1] if need_affine else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# thin convolutions (one channel on one side)
+# ----------------------------------------------------------------------------------------------
+def c1_to_cn(x1, w, bias, flip: bool = False, out: Optional[torch.Tensor] = None):
+    """y[v,c] (+)= bias[c] + sum_t w[c,t]*x1[v+delta(t)].  x1 fp32 [N,D,H,W]; w fp32 [C,T]; out given => accumulate."""
+    _req(x1, torch.float32, "x1")
+    _req(w, torch.float32, "w")
+    n, d, h, ww = x1.shape
+    c, t = w.shape
+    acc = out is not None
+    if out is None:
+        out = torch.empty(n, d, h, ww, c, dtype=torch.bfloat16, device=x1.device)
+    else:
+        _req(out, torch.bfloat16, "out")
+    _check(_L().sivae_c1_to_cn(_p(x1), _p(w), _p(bias), _p(out), n, d, h, ww, c, t, int(flip), int(acc), _stream(x1)),
+           "sivae_c1_to_cn")
+    return out
+
+
+def cn_to_c1(x, w, bias, flip: bool = False, act: int = 0, mask=None, p: float = 0.0, seed: int = 0):
+    """y[v] = act(bias + sum_{t,c} w[c,t]*x[v+delta(t),c]).  x bf16 NDHWC; w fp32 [C,T]; y fp32 [N,D,H,W]."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.float32, "w")
+    n, d, h, ww, c = x.shape
+    assert w.shape[0] == c
+    if mask is not None:
+        _req(mask, torch.uint8, "mask")
+    y = torch.empty(n, d, h, ww, dtype=torch.float32, device=x.device)
+    _check(_L().sivae_cn_to_c1(_p(x), _p(w), _p(bias), _p(y), n, d, h, ww, c, w.shape[1], int(flip), act, _p(mask), p,
+                               seed, _stream(x)), "sivae_cn_to_c1")
+    return y
+
+
+def wgrad_c1(xc, x1, taps: int, flip: bool = False):
+    """-> (dw fp32 [C,T], sum_c fp32 [C] = sum_v xc[v,c], sum_1 fp32 [1] = sum_v x1[v])."""
+    _req(xc, torch.bfloat16, "xc")
+    _req(x1, torch.float32, "x1")
+    n, d, h, ww, c = xc.shape
+    lib = _L()
+    ws = _workspace(xc.device, lib.sivae_wgrad_c1_workspace_bytes(n, d, h, ww, c, taps), "wgrad_c1")
+    dw = torch.empty(c, taps, dtype=torch.float32, device=xc.device)
+    sum_c = torch.empty(c, dtype=torch.float32, device=xc.device)
+    sum_1 = torch.empty(1, dtype=torch.float32, device=xc.device)
+    _check(lib.sivae_wgrad_c1(_p(xc), _p(x1), _p(dw), _p(sum_c), _p(sum_1), n, d, h, ww, c, taps, int(flip), _p(ws),
+                              ws.numel(), _stream(xc)), "sivae_wgrad_c1")
+    return dw, sum_c, sum_1
+
+
+def relu_drop_bwd(g, out, p: float):
+    _req(g, torch.float32, "g")
+    _req(out, torch.float32, "out")
+    dy = torch.empty_like(out)
+    _check(_L().sivae_relu_drop_bwd(_p(g), _p(out), _p(dy), out.numel(), p, _stream(out)), "sivae_relu_drop_bwd")
+    return dy
+
+
+# ----------------------------------------------------------------------------------------------
+# latent / loss
+# ----------------------------------------------------------------------------------------------
+def reparam_fwd(mu, logvar, eps):
+    """eps: fp32 tensor like mu, or a python float (validation: 0.1)."""
+    _req(mu, torch.float32, "mu")
+    _req(logvar, torch.float32, "logvar")
+    z = torch.empty_like(mu)
+    et = eps if isinstance(eps, torch.Tensor) else None
+    if et is not None:
+        _req(et, torch.float32, "eps")
+    _check(_L().sivae_reparam_fwd(_p(mu), _p(logvar), _p(et), 0.0 if et is not None else float(eps), _p(z),
+                                  mu.numel(), _stream(mu)), "sivae_reparam_fwd")
+    return z
+
+
+def reparam_bwd(dz, logvar, eps):
+    _req(dz, torch.float32, "dz")
+    dmu, dlv = torch.empty_like(dz), torch.empty_like(dz)
+    et = eps if isinstance(eps, torch.Tensor) else None
+    _check(_L().sivae_reparam_bwd(_p(dz), _p(logvar), _p(et), 0.0 if et is not None else float(eps), _p(dmu), _p(dlv),
+                                  dz.numel(), 0, _stream(dz)), "sivae_reparam_bwd")
+    return dmu, dlv
+
+
+def kl_persample_fwd(mu, logvar):
+    """mu, logvar: fp32 [B, n] -> kl fp32 [B]."""
+    _req(mu, torch.float32, "mu")
+    _req(logvar, torch.float32, "logvar")
+    b, n = mu.shape
+    kl = torch.empty(b, dtype=torch.float32, device=mu.device)
+    _check(_L().sivae_kl_persample_fwd(_p(mu), _p(logvar), _p(kl), b, n, _stream(mu)), "sivae_kl_persample_fwd")
+    return kl
+
+
+def kl_persample_bwd(mu, logvar, g):
+    _req(g, torch.float32, "g")
+    b, n = mu.shape
+    dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+    _check(_L().sivae_kl_persample_bwd(_p(mu), _p(logvar), _p(g), _p(dmu), _p(dlv), b, n, 0, _stream(mu)),
+           "sivae_kl_persample_bwd")
+    return dmu, dlv
+
+
+def mse_persample_fwd(x, y):
+    """x, y: fp32 [B, n] -> r fp32 [B], r[b] = sum_j (x-y)^2."""
+    _req(x, torch.float32, "x")
+    _req(y, torch.float32, "y")
+    b, n = x.shape
+    lib = _L()
+    ws = _workspace(x.device, lib.sivae_mse_workspace_bytes(b, n), "mse")
+    r = torch.empty(b, dtype=torch.float32, device=x.device)
+    _check(lib.sivae_mse_persample_fwd(_p(x), _p(y), _p(r), b, n, _p(ws), ws.numel(), _stream(x)),
+           "sivae_mse_persample_fwd")
+    return r
+
+
+def mse_persample_bwd(x, y, g, need_dx: bool, need_dy: bool):
+    _req(g, torch.float32, "g")
+    b, n = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dy = torch.empty_like(y) if need_dy else None
+    _check(_L().sivae_mse_persample_bwd(_p(x), _p(y), _p(g), _p(dx), _p(dy), b, n, _stream(x)),
+           "sivae_mse_persample_bwd")
+    return dx, dy
+
+
+# ----------------------------------------------------------------------------------------------
+# layout helpers
+# ----------------------------------------------------------------------------------------------
+def to_ndhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCDHW [N,C,D,H,W] -> bf16 NDHWC [N,D,H,W,C]."""
+    _req(x, torch.float32, "x")
+    n, c, d, h, w = x.shape
+    out = torch.empty(n, d, h, w, c, dtype=torch.bfloat16, device=x.device)
+    _check(_L().sivae_ncdhw_f32_to_ndhwc_bf16(_p(x), _p(out), n, c, d * h * w, _stream(x)), "sivae_ncdhw_f32_to_ndhwc_bf16")
+    return out
+
+
+def to_ncdhw_f32(x: torch.Tensor) -> torch.Tensor:
+    """bf16 NDHWC [N,D,H,W,C] -> fp32 NCDHW [N,C,D,H,W]."""
+    _req(x, torch.bfloat16, "x")
+    n, d, h, w, c = x.shape
+    out = torch.empty(n, c, d, h, w, dtype=torch.float32, device=x.device)
+    _check(_L().sivae_ndhwc_bf16_to_ncdhw_f32(_p(x), _p(out), n, c, d * h * w, _stream(x)), "sivae_ndhwc_bf16_to_ncdhw_f32")
+    return out

@@ -1,0 +1,167 @@
+"""One-process-per-GPU data parallelism replacing ``nn.DataParallel`` (main_DataParallel.py:609).
+
+The training step shards by volumes only: every rank runs the whole network on
+its local batch with *local* BatchNorm statistics (exactly what DataParallel replicas do), and the
+only exchange is the gradient average -- encoder gradients after ``lossE.backward()``, decoder
+gradients after ``lossD.backward()``.  ``GradReducer`` does that with bucketed, asynchronous
+all-reduces launched from ``register_post_accumulate_grad_hook`` while backward is still producing
+the remaining (earlier-layer) gradients, so NCCL traffic over NVLink overlaps the wgrad kernels.
+
+Stock ``DistributedDataParallel`` does not fit this loop: 13 forwards precede 2 backwards, the
+trainable half flips every phase, and some parameters never receive a gradient.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: Optional[str] = None) -> tuple:
+    """Initialise torch.distributed from the torchrun environment.  -> (rank, world_size, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+class _Bucket:
+    __slots__ = ("params", "offsets", "flat", "pending", "work", "launched")
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        self.offsets = []
+        n = 0
+        for p in params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.flat = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        self.pending = set()
+        self.work = None
+        self.launched = False
+
+
+class GradReducer:
+    """Bucketed gradient averaging for one parameter group (encoder or decoder).
+
+    Parameters are bucketed in *reverse* registration order (the order backward produces their
+    gradients), ~``bucket_mb`` MiB of fp32 per bucket.  A bucket's all-reduce is launched
+    asynchronously as soon as its last expected gradient has been accumulated; parameters that do not
+    get a gradient in a given backward (unused projection convs) are learned on the
+    first ``finish()`` and excluded from then on.  ``finish()`` launches whatever is left, waits,
+    and writes the averaged values back into ``param.grad``.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 8.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params]
+        self._index = {}
+        self.buckets: List[_Bucket] = []
+        self._expected = None  # set of params that actually receive gradients (learned on first finish)
+        self._hooks = []
+        cap = int(bucket_mb * (1 << 20) / 4)
+        cur, cur_n = [], 0
+        for p in reversed(self.params):
+            if cur and cur_n + p.numel() > cap:
+                self._add_bucket(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self._add_bucket(cur)
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._arm()
+
+    def _add_bucket(self, params):
+        b = _Bucket(list(params))
+        for p in params:
+            self._index[p] = b
+        self.buckets.append(b)
+
+    def _arm(self):
+        for b in self.buckets:
+            exp = [p for p in b.params if self._expected is None or p in self._expected]
+            b.pending = set(exp)
+            b.work = None
+            b.launched = False
+
+    def _launch(self, b: _Bucket):
+        if b.launched:
+            return
+        b.launched = True
+        any_grad = False
+        for p, off in zip(b.params, b.offsets):
+            dst = b.flat[off: off + p.numel()]
+            if p.grad is not None:
+                dst.copy_(p.grad.reshape(-1))
+                any_grad = True
+            else:
+                dst.zero_()
+        if self.world > 1 and (any_grad or self._expected is None):
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p):
+        if self.world == 1:
+            return
+        b = self._index[p]
+        if p in b.pending:
+            b.pending.discard(p)
+            if not b.pending and self._expected is not None:
+                self._launch(b)
+
+    def finish(self):
+        """Call between ``loss.backward()`` and ``optimizer.step()``."""
+        if self.world == 1:
+            return
+        if self._expected is None:
+            self._expected = {p for p in self.params if p.grad is not None}
+        for b in self.buckets:
+            self._launch(b)
+        inv = 1.0 / self.world
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+            for p, off in zip(b.params, b.offsets):
+                if p.grad is not None:
+                    p.grad.copy_(b.flat[off: off + p.numel()].reshape(p.grad.shape) * inv)
+        self._arm()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
+    """Make parameters and buffers identical on every rank (DataParallel keeps replica 0's)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
+
+
+def all_reduce_mean_scalars(values: dict, group=None) -> dict:
+    """Average a dict of scalar tensors across ranks with a single collective (logging only)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return values
+    keys = sorted(values)
+    flat = torch.stack([values[k].detach().float().reshape(()) for k in keys])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    return {k: flat[i] for i, k in enumerate(keys)}

