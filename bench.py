@@ -1,0 +1,285 @@
+"""bench.py -- headline benchmark of the hot path: Soft-IntroVAE z=1200 training volumes/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libsivae.so on B200)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the reference's CPU path
+
+Workload (BASELINE.json configs[2], z-1200main.py:158,190-202): ``SoftIntroVAE(64, [[64,1,2],[128,1,2],[256,2,2]])``,
+synthetic volumes 1x80x96x80 in [0,1], local batch 8 per GPU, one "step" = one full E-update + D-update of
+utils/my_trainer.py:236-325 (13 forward passes, 2 backward passes, 2 Adam steps), random-init weights
+(init_weights_he under seed 77).  N>1: one process per GPU (torchrun), local batch fixed (weak scaling),
+bucketed NCCL gradient all-reduce overlapped with backward, replica-local BatchNorm statistics.
+
+One JSON line on stdout (rank 0).  ``value`` = volumes/s with inputs resident in HBM; ``e2e`` = the same
+through the public API with pinned-host inputs copied in and the loss scalars read back every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+BLOCK_SETTING = [[64, 1, 2], [128, 1, 2], [256, 2, 2]]
+IN_CH = 64
+VOL = (80, 96, 80)
+LOCAL_BATCH = 8
+GFLOP_PER_VOLUME_STEP = 7270.4       # 32 network passes x 227.2 GFLOP (SURVEY.md section 8d / BASELINE.md section 2)
+METRIC = "train volumes/sec (Soft-IntroVAE z=1200, 80x96x80)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("bf16_tflops_sustained", 1376.2)), float(d.get("hbm_gbs", 6546.9)), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU path (torch fp32, oneDNN) via the oracle port
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(vol=VOL, batch=1, threads=None):
+    """One full Soft-IntroVAE E+D iteration of the headline net on the host cores (fp32, gradients for both
+    phases; the Adam update itself is negligible).  /root/reference does not exist on the GPU box, so this is
+    the oracle port (oracle/sivae_oracle.py, validated against the reference in tests/)."""
+    from oracle import sivae_oracle as O
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    torch.manual_seed(77)
+    cfg = O.NetCfg.soft_intro(IN_CH, BLOCK_SETTING)
+    import sivae_b200
+    net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)          # parameter holder only (never run on CPU)
+    net.apply(sivae_b200.init_weights_he)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+    def step(v=vol):
+        d, h, w = v
+        real = torch.rand(batch, 1, d, h, w)
+        noise = torch.randn(batch, 1, d // 8, h // 8, w // 8)
+        eps = [torch.randn(batch, 1, d // 8, h // 8, w // 8) for _ in range(5)]
+        O.soft_intro_step_grads(sd, cfg, real, noise, eps, None, O.StepHyper())
+    return step
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    step = cpu_reference_step_factory(threads=threads)
+    for _ in range(args.warmup):
+        step((16, 24, 16))            # warm-up on a reduced volume keeps the run bounded
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.steps * 1 / dt
+    sample = (f"{args.steps} x (1 volume 80x96x80, one full E+D iteration, headline net, fp32 torch-CPU/oneDNN, "
+              f"{threads} threads); warm-up on 16x24x16")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "volumes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "z-1200main.py Soft-IntroVAE z=1200, 80x96x80, one E+D train step",
+                       "local_batch": 1, "device": "host CPU"},
+            "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import sivae_b200
+    from sivae_b200 import kernels as K, trainer as T, parallel as P, functional as F
+
+    rank, world, local_rank = P.init_distributed("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    K.device_check()
+    B = args.batch
+    D, H, W = VOL
+    torch.manual_seed(77)                                   # identical init on every rank
+    net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
+    net.apply(T.init_weights_he)
+    net.to(dev).train()
+    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4)
+    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4)
+    red_e = P.GradReducer(net.encoder.parameters()) if world > 1 else None
+    red_d = P.GradReducer(net.decoder.parameters()) if world > 1 else None
+    hp = T.StepHyper()
+    torch.manual_seed(1234 + rank)                          # disjoint synthetic shards / noise per rank
+    F.manual_seed(1234 + rank)
+    real_host = torch.rand(B, 1, D, H, W).pin_memory()
+    noise_host = torch.randn(B, 1, D // 8, H // 8, W // 8).pin_memory()
+    real_dev, noise_dev = real_host.to(dev), noise_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return T.soft_intro_train_step(net, real_dev, noise_dev, opt_e, opt_d, hp, red_e, red_d)
+
+    def step_e2e():
+        real = real_host.to(dev, non_blocking=True)
+        noise = noise_host.to(dev, non_blocking=True)
+        terms = T.soft_intro_train_step(net, real, noise, opt_e, opt_d, hp, red_e, red_d)
+        res = torch.stack([terms["lossE"], terms["lossD"]]).cpu()      # device->host read of the step's result
+        return res
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, out
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = K.launch_count()
+    with K.KernelTimer() as kt:
+        ms, terms = timed(step_resident, args.steps)
+    launches = K.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ksum = kt.summary()
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, res = timed(step_e2e, args.steps)
+    lossE, lossD = float(terms["lossE"]), float(terms["lossD"])
+    if not (lossE == lossE and lossD == lossD):
+        raise SystemExit("NaN loss in the benchmark step")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    vols = world * B * args.steps
+    value = vols / (ms / 1e3)
+    e2e = vols / (ms_e2e / 1e3)
+    peak_tf, peak_gbs, peak_src = _peaks()
+    dom = ksum.get("conv3_igemm", dict(launches=0, ms=0.0, work=0.0, by_shape={}))
+    achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
+    top_shape = max(dom["by_shape"].items(), key=lambda kv: kv[1]["ms"]) if dom["by_shape"] else None
+    wg = ksum.get("conv3_wgrad", dict(launches=0, ms=0.0, work=0.0))
+    roofline = {"bound": "tensor", "kernel": "conv3_igemm_kernel (tcgen05 implicit-GEMM fprop/dgrad)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                "launches": dom["launches"], "share_of_step": dom["ms"] / ms if ms else None,
+                "top_shape": ({"NDHWCiCo": list(top_shape[0]),
+                               "tflops": top_shape[1]["work"] / (top_shape[1]["ms"] * 1e-3) / 1e12,
+                               "ms_per_launch": top_shape[1]["ms"] / top_shape[1]["launches"]} if top_shape else None),
+                "wgrad": {"tflops": wg["work"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] else 0.0,
+                          "share_of_step": wg["ms"] / ms if ms else None, "launches": wg["launches"]},
+                "whole_step_tflops": value / world * GFLOP_PER_VOLUME_STEP / 1e3}
+    line = {"metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "z-1200main.py Soft-IntroVAE(64,[[64,1,2],[128,1,2],[256,2,2]]) z=1200, 80x96x80, "
+                                   "one E+D train step incl. 2 Adam steps",
+                       "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
+                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP},
+            "clocks": clocks, "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / args.steps,
+                                      "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
+                                      "d2h_bytes_per_step": int(res.numel() * 4)},
+            "gpu_launches": int(launches), "roofline": roofline, "loss": {"lossE": lossE, "lossD": lossD}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_reference_step_factory(threads=threads)
+        step((16, 24, 16))
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                "sample": "1 volume 80x96x80, one full E+D iteration of the headline net, fp32 "
+                                          f"torch-CPU/oneDNN on {threads} threads ({dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=LOCAL_BATCH, help="local batch per GPU (headline: 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

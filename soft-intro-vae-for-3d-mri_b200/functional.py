@@ -99,7 +99,8 @@ class _ConvBnAct(torch.autograd.Function):
         y = K.conv3_igemm(x, wf)
         mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
         out = K.bn_act_fwd(y, scale, shift, res, slope, resample)
-        ctx.save_for_backward(x, y, res, mean, invstd, gamma, beta, wd)
+        # x is only needed for the weight gradient: frozen-parameter passes (dgrad-only) do not keep it
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
         ctx.cfg = (slope, resample, bn.training)
         return out
 

@@ -119,6 +119,51 @@ def device_check():
     _check(_L().sivae_device_check(), "sivae_device_check")
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual C-ABI calls on their launch stream (used by bench.py to
+    report the dominant kernel's achieved FLOP/s inside the timed region).  Inactive unless entered."""
+
+    active = None
+
+    def __init__(self, names=("conv3_igemm", "conv3_wgrad")):
+        self.names = set(names)
+        self.records = []   # (name, work, start_event, end_event)
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *a):
+        KernelTimer.active = None
+
+    def summary(self):
+        """-> {name: dict(launches, ms, work)}; call after torch.cuda.synchronize()."""
+        out = {}
+        for name, work, e0, e1 in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, work=0.0, by_shape={}))
+            ms = e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["ms"] += ms
+            d["work"] += work[0]
+            s = d["by_shape"].setdefault(work[1], dict(launches=0, ms=0.0, work=0.0))
+            s["launches"] += 1
+            s["ms"] += ms
+            s["work"] += work[0]
+        return out
+
+
+def _timed(name, work, fn):
+    t = KernelTimer.active
+    if t is None or name not in t.names:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    t.records.append((name, work, e0, e1))
+    return r
+
+
 _ws_cache = {}
 
 
@@ -153,7 +198,10 @@ def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
     co = wpack.shape[1]
     assert wpack.shape == (27, co, ci), (wpack.shape, ci)
     y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
-    _check(_L().sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)), "sivae_conv3_igemm")
+    flops = 2.0 * 27 * ci * co * n * d * h * w
+    _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(_L().sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
+                          "sivae_conv3_igemm"))
     return y
 
 
@@ -168,8 +216,10 @@ def conv3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     nbytes = lib.sivae_conv3_wgrad_workspace_bytes(n, d, h, w, ci, co)
     ws = _workspace(x.device, nbytes, "wgrad")
     dw = torch.empty(co, ci, 3, 3, 3, dtype=torch.float32, device=x.device)
-    _check(lib.sivae_conv3_wgrad(_p(x), _p(dy), _p(dw), _p(ws), ws.numel(), n, d, h, w, ci, co, _stream(x)),
-           "sivae_conv3_wgrad")
+    flops = 2.0 * 27 * ci * co * n * d * h * w
+    _timed("conv3_wgrad", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(lib.sivae_conv3_wgrad(_p(x), _p(dy), _p(dw), _p(ws), ws.numel(), n, d, h, w, ci, co,
+                                                _stream(x)), "sivae_conv3_wgrad"))
     return dw
 
 

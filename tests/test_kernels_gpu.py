@@ -1,0 +1,211 @@
+"""Per-kernel parity (GPU): every function of the C ABI, called through ``sivae_b200.kernels``, against
+its executable specification ``oracle/kernel_spec.py`` evaluated by torch on the same device in fp32
+(TF32 off).  Tolerances: bf16 outputs -> 2^-8 relative rounding + accumulation slack; fp32 outputs ->
+1e-5 relative (stated per test)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import sivae_b200  # noqa: E402
+from sivae_b200 import kernels as K  # noqa: E402
+from oracle import kernel_spec as S  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    K.device_check()
+    torch.manual_seed(1234)
+    yield
+    torch.cuda.synchronize()
+
+
+DEV = "cuda"
+
+
+def bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).to(torch.bfloat16)
+
+
+def assert_bf16_close(got, ref, what, rel=2 ** -7, slack=None):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), what
+    tol = rel * ref.abs() + (slack if slack is not None else rel * float(ref.abs().mean()) + 1e-6)
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} off, max err {float((got - ref).abs().max()):.4e}"
+
+
+def assert_f32_close(got, ref, what, rtol=1e-4):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = float(ref.abs().max()) + 1e-30
+    err = float((got - ref).abs().max())
+    assert err <= rtol * scale, f"{what}: max err {err:.4e} vs scale {scale:.4e}"
+
+
+# ------------------------------------------------------------------------------------------- pointwise
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_bn_train_coeffs(C):
+    y = bf(2, 6, 8, 10, C, scale=2.0) + 0.5
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV)
+    rm, rv = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.5
+    nbt = torch.tensor(3, device=DEV)
+    rm2, rv2, nbt2 = rm.clone(), rv.clone(), nbt.clone()
+    got = K.bn_train_coeffs(y, gamma, beta, rm, rv, nbt, 0.1, 1e-5)
+    ref = S.bn_train_coeffs(y, gamma, beta, rm2, rv2, nbt2, 0.1, 1e-5)
+    for g, r, n in zip(got, ref, ("mean", "invstd", "scale", "shift")):
+        assert_f32_close(g, r, n, 2e-5)
+    assert_f32_close(rm, rm2, "running_mean", 2e-5)
+    assert_f32_close(rv, rv2, "running_var", 2e-5)
+    assert int(nbt) == 4
+
+
+@pytest.mark.parametrize("resample", [0, 1, 2])
+@pytest.mark.parametrize("with_res,with_mask", [(False, False), (True, False), (False, True)])
+def test_bn_act_fwd_bwd(resample, with_res, with_mask):
+    C = 64
+    y = bf(2, 4, 6, 8, C)
+    res = bf(2, 4, 6, 8, C) if with_res else None
+    mask = (torch.rand(2, 4, 6, 8, C, device=DEV) > 0.35).to(torch.uint8) if with_mask else None
+    p = 0.35 if with_mask else 0.0
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV) * 0.3
+    mean, invstd, scale, shift = S.bn_train_coeffs(y, gamma, beta, None, None, None, 0.1, 1e-5)
+    out = K.bn_act_fwd(y, scale, shift, res, 0.2, resample, mask, p, 0)
+    ref = S.bn_act_fwd(y, scale, shift, res, 0.2, resample, mask, p, 0)
+    assert_bf16_close(out, ref, "bn_act_fwd")
+    g = bf(*ref.shape)
+    got = K.bn_act_bwd(g, y, res, mean, invstd, gamma, beta, 0.2, resample, mask, p, 0, need_dres=with_res)
+    exp = S.bn_act_bwd(g, y, res, mean, invstd, gamma, beta, 0.2, resample, mask, p, 0, need_dres=with_res)
+    assert_bf16_close(got[0], exp[0], "dconv", slack=0.02 * float(exp[0].float().abs().mean()) + 1e-6)
+    if with_res:
+        assert_bf16_close(got[1], exp[1], "dres")
+    assert_f32_close(got[2], exp[2], "dgamma", 1e-3)
+    assert_f32_close(got[3], exp[3], "dbeta", 1e-3)
+
+
+def test_bn_act_relu_slope_zero():
+    C = 128
+    y = bf(1, 4, 4, 4, C)
+    scale, shift = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    assert_bf16_close(K.bn_act_fwd(y, scale, shift, None, 0.0, 0), S.bn_act_fwd(y, scale, shift, None, 0.0, 0), "relu")
+
+
+def test_philox_dropout_is_consistent_and_calibrated():
+    C, p = 64, 0.35
+    y = torch.ones(2, 8, 8, 8, C, device=DEV, dtype=torch.bfloat16)
+    one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    a = K.bn_act_fwd(y, one, zero, None, 0.2, 0, None, p, 1234567)
+    b = K.bn_act_fwd(y, one, zero, None, 0.2, 0, None, p, 1234567)
+    c = K.bn_act_fwd(y, one, zero, None, 0.2, 0, None, p, 7654321)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    keep = (a != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01, keep
+    assert torch.allclose(a[a != 0].float(), torch.tensor(1 / (1 - p), device=DEV), rtol=1e-2)
+    # backward regenerates the same mask: with identity BN and positive inputs dt = keep/(1-p), so
+    # sum(dbeta)/numel = E[keep/(1-p)] ~ 1 and dconv vanishes exactly where the forward output is zero
+    g = torch.ones_like(a)
+    dconv, dres, dgamma, dbeta = K.bn_act_bwd(g, y, None, zero, one, one, zero, 0.2, 0, None, p, 1234567,
+                                              need_dres=True)
+    assert torch.equal(dres != 0, a != 0)
+    assert abs(float(dbeta.sum()) / a.numel() - 1.0) < 0.02
+
+
+# ------------------------------------------------------------------------------------------- thin convs
+@pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (256, 1)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_c1_to_cn(C, T, flip):
+    x1 = torch.randn(2, 5, 6, 9, device=DEV)
+    w = torch.randn(C, T, device=DEV) * 0.3
+    b = torch.randn(C, device=DEV)
+    got = K.c1_to_cn(x1, w, b, flip)
+    ref = S.c1_to_cn(x1, w, b, flip)
+    assert_bf16_close(got, ref, "c1_to_cn")
+    x2 = torch.randn(2, 5, 6, 9, device=DEV)
+    acc = K.c1_to_cn(x2, w, None, flip, out=got.clone())
+    ref2 = S.c1_to_cn(x2, w, None, flip, out=ref.clone())
+    assert_bf16_close(acc, ref2, "c1_to_cn accumulate", rel=2 ** -6)
+
+
+@pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (128, 1), (256, 1)])
+@pytest.mark.parametrize("flip,act", [(False, 0), (True, 0), (False, 1)])
+def test_cn_to_c1(C, T, flip, act):
+    x = bf(2, 5, 7, 37, C)   # W=37: ragged 32-wide bricks
+    w = torch.randn(C, T, device=DEV) * 0.1
+    b = torch.randn(1, device=DEV)
+    mask = (torch.rand(2, 5, 7, 37, device=DEV) > 0.35).to(torch.uint8) if act else None
+    got = K.cn_to_c1(x, w, b, flip, act, mask, 0.35 if act else 0.0, 0)
+    ref = S.cn_to_c1(x, w, b, flip, act, mask, 0.35 if act else 0.0, 0)
+    assert_f32_close(got, ref, "cn_to_c1", 2e-5)
+
+
+@pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (256, 1)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_wgrad_c1(C, T, flip):
+    xc = bf(2, 6, 5, 11, C)
+    x1 = torch.randn(2, 6, 5, 11, device=DEV)
+    got = K.wgrad_c1(xc, x1, T, flip)
+    ref = S.wgrad_c1(xc, x1, T, flip)
+    for g, r, n in zip(got, ref, ("dw", "sum_c", "sum_1")):
+        assert_f32_close(g, r, n, 1e-4)
+
+
+def test_relu_drop_bwd():
+    g, out = torch.randn(1000, device=DEV), torch.relu(torch.randn(1000, device=DEV))
+    assert torch.equal(K.relu_drop_bwd(g, out, 0.35), S.relu_drop_bwd(g, out, 0.35))
+
+
+# ------------------------------------------------------------------------------------------- latent / loss
+def test_reparam_bit_exact_and_backward():
+    mu, lv, eps = (torch.randn(8, 1200, device=DEV) for _ in range(3))
+    z = K.reparam_fwd(mu, lv, eps)
+    assert torch.equal(z, mu + eps * torch.exp(0.5 * lv))            # bit-exact vs torch on the same device
+    assert torch.equal(K.reparam_fwd(mu, lv, 0.1), mu + 0.1 * torch.exp(0.5 * lv))
+    dz = torch.randn_like(mu)
+    dmu, dlv = K.reparam_bwd(dz, lv, eps)
+    rmu, rlv = S.reparam_bwd(dz, lv, eps)
+    assert torch.equal(dmu, rmu)
+    assert_f32_close(dlv, rlv, "dlogvar", 1e-6)
+
+
+@pytest.mark.parametrize("B,n", [(8, 1200), (3, 7), (1, 9600)])
+def test_kl(B, n):
+    mu, lv = torch.randn(B, n, device=DEV), torch.randn(B, n, device=DEV) * 0.5
+    assert_f32_close(K.kl_persample_fwd(mu, lv), S.kl_persample_fwd(mu, lv), "kl", 1e-5)
+    g = torch.randn(B, device=DEV)
+    for a, b in zip(K.kl_persample_bwd(mu, lv, g), S.kl_persample_bwd(mu, lv, g)):
+        assert_f32_close(a, b, "kl bwd", 1e-6)
+
+
+@pytest.mark.parametrize("B,n", [(8, 614400), (2, 1001), (1, 3)])
+def test_mse(B, n):
+    x, y = torch.rand(B, n, device=DEV), torch.rand(B, n, device=DEV)
+    assert_f32_close(K.mse_persample_fwd(x, y), ((x.double() - y.double()) ** 2).sum(1).float(), "mse", 1e-5)
+    g = torch.randn(B, device=DEV)
+    dx, dy = K.mse_persample_bwd(x, y, g, True, True)
+    rx, ry = S.mse_persample_bwd(x, y, g, True, True)
+    assert torch.equal(dx, rx) and torch.equal(dy, ry)
+    dx, dy = K.mse_persample_bwd(x, y, g, False, True)
+    assert dx is None and torch.equal(dy, ry)
+
+
+def test_layout_roundtrip():
+    x = torch.randn(2, 24, 3, 4, 5, device=DEV)
+    a = K.to_ndhwc_bf16(x)
+    assert torch.equal(a, S.to_ndhwc_bf16(x))
+    assert torch.equal(K.to_ncdhw_f32(a), x.to(torch.bfloat16).float())
+
+
+def test_argument_errors_are_reported():
+    with pytest.raises(K.SivaeError):
+        K.conv3_igemm(bf(1, 4, 4, 4, 32), bf(27, 64, 32))            # Cin not a multiple of 64
+    with pytest.raises(K.SivaeError):
+        K.bn_act_fwd(bf(1, 3, 4, 4, 64), torch.ones(64, device=DEV), torch.zeros(64, device=DEV), None, 0.2, 1)  # odd D
+    with pytest.raises(K.SivaeError):
+        K.reparam_fwd(torch.zeros(4), torch.zeros(4), 0.1)             # CPU tensor
