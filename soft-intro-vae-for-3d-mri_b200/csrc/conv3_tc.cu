@@ -163,7 +163,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 struct WgradGeom {
   int N, D, H, W;
   int wt, ht, dt, tiles_w, tiles_h, tiles_d;
-  int rows;             // voxel rows per box, multiple of 16
+  int rows;             // voxel rows per box (<= 128); consumed in 16-row K steps, tail rows zeroed
   int cin_blocks;       // Cin/64
   int units;            // 27 * cin_blocks   (one unit = one tap x one 64-wide Cin block)
   int pairs_total;      // ceil(units/2)
@@ -217,6 +217,18 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     fence_barrier_init();
   }
   if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 512);
+  // The voxel rows are the GEMM K dimension and are consumed 16 at a time: rows [rows, roundup16(rows)) of
+  // every tile are never written by TMA, so zero them once (generic proxy -> async proxy fence).
+  const int rows_pad = (g.rows + 15) & ~15;
+  if (rows_pad != g.rows) {
+    constexpr int kTiles = B_STAGES * (NT / 64) + A_STAGES * 2;   // tiles are contiguous from smem
+    const int tail_vec = (rows_pad - g.rows) * 8;                  // uint4 per tile tail
+    for (int i = threadIdx.x; i < kTiles * tail_vec; i += blockDim.x) {
+      const int tile = i / tail_vec, off = i - tile * tail_vec;
+      reinterpret_cast<uint4*>(smem + (size_t)tile * kTileBytes + (size_t)g.rows * 128)[off] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -258,7 +270,7 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp_id == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
-    const int k16s = g.rows / 16;
+    const int k16s = rows_pad / 16;
     uint32_t a_it = 0, b_it = 0;
     for (long long kb = kb0; kb < kb1; ++kb) {
       const int bs = b_it % B_STAGES;
@@ -357,7 +369,7 @@ static void pick_tile(int W, int H, int D, int row_mult, bool cost_per_row, int&
         const double tiles = (double)cdiv(W, a) * cdiv(H, b) * cdiv(D, c);
         // fprop: every tile costs a full 128-row MMA; wgrad: cost follows the rows actually reduced
         // (plus a small per-box overhead).  Tie-break on wider W (longer contiguous TMA runs).
-        const double cost = cost_per_row ? tiles * (rows + 8.0) : tiles * 128.0;
+        const double cost = cost_per_row ? tiles * (((rows + 15) & ~15) + 8.0) : tiles * 128.0;
         const double score = ((double)W * H * D) / cost + 1e-6 * a + 1e-9 * b;
         if (score > best) {
           best = score;
@@ -423,7 +435,7 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
 // ---- wgrad ----
 static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradGeom& g, int& nt, int& ntiles, int& splits) {
   g.N = N; g.D = D; g.H = H; g.W = W;
-  pick_tile(W, H, D, 16, true, g.wt, g.ht, g.dt);
+  pick_tile(W, H, D, 1, true, g.wt, g.ht, g.dt);
   g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
   g.rows = g.wt * g.ht * g.dt;
   g.cin_blocks = Cin / 64;
