@@ -66,6 +66,17 @@ int sivae_conv3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw,
                       void* workspace, size_t workspace_bytes,
                       int N, int D, int H, int W, int Cin, int Cout, void* stream);
 
+/* Single-output-channel 3x3x3 convolution on tcgen05 (N=16 accumulator tile, column 0 used), fp32 output with the
+ * epilogue fused:   y[v] = act( bias[0] + sum_{tap,c} w[c][tap'] * x[v + delta(tap)][c] ),  tap' = flip ? 26-tap : tap.
+ * Decoder tail Conv3d(C,1,3)+ReLU+Dropout(.35) (models/models.py:137-140; act=1) and the input gradient of the
+ * encoder stem Conv3d(1,C,3) (models/models.py:92; flip=1, act=0).  w is the torch weight as it lies in memory
+ * ([1][C][3][3][3] or [C][1][3][3][3] = w[c][tap]); dropout as in sivae_bn_act_fwd with mask [N][D][H][W]. */
+size_t sivae_conv3_to1_workspace_bytes(int C);
+int sivae_conv3_to1(const void* x_bf16, const float* w, const float* bias, float* y,
+                    int N, int D, int H, int W, int C, int flip, int act,
+                    const uint8_t* mask, float p, unsigned long long seed,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm3d (train mode) + (Leaky)ReLU + residual + AvgPool/Upsample + Dropout, fused
  * (nn.BatchNorm3d models/models.py:18,22,56,60,93,119; LeakyReLU :15,19,94,121; residual :39-41;

@@ -60,6 +60,9 @@ int conv3_igemm(const void*, const void*, void*, int, int, int, int, int, int, c
 size_t conv3_wgrad_workspace_bytes(int, int, int, int, int, int);
 int conv3_wgrad(const void*, const void*, float*, void*, size_t, int, int, int, int, int, int, cudaStream_t);
 int pack_conv3_weights(const float*, int, int, void*, void*, cudaStream_t);
+size_t conv3_to1_workspace_bytes(int);
+int conv3_to1(const void*, const float*, const float*, float*, int, int, int, int, int, int, int, const uint8_t*, float,
+              unsigned long long, void*, size_t, cudaStream_t);
 size_t bn_workspace_bytes(int);
 int bn_train_coeffs(const void*, long long, int, const float*, const float*, float*, float*, long long*, float, float,
                     float*, float*, float*, float*, void*, size_t, cudaStream_t);
@@ -122,6 +125,12 @@ size_t sivae_conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, in
 int sivae_conv3_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
                       int Cin, int Cout, void* stream) {
   return conv3_wgrad(x, dy, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, ST(stream));
+}
+size_t sivae_conv3_to1_workspace_bytes(int C) { return conv3_to1_workspace_bytes(C); }
+int sivae_conv3_to1(const void* x, const float* w, const float* bias, float* y, int N, int D, int H, int W, int C,
+                    int flip, int act, const uint8_t* mask, float p, unsigned long long seed, void* ws, size_t ws_bytes,
+                    void* stream) {
+  return conv3_to1(x, w, bias, y, N, D, H, W, C, flip, act, mask, p, seed, ws, ws_bytes, ST(stream));
 }
 size_t sivae_bn_workspace_bytes(int C) { return bn_workspace_bytes(C); }
 int sivae_bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, const float* beta,

@@ -44,10 +44,23 @@ __device__ __forceinline__ void decode_tile(const Geom& g, long long id, int& w0
 // =================================================================================================
 // fprop / dgrad
 // =================================================================================================
-template <int BLOCK_N, int STAGES>
+// Epilogue of the single-output-channel variant (decoder tail Conv3d(C,1,3)+ReLU+Dropout, models/models.py:137-140,
+// and the input gradient of the encoder stem): only accumulator column 0 is meaningful; it is written as fp32
+// [N][D][H][W] with bias / ReLU / dropout fused.
+struct ToOneEpilogue {
+  float* y;
+  const float* bias;   // 1 element or NULL
+  const uint8_t* mask; // [N][D][H][W] keep-mask or NULL
+  unsigned long long seed;
+  float p;
+  int act;             // 0 identity, 1 ReLU + dropout
+};
+
+template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(192)
 conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmC, const ConvGeom g) {
+                   const __grid_constant__ CUtensorMap tmC, const ConvGeom g, const ToOneEpilogue ep) {
+  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = kTileBytes + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +88,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, BLOCK_N);
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -124,6 +137,23 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const int q = warp_id & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
+    if constexpr (EPI == 1) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      const int w = w0 + row % g.wt, h = h0 + (row / g.wt) % g.ht, d = d0 + row / (g.wt * g.ht);
+      if (row < g.rows && w < g.W && h < g.H && d < g.D) {
+        const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+        float r = __uint_as_float(v[0]) + (ep.bias ? ep.bias[0] : 0.f);
+        if (ep.act == 1) {
+          r = fmaxf(r, 0.f);
+          const float inv_keep = 1.f / (1.f - ep.p);
+          if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
+          else if (ep.p > 0.f) r = philox_keep(ep.seed, (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+        }
+        ep.y[vox] = r;
+      }
+    } else {
     uint8_t* out_stage = smem;  // pipeline buffers are idle once tmem_full has fired
 #pragma unroll 1
     for (int j = 0; j < BLOCK_N / 32; ++j) {
@@ -151,10 +181,11 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tma_store_commit();
       tma_store_wait_all();
     }
+    }  // EPI == 0
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_id == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp_id == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =================================================================================================
@@ -387,20 +418,20 @@ static int make_act_tmap(CUtensorMap* tm, const void* base, int N, int D, int H,
   return make_tmap_bf16(tm, base, 5, dims, strides, box);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EPI>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGeom& g,
-                        long long tiles, int nblocks, cudaStream_t st) {
+                        long long tiles, int nblocks, const ToOneEpilogue& ep, cudaStream_t st) {
   constexpr int smem = STAGES * (kTileBytes + BLOCK_N * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(conv3_igemm_kernel<BLOCK_N, STAGES>,
+    if (check_cuda(cudaFuncSetAttribute(conv3_igemm_kernel<BLOCK_N, STAGES, EPI>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                    "cudaFuncSetAttribute(conv3_igemm)"))
       return -1;
     attr_set = true;
   }
   dim3 grid((unsigned)tiles, (unsigned)nblocks);
-  conv3_igemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, tmC, g);
+  conv3_igemm_kernel<BLOCK_N, STAGES, EPI><<<grid, 192, smem, st>>>(tmA, tmB, tmC, g, ep);
   SIVAE_LAUNCH_OK("conv3_igemm_kernel");
   return 0;
 }
@@ -428,8 +459,51 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
     uint32_t box[3] = {64, (uint32_t)block_n, 1};
     if (make_tmap_bf16(&tmB, wpack, 3, dims, strides, box)) return -1;
   }
-  if (block_n == 128) return launch_igemm<128, 3>(tmA, tmB, tmC, g, tiles, Cout / 128, st);
-  return launch_igemm<64, 3>(tmA, tmB, tmC, g, tiles, Cout / 64, st);
+  const ToOneEpilogue ep{};
+  if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
+  return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
+}
+
+// fp32 [C][27] (one output channel) -> bf16 [27][16][C]; row 0 = the filter (tap-flipped when `flip`), rows 1..15 zero
+__global__ void pack_to1_weights_kernel(const float* __restrict__ w, int C, int flip, __nv_bfloat16* __restrict__ wp) {
+  const int total = 27 * 16 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, r = (i / C) % 16, tap = i / (16 * C);
+    wp[i] = __float2bfloat16_rn(r == 0 ? w[c * 27 + (flip ? 26 - tap : tap)] : 0.f);
+  }
+}
+
+size_t conv3_to1_workspace_bytes(int C) { return (size_t)27 * 16 * C * sizeof(__nv_bfloat16); }
+
+// y[v] = act(bias + sum_{tap,c} w[c][tap'] * x[v + delta(tap)][c]) on tcgen05 (N = 16 tile, column 0 used)
+int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N, int D, int H, int W, int C, int flip,
+              int act, const uint8_t* mask, float p, unsigned long long seed, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+  SIVAE_CHECK(C % 64 == 0 && C >= 64, "conv3_to1: C=%d must be a multiple of 64", C);
+  SIVAE_CHECK(p >= 0.f && p < 1.f, "conv3_to1: dropout p=%f out of range", p);
+  SIVAE_CHECK(ws && ws_bytes >= conv3_to1_workspace_bytes(C), "conv3_to1: workspace too small");
+  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_to1: empty tensor");
+  pack_to1_weights_kernel<<<cdiv(27 * 16 * C, 256), 256, 0, st>>>(w, C, flip, (__nv_bfloat16*)ws);
+  SIVAE_LAUNCH_OK("pack_to1_weights_kernel");
+  ConvGeom g;
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  pick_tile(W, H, D, 1, false, g.wt, g.ht, g.dt);
+  g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
+  g.rows = g.wt * g.ht * g.dt;
+  g.cin_blocks = C / 64;
+  const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
+  SIVAE_CHECK(tiles < (1ll << 31), "conv3_to1: too many tiles");
+  CUtensorMap tmA, tmB;
+  if (make_act_tmap(&tmA, x, N, D, H, W, C, g.wt, g.ht, g.dt)) return -1;
+  {
+    uint64_t dims[3] = {(uint64_t)C, 16, 27};
+    uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)16 * C * 2};
+    uint32_t box[3] = {64, 16, 1};
+    if (make_tmap_bf16(&tmB, ws, 3, dims, strides, box)) return -1;
+  }
+  ToOneEpilogue ep;
+  ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = seed; ep.p = p; ep.act = act;
+  return launch_igemm<16, 4, 1>(tmA, tmB, tmA, g, tiles, 1, ep, st);
 }
 
 // ---- wgrad ----

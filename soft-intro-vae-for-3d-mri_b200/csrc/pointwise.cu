@@ -95,18 +95,33 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const __nv_bfloat1
   block_reduce_channels(s1, s2, C, cpc, partial);
 }
 
+// one warp per channel: lanes stride over the per-block partials, fp64 accumulate, shuffle tree
+__device__ __forceinline__ void warp_channel_sums(const float* __restrict__ partial, int nblocks, int C, int c,
+                                                  double& a, double& b) {
+  const int lane = threadIdx.x & 31;
+  a = 0.0;
+  b = 0.0;
+  for (int i = lane; i < nblocks; i += 32) {
+    a += (double)partial[((long long)i * 2 + 0) * C + c];
+    b += (double)partial[((long long)i * 2 + 1) * C + c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long nvox,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* running_mean, float* running_var, long long* nbt, float momentum,
                                          float eps, float* mean_o, float* invstd_o, float* scale_o, float* shift_o) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt != nullptr) *nbt += 1;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
   if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblocks; ++i) {
-    a += (double)partial[((long long)i * 2 + 0) * C + c];
-    b += (double)partial[((long long)i * 2 + 1) * C + c];
-  }
+  double a, b;
+  warp_channel_sums(partial, nblocks, C, c, a, b);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = (double)nvox;
   const double mean = a / n;
   double var = b / n - mean * mean;
@@ -280,13 +295,11 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
 // coef[0][c] = sum(dt)/n, coef[1][c] = sum(dt*xhat)/n ; dgamma = sum(dt*xhat), dbeta = sum(dt)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long nvox,
                                        float* __restrict__ coef, float* dgamma, float* dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblocks; ++i) {
-    a += (double)partial[((long long)i * 2 + 0) * C + c];
-    b += (double)partial[((long long)i * 2 + 1) * C + c];
-  }
+  double a, b;
+  warp_channel_sums(partial, nblocks, C, c, a, b);
+  if ((threadIdx.x & 31) != 0) return;
   coef[c] = (float)(a / (double)nvox);
   coef[C + c] = (float)(b / (double)nvox);
   if (dbeta) dbeta[c] = (float)a;
@@ -369,7 +382,7 @@ int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, co
   const int blocks = reduce_blocks(nvox, C);
   bn_stats_kernel<<<blocks, kBnThreads, 0, st>>>((const __nv_bfloat16*)y, nvox, C, (float*)ws);
   SIVAE_LAUNCH_OK("bn_stats_kernel");
-  bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>((const float*)ws, blocks, C, nvox, gamma, beta, rm, rv, nbt,
+  bn_stats_finalize_kernel<<<cdiv(C, 4), 128, 0, st>>>((const float*)ws, blocks, C, nvox, gamma, beta, rm, rv, nbt,
                                                          momentum, eps, mean, invstd, scale, shift);
   SIVAE_LAUNCH_OK("bn_stats_finalize_kernel");
   return 0;
@@ -425,7 +438,7 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   else SIVAE_BWD_REDUCE(2);
 #undef SIVAE_BWD_REDUCE
   SIVAE_LAUNCH_OK("bn_act_bwd_reduce_kernel");
-  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, blocks, C, nvox, coef, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, blocks, C, nvox, coef, dgamma, dbeta);
   SIVAE_LAUNCH_OK("bn_bwd_finalize_kernel");
   const int ablocks = grid_for(nvox * (C / 8), 256);
 #define SIVAE_BWD_APPLY(M)                                                                                      \

@@ -58,6 +58,81 @@ __global__ void __launch_bounds__(256) c1_to_cn_kernel(const float* __restrict__
   }
 }
 
+// 3x3x3 variant, brick-tiled: a block owns a 4 x 4 x 16 (d,h,w) brick of voxels, stages the 6 x 6 x 18 fp32 halo of the
+// one-channel input in shared memory, and each thread produces all C channels of one voxel (27 taps in registers,
+// weights broadcast from shared memory).  1728 FMA per voxel for C = 64: FMA-pipe bound, not latency bound.
+static constexpr int kBrickD = 4, kBrickH = 4, kBrickW = 16;
+static constexpr int kHaloElems = (kBrickD + 2) * (kBrickH + 2) * (kBrickW + 2);
+
+__device__ __forceinline__ void load_halo(const float* __restrict__ x1, float* xs, long long n, int d0, int h0, int w0,
+                                          int D, int H, int W) {
+  for (int i = threadIdx.x; i < kHaloElems; i += blockDim.x) {
+    const int wx = i % (kBrickW + 2), hy = (i / (kBrickW + 2)) % (kBrickH + 2), dz = i / ((kBrickW + 2) * (kBrickH + 2));
+    const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+    float v = 0.f;
+    if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+      v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+    xs[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) c1_to_cn27_kernel(const float* __restrict__ x1, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ y, int N, int D, int H, int W,
+                                                         int C, int flip, int accumulate) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                 // [27][C]
+  float* b_s = sm + 27 * C;        // [C]
+  float* xs = b_s + C;             // halo
+  for (int i = threadIdx.x; i < C * 27; i += blockDim.x) {
+    const int c = i / 27, t = i % 27;
+    w_s[(flip ? (26 - t) : t) * C + c] = w[i];
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) b_s[i] = bias ? bias[i] : 0.f;
+  const int bw = cdiv(W, kBrickW), bh = cdiv(H, kBrickH), bd = cdiv(D, kBrickD);
+  const long long bricks = (long long)N * bd * bh * bw;
+  const int wq = threadIdx.x % kBrickW, hq = (threadIdx.x / kBrickW) % kBrickH, dq = threadIdx.x / (kBrickW * kBrickH);
+  for (long long b = blockIdx.x; b < bricks; b += gridDim.x) {
+    const int tw = (int)(b % bw), th = (int)((b / bw) % bh), td = (int)((b / ((long long)bw * bh)) % bd);
+    const long long n = b / ((long long)bw * bh * bd);
+    const int d0 = td * kBrickD, h0 = th * kBrickH, w0 = tw * kBrickW;
+    __syncthreads();
+    load_halo(x1, xs, n, d0, h0, w0, D, H, W);
+    __syncthreads();
+    const int d = d0 + dq, h = h0 + hq, ww = w0 + wq;
+    if (d < D && h < H && ww < W) {
+      float xv[27];
+#pragma unroll
+      for (int t = 0; t < 27; ++t)
+        xv[t] = xs[((dq + t / 9) * (kBrickH + 2) + hq + (t / 3) % 3) * (kBrickW + 2) + wq + t % 3];
+      __nv_bfloat16* dst = y + (((n * D + d) * H + h) * W + ww) * C;
+      for (int cg = 0; cg < C; cg += 8) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = b_s[cg + k];
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+          const float4 wa = *reinterpret_cast<const float4*>(w_s + t * C + cg);
+          const float4 wb = *reinterpret_cast<const float4*>(w_s + t * C + cg + 4);
+          acc[0] = fmaf(wa.x, xv[t], acc[0]); acc[1] = fmaf(wa.y, xv[t], acc[1]);
+          acc[2] = fmaf(wa.z, xv[t], acc[2]); acc[3] = fmaf(wa.w, xv[t], acc[3]);
+          acc[4] = fmaf(wb.x, xv[t], acc[4]); acc[5] = fmaf(wb.y, xv[t], acc[5]);
+          acc[6] = fmaf(wb.z, xv[t], acc[6]); acc[7] = fmaf(wb.w, xv[t], acc[7]);
+        }
+        if (accumulate) {
+          const uint4 u = *reinterpret_cast<const uint4*>(dst + cg);
+          const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += bq.x; acc[3] += bq.y; acc[4] += c.x; acc[5] += c.y; acc[6] += e.x; acc[7] += e.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(dst + cg) = o;
+      }
+    }
+  }
+}
+
 // ---- C -> 1 -------------------------------------------------------------------------------------
 // One warp per output voxel; lane owns CPL = C/32 consecutive channels (coalesced 64..512-byte reads per tap).
 // A block covers a 2 x 4 x 32 (d,h,w) brick so the 27-tap neighbourhood mostly hits L1.
@@ -174,6 +249,93 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           const int idx = t * C + lane * CPL + k;
+          red[idx] = (wsel == 0 ? 0.f : red[idx]) + acc[t][k];
+        }
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int idx = T * C + lane * CPL + k;
+        red[idx] = (wsel == 0 ? 0.f : red[idx]) + sc[k];
+      }
+      if (lane == 0) red[T * C + C] = (wsel == 0 ? 0.f : red[T * C + C]) + s1;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < PER; i += blockDim.x) partial[(long long)blockIdx.x * PER + i] = red[i];
+}
+
+// 3x3x3 variant, brick-tiled like c1_to_cn27_kernel: the one-channel operand's halo lives in shared memory (27 broadcast
+// LDS per voxel), the C-channel operand streams through coalesced 4/8-byte-per-lane loads, four voxels in flight per warp.
+template <int CPL>
+__global__ void __launch_bounds__(256) wgrad_c1_27_kernel(const __nv_bfloat16* __restrict__ xc,
+                                                          const float* __restrict__ x1, int N, int D, int H, int W,
+                                                          int flip, float* __restrict__ partial) {
+  constexpr int C = CPL * 32, T = 27;
+  constexpr int PER = T * C + C + 1;
+  __shared__ float red[PER];
+  __shared__ float xs[kHaloElems];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[T][CPL], sc[CPL], s1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[t][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) sc[k] = 0.f;
+  const int bw = cdiv(W, kBrickW), bh = cdiv(H, kBrickH), bd = cdiv(D, kBrickD);
+  const long long bricks = (long long)N * bd * bh * bw;
+  for (long long b = blockIdx.x; b < bricks; b += gridDim.x) {
+    const int tw = (int)(b % bw), th = (int)((b / bw) % bh), td = (int)((b / ((long long)bw * bh)) % bd);
+    const long long n = b / ((long long)bw * bh * bd);
+    const int d0 = td * kBrickD, h0 = th * kBrickH, w0 = tw * kBrickW;
+    __syncthreads();
+    load_halo(x1, xs, n, d0, h0, w0, D, H, W);
+    __syncthreads();
+    // warp `warp` owns voxels [warp*32, warp*32+32) of the brick: 2 h-rows of 16 w at depth warp/2
+    const int dq = warp >> 1;
+    const int d = d0 + dq;
+    if (d >= D) continue;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+      float f[4][CPL];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const int hq = (warp & 1) * 2 + (j >> 4), wq = j & 15;
+        const int h = h0 + hq, ww = w0 + wq;
+        if (h < H && ww < W) {
+          ld_cpl<CPL>(xc + (((n * D + d) * H + h) * W + ww) * C + lane * CPL, f[u]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) f[u][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const int hq = (warp & 1) * 2 + (j >> 4), wq = j & 15;
+        const float* xb = xs + (dq * (kBrickH + 2) + hq) * (kBrickW + 2) + wq;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) sc[k] += f[u][k];
+        s1 += xb[(kBrickH + 2) * (kBrickW + 2) + (kBrickW + 2) + 1];   // centre tap (zero outside the volume)
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          // offsets are compile-time; the tap flip is applied when the accumulators are written out
+          const float xv = xb[(t / 9) * (kBrickH + 2) * (kBrickW + 2) + ((t / 3) % 3) * (kBrickW + 2) + t % 3];
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) acc[t][k] = fmaf(f[u][k], xv, acc[t][k]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int nwarps = blockDim.x >> 5;
+  for (int wsel = 0; wsel < nwarps; ++wsel) {
+    if (warp == wsel) {
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const int idx = (flip ? (T - 1 - t) : t) * C + lane * CPL + k;
           red[idx] = (wsel == 0 ? 0.f : red[idx]) + acc[t][k];
         }
 #pragma unroll
@@ -330,9 +492,13 @@ int c1_to_cn(const float* x1, const float* w, const float* bias, void* y, int N,
   const size_t smem = (size_t)(T + 1) * C * sizeof(float);
   SIVAE_CHECK(smem <= 48 * 1024, "c1_to_cn: C=%d too large", C);
   const int blocks = grid_for(items, 256);
-  if (T == 27)
-    c1_to_cn_kernel<27><<<blocks, 256, smem, st>>>(x1, w, bias, (__nv_bfloat16*)y, N, D, H, W, C, flip, accumulate);
-  else
+  if (T == 27) {
+    const long long bricks = (long long)N * cdiv(D, kBrickD) * cdiv(H, kBrickH) * cdiv(W, kBrickW);
+    const size_t smem27 = ((size_t)28 * C + kHaloElems) * sizeof(float);
+    SIVAE_CHECK(smem27 <= 48 * 1024, "c1_to_cn: C=%d too large", C);
+    const int b27 = (int)(bricks < 148ll * 8 ? bricks : 148ll * 8);
+    c1_to_cn27_kernel<<<b27, 256, smem27, st>>>(x1, w, bias, (__nv_bfloat16*)y, N, D, H, W, C, flip, accumulate);
+  } else
     c1_to_cn_kernel<1><<<blocks, 256, smem, st>>>(x1, w, bias, (__nv_bfloat16*)y, N, D, H, W, C, flip, accumulate);
   SIVAE_LAUNCH_OK("c1_to_cn_kernel");
   return 0;
@@ -378,9 +544,12 @@ int wgrad_c1(const void* xc, const float* x1, float* dw, float* sum_c, float* su
   const __nv_bfloat16* xx = (const __nv_bfloat16*)xc;
   float* partial = (float*)ws;
 #define SIVAE_WG1(CPL, TT) wgrad_c1_kernel<CPL, TT><<<blocks, 256, 0, st>>>(xx, x1, N, D, H, W, flip, partial)
-  if (C == 64 && T == 27) SIVAE_WG1(2, 27);
-  else if (C == 64) SIVAE_WG1(2, 1);
-  else if (C == 128 && T == 27) SIVAE_WG1(4, 27);
+  if (T == 27) {
+    const long long bricks = (long long)N * cdiv(D, kBrickD) * cdiv(H, kBrickH) * cdiv(W, kBrickW);
+    blocks = (int)(bricks < kWgradC1Blocks ? bricks : kWgradC1Blocks);
+    if (C == 64) wgrad_c1_27_kernel<2><<<blocks, 256, 0, st>>>(xx, x1, N, D, H, W, flip, partial);
+    else wgrad_c1_27_kernel<4><<<blocks, 256, 0, st>>>(xx, x1, N, D, H, W, flip, partial);
+  } else if (C == 64) SIVAE_WG1(2, 1);
   else if (C == 128) SIVAE_WG1(4, 1);
   else SIVAE_WG1(8, 1);
 #undef SIVAE_WG1

@@ -35,6 +35,8 @@ _SIGNATURES = {
     "sivae_conv3_igemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_conv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_conv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_conv3_to1_workspace_bytes": (_sz, [_i]),
+    "sivae_conv3_to1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp, _sz, _vp]),
     "sivae_bn_workspace_bytes": (_sz, [_i]),
     "sivae_bn_train_coeffs": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sivae_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _f, _u64, _vp]),
@@ -314,8 +316,18 @@ def cn_to_c1(x, w, bias, flip: bool = False, act: int = 0, mask=None, p: float =
     if mask is not None:
         _req(mask, torch.uint8, "mask")
     y = torch.empty(n, d, h, ww, dtype=torch.float32, device=x.device)
-    _check(_L().sivae_cn_to_c1(_p(x), _p(w), _p(bias), _p(y), n, d, h, ww, c, w.shape[1], int(flip), act, _p(mask), p,
-                               seed, _stream(x)), "sivae_cn_to_c1")
+    lib = _L()
+    if w.shape[1] == 27 and c % 64 == 0:
+        # 3x3x3: implicit GEMM on tcgen05 (N=16 tile, fp32 column-0 epilogue); weights are rounded to bf16
+        ws = _workspace(x.device, lib.sivae_conv3_to1_workspace_bytes(c), "to1")
+        flops = 2.0 * 27 * c * 16 * n * d * h * ww
+        _timed("conv3_to1", (flops, (n, d, h, ww, c, 1)),
+               lambda: _check(lib.sivae_conv3_to1(_p(x), _p(w), _p(bias), _p(y), n, d, h, ww, c, int(flip), act,
+                                                  _p(mask), p, seed, _p(ws), ws.numel(), _stream(x)),
+                              "sivae_conv3_to1"))
+        return y
+    _check(lib.sivae_cn_to_c1(_p(x), _p(w), _p(bias), _p(y), n, d, h, ww, c, w.shape[1], int(flip), act, _p(mask), p,
+                              seed, _stream(x)), "sivae_cn_to_c1")
     return y
 
 

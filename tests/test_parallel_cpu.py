@@ -1,0 +1,88 @@
+"""world_size-2 gloo test of the bucketed gradient reducer (the N>1 path of bench.py) on CPU:
+two ranks with different data must end with identical, averaged gradients -- including a parameter
+that never receives a gradient and a phase in which half the parameters are frozen."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sivae_b200
+    from sivae_b200 import parallel as P
+    r, w, _ = P.init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    enc = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 4))
+    unused = torch.nn.Linear(3, 3)                      # registered but never used (like the shortcut convs)
+    dec = torch.nn.Linear(4, 2)
+    params_e = list(enc.parameters()) + list(unused.parameters())
+    red_e = P.GradReducer(params_e, bucket_mb=0.0001)   # tiny buckets -> several collectives
+    red_d = P.GradReducer(dec.parameters(), bucket_mb=0.0001)
+    P.broadcast_module_state(enc); P.broadcast_module_state(dec)
+    out = {}
+    for step in range(3):
+        torch.manual_seed(100 + 10 * step + rank)       # rank-specific data
+        x = torch.randn(7, 6)
+        # phase E: decoder frozen
+        for p in dec.parameters():
+            p.requires_grad = False
+        for p in enc.parameters():
+            p.requires_grad = True
+        for p in params_e:
+            p.grad = None
+        dec(enc(x)).pow(2).mean().backward()
+        local = [p.grad.clone() for p in enc.parameters()]
+        red_e.finish()
+        gathered = [torch.zeros_like(torch.cat([g.flatten() for g in local])) for _ in range(world)]
+        dist.all_gather(gathered, torch.cat([g.flatten() for g in local]))
+        expect = sum(gathered) / world
+        got = torch.cat([p.grad.flatten() for p in enc.parameters()])
+        assert torch.allclose(got, expect, atol=1e-6), (step, rank)
+        assert all(p.grad is None for p in unused.parameters())
+        # phase D: encoder frozen
+        for p in dec.parameters():
+            p.requires_grad = True
+            p.grad = None
+        for p in enc.parameters():
+            p.requires_grad = False
+        dec(enc(x)).pow(2).mean().backward()
+        local = torch.cat([p.grad.flatten() for p in dec.parameters()])
+        red_d.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        got = torch.cat([p.grad.flatten() for p in dec.parameters()])
+        assert torch.allclose(got, sum(gathered) / world, atol=1e-6), (step, rank)
+        out[step] = got.clone()
+    scal = P.all_reduce_mean_scalars({"a": torch.tensor(float(rank)), "b": torch.tensor(2.0)})
+    assert float(scal["a"]) == pytest.approx((world - 1) / 2) and float(scal["b"]) == 2.0
+    q.put((rank, out[2]))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(res[0], res[1])
