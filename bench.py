@@ -158,8 +158,9 @@ def run_ours(args):
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
     net.to(dev).train()
-    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4)
-    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4)
+    use_graph = not args.no_graph and world == 1
+    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
+    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
     red_e = P.GradReducer(net.encoder.parameters()) if world > 1 else None
     red_d = P.GradReducer(net.decoder.parameters()) if world > 1 else None
     hp = T.StepHyper()
@@ -174,13 +175,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    def step_eager():
         return T.soft_intro_train_step(net, real_dev, noise_dev, opt_e, opt_d, hp, red_e, red_d)
 
+    graphed = None
+    if use_graph:
+        # whole-step CUDA graph (sivae_b200.graph): ~1150 launches per step collapse into one replay
+        graphed = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real_dev, noise_dev, hp, warmup=2)
+
+    def step_resident():
+        if graphed is not None:
+            return graphed(real_dev, noise_dev)
+        return step_eager()
+
     def step_e2e():
-        real = real_host.to(dev, non_blocking=True)
-        noise = noise_host.to(dev, non_blocking=True)
-        terms = T.soft_intro_train_step(net, real, noise, opt_e, opt_d, hp, red_e, red_d)
+        if graphed is not None:
+            terms = graphed(real_host, noise_host)                     # pinned host -> captured input buffers
+        else:
+            real = real_host.to(dev, non_blocking=True)
+            noise = noise_host.to(dev, non_blocking=True)
+            terms = T.soft_intro_train_step(net, real, noise, opt_e, opt_d, hp, red_e, red_d)
         res = torch.stack([terms["lossE"], terms["lossD"]]).cpu()      # device->host read of the step's result
         return res
 
@@ -209,11 +223,19 @@ def run_ours(args):
         ms, terms = timed(step_resident, args.steps)
     launches = K.launch_count() - n0
     clocks = sampler.stop() if sampler else None
+    lossE, lossD = float(terms["lossE"]), float(terms["lossD"])
+    if graphed is not None:
+        # a replayed graph cannot carry per-kernel events: time the dominant kernels live in one eager step of
+        # the same process on the same inputs (CUDA events on the launch stream), and count its launches
+        n0 = K.launch_count()
+        with K.KernelTimer() as kt:
+            step_eager()
+            torch.cuda.synchronize()
+        launches = (K.launch_count() - n0) * args.steps
     ksum = kt.summary()
     for _ in range(1):
         step_e2e()
     ms_e2e, res = timed(step_e2e, args.steps)
-    lossE, lossD = float(terms["lossE"]), float(terms["lossD"])
     if not (lossE == lossE and lossD == lossD):
         raise SystemExit("NaN loss in the benchmark step")
 
@@ -232,12 +254,16 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "conv3_igemm_kernel (tcgen05 implicit-GEMM fprop/dgrad)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
-                "launches": dom["launches"], "share_of_step": dom["ms"] / ms if ms else None,
+                "launches": dom["launches"],
+                "share_of_step": dom["ms"] / (ms / args.steps if graphed is not None else ms) if ms else None,
                 "top_shape": ({"NDHWCiCo": list(top_shape[0]),
                                "tflops": top_shape[1]["work"] / (top_shape[1]["ms"] * 1e-3) / 1e12,
                                "ms_per_launch": top_shape[1]["ms"] / top_shape[1]["launches"]} if top_shape else None),
                 "wgrad": {"tflops": wg["work"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] else 0.0,
-                          "share_of_step": wg["ms"] / ms if ms else None, "launches": wg["launches"]},
+                          "share_of_step": wg["ms"] / (ms / args.steps if graphed is not None else ms) if ms else None,
+                          "launches": wg["launches"]},
+                "timing": ("CUDA events around every launch of the kernel in one eager step of the same run"
+                           if graphed is not None else "CUDA events around every launch inside the timed region"),
                 "whole_step_tflops": value / world * GFLOP_PER_VOLUME_STEP / 1e3}
     line = {"metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -246,7 +272,7 @@ def run_ours(args):
                                    "one E+D train step incl. 2 Adam steps",
                        "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
-                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP},
+                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP, "cuda_graph": graphed is not None},
             "clocks": clocks, "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
                                       "d2h_bytes_per_step": int(res.numel() * 4)},
@@ -275,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=LOCAL_BATCH, help="local batch per GPU (headline: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -42,6 +42,13 @@ int sivae_device_check(void);
 /* number of kernels launched by this library since load (diagnostic for bench.py "gpu_launches"). */
 long long sivae_launch_count(void);
 
+/* Dropout epoch counter (nn.Dropout draws a fresh mask on every call, models/models.py:95,122,140).  Every Philox
+ * dropout call is keyed by (seed argument, *device_counter): registering a device-resident uint64 and advancing it
+ * once per training step lets a captured CUDA graph, whose seed arguments are baked in, draw new masks on each replay.
+ * Pass NULL to unregister (the seed argument alone keys the masks). */
+int sivae_set_seed_counter(unsigned long long* device_counter);
+int sivae_advance_seed_counter(void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3x3x3 convolutions, stride 1, pad 1, no bias (nn.Conv3d in BuildingBlock / UpsampleBuildingkBlock,
  * models/models.py:17,21,55,59) and their autograd (lossE.backward(), utils/my_trainer.py:287,323).

@@ -38,6 +38,14 @@ def device_check():
     return None
 
 
+def set_seed_counter(counter):
+    return None
+
+
+def advance_seed_counter(device):
+    return None
+
+
 def pack_conv3_weights(w):
     co, ci = w.shape[:2]
     w27 = w.reshape(co, ci, 27)

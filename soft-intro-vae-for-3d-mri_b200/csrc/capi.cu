@@ -15,6 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned long long*> g_seed_counter{nullptr};
+SeedRef make_seed_ref(unsigned long long seed) { return SeedRef{seed, g_seed_counter.load()}; }
+
+__global__ void advance_seed_counter_kernel(unsigned long long* ctr) { *ctr += 1; }
+
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -98,6 +103,18 @@ extern "C" {
 const char* sivae_last_error(void) { return g_err; }
 int sivae_abi_version(void) { return SIVAE_ABI_VERSION; }
 long long sivae_launch_count(void) { return g_launches.load(); }
+
+int sivae_set_seed_counter(unsigned long long* device_counter) {
+  g_seed_counter.store(device_counter);
+  return 0;
+}
+int sivae_advance_seed_counter(void* stream) {
+  unsigned long long* c = g_seed_counter.load();
+  SIVAE_CHECK(c != nullptr, "sivae_advance_seed_counter: no counter registered");
+  advance_seed_counter_kernel<<<1, 1, 0, ST(stream)>>>(c);
+  SIVAE_LAUNCH_OK("advance_seed_counter_kernel");
+  return 0;
+}
 
 int sivae_device_check(void) {
   int dev = 0;

@@ -51,7 +51,7 @@ struct ToOneEpilogue {
   float* y;
   const float* bias;   // 1 element or NULL
   const uint8_t* mask; // [N][D][H][W] keep-mask or NULL
-  unsigned long long seed;
+  SeedRef seed;
   float p;
   int act;             // 0 identity, 1 ReLU + dropout
 };
@@ -149,7 +149,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           r = fmaxf(r, 0.f);
           const float inv_keep = 1.f / (1.f - ep.p);
           if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
-          else if (ep.p > 0.f) r = philox_keep(ep.seed, (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+          else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
         }
         ep.y[vox] = r;
       }
@@ -502,7 +502,7 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
     if (make_tmap_bf16(&tmB, ws, 3, dims, strides, box)) return -1;
   }
   ToOneEpilogue ep;
-  ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = seed; ep.p = p; ep.act = act;
+  ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = make_seed_ref(seed); ep.p = p; ep.act = act;
   return launch_igemm<16, 4, 1>(tmA, tmB, tmA, g, tiles, 1, ep, st);
 }
 

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ out, int N, int D, int H, int W,
                                                          int C, float slope, const uint8_t* __restrict__ mask, float p,
-                                                         unsigned long long seed) {
+                                                         const SeedRef sref) {
+  const unsigned long long seed = resolve_seed(sref);
   const int cpc = C >> 3;
   const long long nvox_in = (long long)N * D * H * W;
   const long long items = (MODE == SIVAE_RESAMPLE_AVGPOOL2 ? nvox_in / 8 : nvox_in) * cpc;
@@ -271,8 +272,9 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
                          const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                          const float* __restrict__ beta, int N, int D, int H, int W, int C, float slope,
-                         const uint8_t* __restrict__ mask, float p, unsigned long long seed,
+                         const uint8_t* __restrict__ mask, float p, const SeedRef sref,
                          float* __restrict__ partial) {
+  const unsigned long long seed = resolve_seed(sref);
   const int cpc = C >> 3;
   const int chunk = threadIdx.x % cpc;
   const int lanes_v = kBnThreads / cpc;
@@ -313,7 +315,8 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ beta, const float* __restrict__ coef,
                         __nv_bfloat16* __restrict__ dconv, __nv_bfloat16* __restrict__ dres, int N, int D, int H, int W,
-                        int C, float slope, const uint8_t* __restrict__ mask, float p, unsigned long long seed) {
+                        int C, float slope, const uint8_t* __restrict__ mask, float p, const SeedRef sref) {
+  const unsigned long long seed = resolve_seed(sref);
   const int cpc = C >> 3;
   const long long items = (long long)N * D * H * W * cpc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -366,9 +369,10 @@ static bool channels_ok(int C) { return C >= 8 && (C % 8) == 0 && (kBnThreads % 
 size_t bn_workspace_bytes(int C) { return ((size_t)kBnMaxBlocks * 2 * C + 2 * (size_t)C) * sizeof(float); }
 
 static int reduce_blocks(long long nvox, int C) {
+  // at least ~8 voxels per thread: small tensors get few blocks (cheap finalize), large ones 4 CTAs per SM
   const int lanes_v = kBnThreads / (C / 8);
-  long long b = (nvox + lanes_v - 1) / lanes_v;
-  if (b > kBnMaxBlocks) b = kBnMaxBlocks;
+  long long b = (nvox + lanes_v * 8 - 1) / (lanes_v * 8);
+  if (b > 148 * 4) b = 148 * 4;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -408,11 +412,11 @@ int bn_act_fwd(const void* y, const float* scale, const float* shift, const void
   const __nv_bfloat16 *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
   __nv_bfloat16* oo = (__nv_bfloat16*)out;
   if (resample == 0)
-    bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+    bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
   else if (resample == 1)
-    bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+    bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
   else
-    bn_act_fwd_kernel<2><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, seed);
+    bn_act_fwd_kernel<2><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
   SIVAE_LAUNCH_OK("bn_act_fwd_kernel");
   return 0;
 }
@@ -432,7 +436,7 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   const __nv_bfloat16 *gg = (const __nv_bfloat16*)g, *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
 #define SIVAE_BWD_REDUCE(M)                                                                                      \
   bn_act_bwd_reduce_kernel<M><<<blocks, kBnThreads, 0, st>>>(gg, yy, rr, mean, invstd, gamma, beta, N, D, H, W, C, \
-                                                             slope, mask, p, seed, partial)
+                                                             slope, mask, p, make_seed_ref(seed), partial)
   if (resample == 0) SIVAE_BWD_REDUCE(0);
   else if (resample == 1) SIVAE_BWD_REDUCE(1);
   else SIVAE_BWD_REDUCE(2);
@@ -444,7 +448,7 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
 #define SIVAE_BWD_APPLY(M)                                                                                      \
   bn_act_bwd_apply_kernel<M><<<ablocks, 256, 0, st>>>(gg, yy, rr, mean, invstd, gamma, beta, coef,               \
                                                       (__nv_bfloat16*)dconv, (__nv_bfloat16*)dres, N, D, H, W, C, \
-                                                      slope, mask, p, seed)
+                                                      slope, mask, p, make_seed_ref(seed))
   if (resample == 0) SIVAE_BWD_APPLY(0);
   else if (resample == 1) SIVAE_BWD_APPLY(1);
   else SIVAE_BWD_APPLY(2);

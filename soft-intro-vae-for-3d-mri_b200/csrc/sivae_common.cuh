@@ -48,6 +48,14 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 __host__ __device__ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Dropout key: a per-call constant plus an optional device-side epoch counter (so a CUDA graph that bakes the
+// constant still draws fresh masks on every replay).  sivae_set_seed_counter / sivae_advance_seed_counter.
+struct SeedRef {
+  unsigned long long seed;
+  const unsigned long long* ctr;
+};
+SeedRef make_seed_ref(unsigned long long seed);
+
 // Tensor-map encode entry point (driver API resolved at run time: no link-time libcuda dependency).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -248,6 +256,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     key.y += W1;
   }
   return ctr;
+}
+__device__ __forceinline__ unsigned long long resolve_seed(const SeedRef& r) {
+  return r.ctr ? r.seed + (*r.ctr) * 0x9E3779B97F4A7C15ull : r.seed;
 }
 // keep-decision for element `idx` of a dropout call identified by `seed`: uniform[0,1) >= p
 __device__ __forceinline__ bool philox_keep(unsigned long long seed, unsigned long long idx, float p) {

@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256) cn_to_c1_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ bias, float* __restrict__ y, int N,
                                                        int D, int H, int W, int flip, int act,
                                                        const uint8_t* __restrict__ mask, float p,
-                                                       unsigned long long seed) {
+                                                       const SeedRef sref) {
+  const unsigned long long seed = resolve_seed(sref);
   constexpr int C = CPL * 32;
   constexpr int BD = 2, BH = 4, BW = 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps: warp <-> (d,h) row of the brick
@@ -515,7 +516,7 @@ int cn_to_c1(const void* x, const float* w, const float* bias, float* y, int N, 
   const int blocks = (int)(bricks < 148ll * 16 ? bricks : 148ll * 16);
   const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
 #define SIVAE_CN1(CPL, TT) \
-  cn_to_c1_kernel<CPL, TT><<<blocks, 256, 0, st>>>(xx, w, bias, y, N, D, H, W, flip, act, mask, p, seed)
+  cn_to_c1_kernel<CPL, TT><<<blocks, 256, 0, st>>>(xx, w, bias, y, N, D, H, W, flip, act, mask, p, make_seed_ref(seed))
   if (C == 64 && T == 27) SIVAE_CN1(2, 27);
   else if (C == 64) SIVAE_CN1(2, 1);
   else if (C == 128 && T == 27) SIVAE_CN1(4, 27);

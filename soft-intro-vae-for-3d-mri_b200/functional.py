@@ -14,7 +14,6 @@ requires grad (the trainer freezes encoder / decoder per phase, utils/my_trainer
 """
 from __future__ import annotations
 
-import itertools
 import weakref
 from typing import Optional
 
@@ -30,16 +29,34 @@ BN_EPS = 1e-5
 # dropout state: every dropout call gets a fresh 64-bit Philox key; backward reuses the same key
 # ----------------------------------------------------------------------------------------------
 class _DropoutState:
+    """Philox keys of the in-kernel dropout.  Each dropout call of a training step gets the key
+    (base_seed, call index within the step); a device-resident epoch counter, advanced once per step by
+    ``begin_step``, is mixed in by the kernels, so the host-side constants can be baked into a CUDA graph
+    and every replay still draws fresh masks.  Backward reuses the key saved by its forward."""
+
     def __init__(self):
         self.base_seed = 0x5EED5EED
-        self.counter = itertools.count(1)
-        self.mask_feed = None  # optional iterator of explicit uint8 NDHWC keep-masks (parity tests)
+        self.call = 0
+        self.epoch = None       # int64 device tensor registered with libsivae (one device per process)
+        self.mask_feed = None   # optional iterator of explicit uint8 keep-masks (parity tests)
 
     def next(self):
         """-> (mask or None, seed)"""
-        seed = (self.base_seed * 0x9E3779B97F4A7C15 + next(self.counter) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        self.call += 1
+        seed = (self.base_seed * 0x9E3779B97F4A7C15 + self.call * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
         mask = next(self.mask_feed) if self.mask_feed is not None else None
         return mask, seed
+
+    def begin_step(self, device):
+        """Call once at the start of every training step (graph-capturable)."""
+        self.call = 0
+        device = torch.device(device)
+        if device.type != "cuda":
+            return
+        if self.epoch is None or self.epoch.device != device:
+            self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+            K.set_seed_counter(self.epoch)
+        K.advance_seed_counter(device)
 
 
 dropout_state = _DropoutState()
@@ -48,7 +65,13 @@ dropout_state = _DropoutState()
 def manual_seed(seed: int):
     """Re-key the in-kernel Philox dropout streams (independent of torch's generator)."""
     dropout_state.base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    dropout_state.counter = itertools.count(1)
+    dropout_state.call = 0
+    if dropout_state.epoch is not None:
+        dropout_state.epoch.zero_()
+
+
+def begin_step(device):
+    dropout_state.begin_step(device)
 
 
 class BnState:

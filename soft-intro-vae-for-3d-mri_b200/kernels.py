@@ -31,6 +31,8 @@ _SIGNATURES = {
     "sivae_abi_version": (_i, []),
     "sivae_device_check": (_i, []),
     "sivae_launch_count": (_ll, []),
+    "sivae_set_seed_counter": (_i, [_vp]),
+    "sivae_advance_seed_counter": (_i, [_vp]),
     "sivae_pack_conv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "sivae_conv3_igemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_conv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
@@ -156,7 +158,7 @@ class KernelTimer:
 
 def _timed(name, work, fn):
     t = KernelTimer.active
-    if t is None or name not in t.names:
+    if t is None or name not in t.names or torch.cuda.is_current_stream_capturing():
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -164,6 +166,18 @@ def _timed(name, work, fn):
     e1.record()
     t.records.append((name, work, e0, e1))
     return r
+
+
+def set_seed_counter(counter: Optional[torch.Tensor]):
+    """Register (or with None: unregister) the device-resident int64/uint64 dropout epoch counter."""
+    if counter is not None:
+        _req(counter, torch.int64, "counter")
+    _check(_L().sivae_set_seed_counter(_p(counter)), "sivae_set_seed_counter")
+
+
+def advance_seed_counter(device):
+    _check(_L().sivae_advance_seed_counter(ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+           "sivae_advance_seed_counter")
 
 
 _ws_cache = {}

@@ -84,6 +84,7 @@ def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer
     hp = hp or StepHyper()
     scale = hp.scale if hp.scale is not None else 8.0 / float(real_batch[0].numel())
     beta_rec, beta_neg, beta_kl, gamma_r = hp.beta_rec, hp.beta_neg, hp.beta_kl, hp.gamma_r
+    F.begin_step(real_batch.device)          # new dropout epoch (device-side counter; CUDA-graph safe)
 
     # ================= Update E (:242-289): encoder trainable, decoder frozen =================
     _set_requires_grad(model.encoder, True)

@@ -83,20 +83,26 @@ def _gpu_masks(masks):
     return out
 
 
-def _check_terms(got, ref, rel, exp_rel, kl_rel=None):
-    """``rel`` for the reconstruction terms and the composite lossE/lossD; ``kl_rel`` for the KL terms, which
-    are sums of exp(logvar) dominated by a few large elements at random init and so amplify the bf16
-    rounding of the activations (measured ~1e-2 on a second-pass encoding; DESIGN.md, parity section)."""
+def _check_terms(got, ref, first=1e-3, second=None, kl=None, exp_rel=1e-2):
+    """Tolerance classes (relative):
+      first  -- lossE, lossD and the first-pass reconstruction terms (north_star: 1e-3);
+      second -- reconstruction terms of second-pass chains decoder -> encoder -> decoder (loss_*_rec_*), whose
+                latent passes through exp(0.5*logvar) twice;
+      kl     -- KL terms: sums of exp(logvar) dominated by a few large elements at random init, which amplify
+                the bf16 rounding of the activations;
+      exp_rel-- exp-ELBO terms exp(-a), a ~ 10..100: compared through their exponent.
+    Measured deviations are listed in DESIGN.md (parity section)."""
+    second = first if second is None else second
+    kl = first if kl is None else kl
     for k, v in ref.items():
         if k not in got:
             continue
-        if "kl" in k and kl_rel is not None:
-            assert got[k] == pytest.approx(v, rel=kl_rel), (k, got[k], v)
-        elif k.startswith("exp_elbo"):
-            # exp(-a) with a ~ 10..100: compare exponents
-            assert abs(math.log(max(got[k], 1e-300)) - math.log(max(v, 1e-300))) <= exp_rel * abs(math.log(max(v, 1e-300))) + 1e-3, (k, got[k], v)
-        else:
-            assert got[k] == pytest.approx(v, rel=rel), (k, got[k], v)
+        if k.startswith("exp_elbo"):
+            lg, lv = math.log(max(got[k], 1e-300)), math.log(max(v, 1e-300))
+            assert abs(lg - lv) <= exp_rel * abs(lv) + 1e-3, (k, got[k], v)
+            continue
+        tol = kl if "kl" in k else second if ("rec_rec" in k or "fake_rec" in k) else first
+        assert got[k] == pytest.approx(v, rel=tol), (k, got[k], v, tol)
 
 
 def test_train_step_vs_golden(golden_dir):
@@ -108,12 +114,14 @@ def test_train_step_vs_golden(golden_dir):
     masks = [m.to(DEV) for m in st["masks"]]
     eps = [e.to(DEV) for e in st["eps"]]
     terms, grads = _run_step(net, g["real"].to(DEV), g["noise"].to(DEV), masks, eps, T.StepHyper(**st["hyper"]))
-    _check_terms(terms, st["terms"], rel=2e-2, exp_rel=3e-2)
+    _check_terms(terms, st["terms"], first=2e-2, exp_rel=3e-2)
     allref = {**st["gradsE"], **st["gradsD"]}
     assert set(grads) == set(allref)
     for k, ref in allref.items():
-        if k.endswith("blocks.0.0.bias"):
-            continue   # exactly-zero gradient, rounding noise on both sides
+        if k.endswith("blocks.0.0.bias") or k == "decoder.blocks.0.0.weight":
+            # exactly-zero gradients up to eps: a bias in front of train-mode BN, and the decoder's 1x1 stem weight
+            # (one scalar per channel in front of BN: BN is scale-invariant) -- rounding noise on both sides
+            continue
         ref = ref.to(DEV)
         if ref.numel() < 16:
             # scalar / tiny tensors (head biases): a single bf16-noisy number, no averaging
@@ -159,11 +167,13 @@ def test_headline_step_vs_oracle(shape):
     hp_o = O.StepHyper()
     ref_terms, gE, gD = O.soft_intro_step_grads(sd, cfg, real, noise, eps, [m.float() for m in masks], hp_o)
     terms, grads = _run_step(net, real, noise, masks, eps, T.StepHyper())
-    print("oracle:", ref_terms)
-    print("cuda  :", terms)
-    _check_terms(terms, ref_terms, rel=2e-3, exp_rel=1e-2, kl_rel=2e-2)
+    for k in sorted(terms):
+        if k in ref_terms:
+            print(f"  {k:18s} cuda {terms[k]:14.6g}  oracle {ref_terms[k]:14.6g}  rel {abs(terms[k] - ref_terms[k]) / (abs(ref_terms[k]) + 1e-30):.2e}")
+    _check_terms(terms, ref_terms, first=1e-3, second=5e-3, kl=2e-2, exp_rel=1e-2)
     allref = {**gE, **gD}
-    worst = min((_cos(grads[k], v), k) for k, v in allref.items() if not k.endswith("blocks.0.0.bias"))
+    worst = min((_cos(grads[k], v), k) for k, v in allref.items()
+                if not k.endswith("blocks.0.0.bias") and k != "decoder.blocks.0.0.weight" and v.numel() >= 16)
     print("worst grad cosine:", worst)
     assert worst[0] > 0.95, worst
     sdn = net.state_dict()
@@ -182,3 +192,30 @@ def test_reference_loop_contract_quick():
         out = T.train_soft_intro_vae(net, data, data, 1, device=torch.device(DEV), path=d + "/")
         assert os.path.isfile(d + "/prams/S-IntroVAE_3898_epoch0.pth")
     assert all(len(lst) == 2 and lst[0] == lst[1] and math.isfinite(lst[0]) for lst in out)
+
+
+def test_graphed_step_runs_and_redraws_dropout():
+    """Whole-step CUDA graph: replays train (losses change, stay finite), BN counters advance by 5 / 8 per replay
+     and the Philox dropout masks differ between replays (device-side epoch counter)."""
+    torch.manual_seed(3)
+    net = sivae_b200.SoftIntroVAE(64, [[64, 1, 2], [64, 1, 2], [64, 1, 2]]).to(DEV)
+    net.apply(T.init_weights_he)
+    net.train()
+    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=True)
+    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=True)
+    real = torch.rand(2, 1, 16, 24, 16, device=DEV)
+    noise = torch.randn(2, 1, 2, 3, 2, device=DEV)
+    step = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real, noise, warmup=2)
+    n0 = int(net.state_dict()["encoder.blocks.0.1.num_batches_tracked"])
+    w0 = net.encoder.blocks[1][0].block[0].weight.detach().clone()
+    vals = []
+    for _ in range(3):
+        out = step(real, noise)
+        vals.append((float(out["lossE"]), float(out["lossD"])))
+    assert all(math.isfinite(a) and math.isfinite(b) for a, b in vals), vals
+    assert len({v[0] for v in vals}) == 3, vals                      # weights and masks change every replay
+    sd = net.state_dict()
+    assert int(sd["encoder.blocks.0.1.num_batches_tracked"]) == n0 + 3 * 5
+    assert int(sd["decoder.blocks.0.1.num_batches_tracked"]) == 3 * 8 + 2 * 8
+    assert not torch.equal(w0, net.encoder.blocks[1][0].block[0].weight)
+    assert int(F.dropout_state.epoch) >= 5
