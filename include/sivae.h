@@ -73,6 +73,25 @@ int sivae_conv3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw,
                       void* workspace, size_t workspace_bytes,
                       int N, int D, int H, int W, int Cin, int Cout, void* stream);
 
+/* nn.Upsample(scale_factor=2, nearest) followed by the 3x3x3 convolution (UpsampleBuildingkBlock, models/models.py:58-59)
+ * WITHOUT materialising the upsampled tensor: an output voxel (2d+pd, 2h+ph, 2w+pw) sees only 2x2x2 distinct low-res
+ * inputs, so each of the 8 output parities is an 8-tap convolution on the low-res grid with pre-summed weights
+ * (27 -> 8 multiply-accumulates per output; exact in real arithmetic, weights are summed in fp32 before the bf16 cast).
+ *   x_lo  [N][D][H][W][Cin],  y_hi / dy_hi [N][2D][2H][2W][Cout]   (D, H, W are the LOW-resolution extents)
+ *   wup  bf16 [64 = parity*8 + abc][Cout][Cin],  wupT bf16 [64][Cin][Cout]   (from sivae_pack_upconv3_weights)
+ * fprop:  y_hi = conv3(upsample2(x_lo), w)
+ * dgrad:  dx_lo = upsample2^T(conv3^T(dy_hi))       (what autograd computes through Upsample + Conv3d)
+ * wgrad:  dw fp32 [Cout][Cin][3][3][3] = conv3 weight gradient with input upsample2(x_lo) and output gradient dy_hi */
+int sivae_pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup_bf16, void* wupT_bf16, void* stream);
+int sivae_upconv3_fprop(const void* x_lo_bf16, const void* wup_bf16, void* y_hi_bf16,
+                        int N, int D, int H, int W, int Cin, int Cout, void* stream);
+int sivae_upconv3_dgrad(const void* dy_hi_bf16, const void* wupT_bf16, void* dx_lo_bf16,
+                        int N, int D, int H, int W, int Cin, int Cout, void* stream);
+size_t sivae_upconv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
+int sivae_upconv3_wgrad(const void* x_lo_bf16, const void* dy_hi_bf16, float* dw,
+                        void* workspace, size_t workspace_bytes,
+                        int N, int D, int H, int W, int Cin, int Cout, void* stream);
+
 /* Single-output-channel 3x3x3 convolution on tcgen05 (N=16 accumulator tile, column 0 used), fp32 output with the
  * epilogue fused:   y[v] = act( bias[0] + sum_{tap,c} w[c][tap'] * x[v + delta(tap)][c] ),  tap' = flip ? 26-tap : tap.
  * Decoder tail Conv3d(C,1,3)+ReLU+Dropout(.35) (models/models.py:137-140; act=1) and the input gradient of the

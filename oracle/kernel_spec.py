@@ -67,6 +67,64 @@ def conv3_wgrad(x, dy):
     return torch.nn.grad.conv3d_weight(xi, (co, ci, 3, 3, 3), g, stride=1, padding=1)
 
 
+def _up_tapset(p, a):
+    """3x3x3 taps (per axis) that land on low-res offset index a for output parity p."""
+    return ([0], [1, 2])[a] if p == 0 else ([0, 1], [2])[a]
+
+
+def pack_upconv3_weights(w):
+    co, ci = w.shape[:2]
+    wup = torch.zeros(64, co, ci, dtype=torch.float32, device=w.device)
+    for p in range(8):
+        pd, ph, pw = p >> 2, (p >> 1) & 1, p & 1
+        for abc in range(8):
+            a, b, c = abc >> 2, (abc >> 1) & 1, abc & 1
+            acc = 0
+            for kd in _up_tapset(pd, a):
+                for kh in _up_tapset(ph, b):
+                    for kw in _up_tapset(pw, c):
+                        acc = acc + w[:, :, kd, kh, kw]
+            wup[p * 8 + abc] = acc
+    return wup.to(ACT_DTYPE), wup.transpose(1, 2).contiguous().to(ACT_DTYPE)
+
+
+def _upconv3_fprop_f32(x_lo, wup):
+    n, d, h, w, ci = x_lo.shape
+    co = wup.shape[1]
+    xp = F.pad(x_lo.float(), (0, 0, 1, 1, 1, 1, 1, 1))
+    y = torch.zeros(n, 2 * d, 2 * h, 2 * w, co, dtype=torch.float32, device=x_lo.device)
+    for p in range(8):
+        pd, ph, pw = p >> 2, (p >> 1) & 1, p & 1
+        acc = 0
+        for abc in range(8):
+            a, b, c = abc >> 2, (abc >> 1) & 1, abc & 1
+            od, oh, ow = a - 1 + pd, b - 1 + ph, c - 1 + pw
+            xs = xp[:, 1 + od:1 + od + d, 1 + oh:1 + oh + h, 1 + ow:1 + ow + w]
+            acc = acc + xs @ wup[p * 8 + abc].float().t()
+        y[:, pd::2, ph::2, pw::2] = acc
+    return y
+
+
+def upconv3_fprop(x_lo, wup):
+    return _upconv3_fprop_f32(x_lo, wup).to(x_lo.dtype)
+
+
+def upconv3_dgrad(dy_hi, wupT):
+    n, d2, h2, w2, co = dy_hi.shape
+    ci = wupT.shape[1]
+    with torch.enable_grad():
+        x = torch.zeros(n, d2 // 2, h2 // 2, w2 // 2, ci, dtype=torch.float32, device=dy_hi.device, requires_grad=True)
+        y = _upconv3_fprop_f32(x, wupT.transpose(1, 2))
+        (g,) = torch.autograd.grad(y, x, dy_hi.float())
+    return g.to(dy_hi.dtype)
+
+
+def upconv3_wgrad(x_lo, dy_hi):
+    xu = x_lo.float().repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    xi, g = xu.permute(0, 4, 1, 2, 3), dy_hi.float().permute(0, 4, 1, 2, 3)
+    return torch.nn.grad.conv3d_weight(xi, (g.shape[1], xi.shape[1], 3, 3, 3), g, stride=1, padding=1)
+
+
 def bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps):
     c = y.shape[-1]
     f = y.float().reshape(-1, c)

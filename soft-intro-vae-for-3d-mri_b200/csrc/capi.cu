@@ -65,6 +65,11 @@ int conv3_igemm(const void*, const void*, void*, int, int, int, int, int, int, c
 size_t conv3_wgrad_workspace_bytes(int, int, int, int, int, int);
 int conv3_wgrad(const void*, const void*, float*, void*, size_t, int, int, int, int, int, int, cudaStream_t);
 int pack_conv3_weights(const float*, int, int, void*, void*, cudaStream_t);
+int upconv3_fprop(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int upconv3_dgrad(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+size_t upconv3_wgrad_workspace_bytes(int, int, int, int, int, int);
+int upconv3_wgrad(const void*, const void*, float*, void*, size_t, int, int, int, int, int, int, cudaStream_t);
+int pack_upconv3_weights(const float*, int, int, void*, void*, cudaStream_t);
 size_t conv3_to1_workspace_bytes(int);
 int conv3_to1(const void*, const float*, const float*, float*, int, int, int, int, int, int, int, const uint8_t*, float,
               unsigned long long, void*, size_t, cudaStream_t);
@@ -142,6 +147,24 @@ size_t sivae_conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, in
 int sivae_conv3_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
                       int Cin, int Cout, void* stream) {
   return conv3_wgrad(x, dy, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, ST(stream));
+}
+int sivae_pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wupT, void* stream) {
+  return pack_upconv3_weights(w, Cout, Cin, wup, wupT, ST(stream));
+}
+int sivae_upconv3_fprop(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin, int Cout,
+                        void* stream) {
+  return upconv3_fprop(x_lo, wup, y_hi, N, D, H, W, Cin, Cout, ST(stream));
+}
+int sivae_upconv3_dgrad(const void* dy_hi, const void* wupT, void* dx_lo, int N, int D, int H, int W, int Cin, int Cout,
+                        void* stream) {
+  return upconv3_dgrad(dy_hi, wupT, dx_lo, N, D, H, W, Cin, Cout, ST(stream));
+}
+size_t sivae_upconv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+  return upconv3_wgrad_workspace_bytes(N, D, H, W, Cin, Cout);
+}
+int sivae_upconv3_wgrad(const void* x_lo, const void* dy_hi, float* dw, void* ws, size_t ws_bytes, int N, int D, int H,
+                        int W, int Cin, int Cout, void* stream) {
+  return upconv3_wgrad(x_lo, dy_hi, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, ST(stream));
 }
 size_t sivae_conv3_to1_workspace_bytes(int C) { return conv3_to1_workspace_bytes(C); }
 int sivae_conv3_to1(const void* x, const float* w, const float* bias, float* y, int N, int D, int H, int W, int C,

@@ -25,7 +25,23 @@ struct ConvGeom {
   int wt, ht, dt;  // box extents of one tile of output voxels
   int tiles_w, tiles_h, tiles_d;
   int rows;        // wt*ht*dt  (<= 128)
-  int cin_blocks;  // Cin / 64
+  int cin_blocks;  // (GEMM-K channels) / 64
+  int mode;        // kTapsPlain / kTapsUpFprop / kTapsUpDgrad
+};
+
+// Tap schedules of the implicit GEMM.
+//   kTapsPlain   : 27 taps, offsets (kd-1, kh-1, kw-1), weights wpack[tap].
+//   kTapsUpFprop : nearest-Upsample(2) folded into the convolution (nn.Upsample models/models.py:58 followed by
+//                  Conv3d :59).  Output voxel (2d+pd, 2h+ph, 2w+pw) only sees 2x2x2 distinct low-resolution inputs, so
+//                  each of the 8 output parities (blockIdx.z) is an 8-tap convolution on the low-res grid with
+//                  pre-summed weights wpack[parity*8 + abc] and offsets (a-1+pd, b-1+ph, c-1+pw); it stores to the
+//                  parity sub-lattice of the high-res output (tensor map tmC.m[parity]).  27 -> 8 MACs per output.
+//   kTapsUpDgrad : the transpose: dX_low = sum over 8 parities x 8 taps of dY on the parity sub-lattice
+//                  (tensor map tmA.m[parity]) at offsets -(a-1+pd), ... with weights wpack[parity*8 + abc] (transposed).
+static constexpr int kTapsPlain = 0, kTapsUpFprop = 1, kTapsUpDgrad = 2;
+
+struct TmapPack {
+  CUtensorMap m[8];
 };
 
 template <class Geom>
@@ -58,8 +74,8 @@ struct ToOneEpilogue {
 
 template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(192)
-conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmC, const ConvGeom g, const ToOneEpilogue ep) {
+conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ TmapPack tmC, const ConvGeom g, const ToOneEpilogue ep) {
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = kTileBytes + B_BYTES;
@@ -75,12 +91,14 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   int w0, h0, d0, n;
   decode_tile(g, blockIdx.x, w0, h0, d0, n);
   const int nb = blockIdx.y;
-  const int num_kb = 27 * g.cin_blocks;
+  const int parity = blockIdx.z;   // kTapsUpFprop only (gridDim.z == 8), else 0
+  const int ntaps = g.mode == kTapsPlain ? 27 : g.mode == kTapsUpFprop ? 8 : 64;
+  const int num_kb = ntaps * g.cin_blocks;
 
   if (warp_id == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmA.m[0]);
     prefetch_tmap(&tmB);
-    prefetch_tmap(&tmC);
+    prefetch_tmap(&tmC.m[parity]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -104,10 +122,21 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], tx_bytes);
         const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        int od, oh, ow, wtap = tap;
+        const CUtensorMap* amap = &tmA.m[0];
+        if (g.mode == kTapsPlain) {
+          od = tap / 9 - 1; oh = (tap / 3) % 3 - 1; ow = tap % 3 - 1;
+        } else if (g.mode == kTapsUpFprop) {
+          od = (tap >> 2) - 1 + (parity >> 2); oh = ((tap >> 1) & 1) - 1 + ((parity >> 1) & 1); ow = (tap & 1) - 1 + (parity & 1);
+          wtap = parity * 8 + tap;
+        } else {
+          const int pp = tap >> 3, abc = tap & 7;
+          od = -((abc >> 2) - 1 + (pp >> 2)); oh = -(((abc >> 1) & 1) - 1 + ((pp >> 1) & 1)); ow = -((abc & 1) - 1 + (pp & 1));
+          amap = &tmA.m[pp];
+        }
         uint8_t* a_dst = smem + s * STAGE_BYTES;
-        tma_load_5d(a_dst, &tmA, &full_bar[s], cb * 64, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, n);
-        tma_load_3d(a_dst + kTileBytes, &tmB, &full_bar[s], cb * 64, nb * BLOCK_N, tap);
+        tma_load_5d(a_dst, amap, &full_bar[s], cb * 64, w0 + ow, h0 + oh, d0 + od, n);
+        tma_load_3d(a_dst + kTileBytes, &tmB, &full_bar[s], cb * 64, nb * BLOCK_N, wtap);
       }
     }
   } else if (warp_id == 1) {
@@ -144,7 +173,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int w = w0 + row % g.wt, h = h0 + (row / g.wt) % g.ht, d = d0 + row / (g.wt * g.ht);
       if (row < g.rows && w < g.W && h < g.H && d < g.D) {
         const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-        float r = __uint_as_float(v[0]) + (ep.bias ? ep.bias[0] : 0.f);
+        float r = (__uint_as_float(v[0]) + __uint_as_float(v[1])) + (ep.bias ? ep.bias[0] : 0.f);
         if (ep.act == 1) {
           r = fmaxf(r, 0.f);
           const float inv_keep = 1.f / (1.f - ep.p);
@@ -177,7 +206,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp_id == 2 && lane == 0) {
 #pragma unroll
       for (int jb = 0; jb < BLOCK_N / 64; ++jb)
-        tma_store_5d(&tmC, out_stage + jb * kTileBytes, nb * BLOCK_N + jb * 64, w0, h0, d0, n);
+        tma_store_5d(&tmC.m[parity], out_stage + jb * kTileBytes, nb * BLOCK_N + jb * 64, w0, h0, d0, n);
       tma_store_commit();
       tma_store_wait_all();
     }
@@ -192,23 +221,26 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // wgrad
 // =================================================================================================
 struct WgradGeom {
-  int N, D, H, W;
+  int N, D, H, W;       // lattice of the GEMM-K voxels (low-res grid in the upsample-fused mode)
   int wt, ht, dt, tiles_w, tiles_h, tiles_d;
   int rows;             // voxel rows per box (<= 128); consumed in 16-row K steps, tail rows zeroed
   int cin_blocks;       // Cin/64
-  int units;            // 27 * cin_blocks   (one unit = one tap x one 64-wide Cin block)
-  int pairs_total;      // ceil(units/2)
+  int mode;             // kTapsPlain, or kTapsUpFprop (upsample folded in: 8 parity classes x 8 taps)
+  int nclasses;         // 1 (plain) or 8 (output parities); all units of a CTA share the dy operand of one class
+  int units_pc;         // units per class: taps(27|8) * cin_blocks   (one unit = one tap x one 64-wide Cin block)
+  int pairs_pc;         // ceil(units_pc/2)
   int ppc;              // unit pairs accumulated per CTA (TMEM: ppc * NT columns)
-  int groups;           // ceil(pairs_total / ppc)
+  int groups_pc;        // ceil(pairs_pc / ppc)
+  int units;            // nclasses * units_pc
   int Cout;
-  long long total_kb;   // voxel boxes in the whole tensor
+  long long total_kb;   // voxel boxes in the whole lattice
   long long kb_per_split;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor strides (bytes), see make_smem_desc
 };
 
 template <int NT, int A_STAGES>
 __global__ void __launch_bounds__(192, 1)
-conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ TmapPack tmDY,
                    const WgradGeom g, float* __restrict__ partial) {
   constexpr int B_STAGES = 2;
   constexpr int B_STAGE_BYTES = (NT / 64) * kTileBytes;
@@ -226,16 +258,18 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int grp = blockIdx.x % g.groups;
-  const int ntile = blockIdx.x / g.groups;
-  const int pair0 = grp * g.ppc;
-  const int npairs = min(g.ppc, g.pairs_total - pair0);
+  const int groups_all = g.groups_pc * g.nclasses;
+  const int grp_all = blockIdx.x % groups_all;
+  const int ntile = blockIdx.x / groups_all;
+  const int cls = grp_all / g.groups_pc;
+  const int pair0 = (grp_all % g.groups_pc) * g.ppc;
+  const int npairs = min(g.ppc, g.pairs_pc - pair0);
   const long long kb0 = (long long)blockIdx.y * g.kb_per_split;
   const long long kb1 = min(g.total_kb, kb0 + g.kb_per_split);
 
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmX);
-    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmDY.m[cls]);
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
@@ -278,22 +312,27 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           mbar_expect_tx(&b_full[s], tile_tx * (NT / 64));
 #pragma unroll
           for (int jc = 0; jc < NT / 64; ++jc)
-            tma_load_5d(smem_b + s * B_STAGE_BYTES + jc * kTileBytes, &tmDY, &b_full[s], ntile * NT + jc * 64, w0, h0,
-                        d0, n);
+            tma_load_5d(smem_b + s * B_STAGE_BYTES + jc * kTileBytes, &tmDY.m[cls], &b_full[s], ntile * NT + jc * 64, w0,
+                        h0, d0, n);
           ++b_it;
         }
         for (int lp = 0; lp < npairs; ++lp) {
           const int s = a_it % A_STAGES;
           mbar_wait(&a_empty[s], ((a_it / A_STAGES) & 1u) ^ 1u);
           const int u0 = 2 * (pair0 + lp);
-          const int nu = (u0 + 1 < g.units) ? 2 : 1;
+          const int nu = (u0 + 1 < g.units_pc) ? 2 : 1;
           mbar_expect_tx(&a_full[s], tile_tx * nu);
           for (int uu = 0; uu < nu; ++uu) {
             const int u = u0 + uu;
             const int tap = u / g.cin_blocks, cb = u - tap * g.cin_blocks;
-            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            tma_load_5d(smem_a + s * A_STAGE_BYTES + uu * kTileBytes, &tmX, &a_full[s], cb * 64, w0 + kw - 1,
-                        h0 + kh - 1, d0 + kd - 1, n);
+            int od, oh, ow;
+            if (g.mode == kTapsPlain) {
+              od = tap / 9 - 1; oh = (tap / 3) % 3 - 1; ow = tap % 3 - 1;
+            } else {
+              od = (tap >> 2) - 1 + (cls >> 2); oh = ((tap >> 1) & 1) - 1 + ((cls >> 1) & 1); ow = (tap & 1) - 1 + (cls & 1);
+            }
+            tma_load_5d(smem_a + s * A_STAGE_BYTES + uu * kTileBytes, &tmX, &a_full[s], cb * 64, w0 + ow, h0 + oh,
+                        d0 + od, n);
           }
           ++a_it;
         }
@@ -334,7 +373,8 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int q = warp_id & 3;
     const int row = q * 32 + lane;
     for (int lp = 0; lp < npairs; ++lp) {
-      const int unit = 2 * (pair0 + lp) + (row >> 6);
+      const int ul = 2 * (pair0 + lp) + (row >> 6);          // unit within the class
+      const int unit = cls * g.units_pc + ul;
       const int ci_in = row & 63;
       float* dst = partial + (((long long)blockIdx.y * g.units + unit) * 64 + ci_in) * g.Cout + ntile * NT;
 #pragma unroll 1
@@ -342,7 +382,7 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(lp * NT + j * 32), v);
         tmem_ld_wait();
-        if (unit < g.units) {
+        if (ul < g.units_pc) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(dst + j * 32 + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
@@ -353,6 +393,32 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp_id == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// upsample-fused mode: dw[co][ci][k] = sum_s sum_parity partial[s][(parity*8 + abc(k,parity))*cin_blocks + ci/64][ci%64][co]
+// (the transpose of the weight pre-summation: every 3x3x3 tap receives exactly one contribution per output parity)
+__global__ void wgrad_reduce_up_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
+                                       int cin_blocks, int Cin, int Cout) {
+  const long long per_split = 64ll * cin_blocks * 64 * Cout;
+  const long long total = 27ll * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int k = (int)(i / ((long long)Cout * Cin));
+    const int kd = k / 9, kh = (k / 3) % 3, kw = k % 3;
+    const int cb = ci >> 6, ci_in = ci & 63;
+    float acc = 0.f;
+    for (int p = 0; p < 8; ++p) {
+      const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+      const int a = pd == 0 ? (kd == 0 ? 0 : 1) : (kd == 2 ? 1 : 0);
+      const int b = ph == 0 ? (kh == 0 ? 0 : 1) : (kh == 2 ? 1 : 0);
+      const int c = pw == 0 ? (kw == 0 ? 0 : 1) : (kw == 2 ? 1 : 0);
+      const int unit = (p * 8 + (a << 2 | b << 1 | c)) * cin_blocks + cb;
+      const float* src = partial + ((long long)unit * 64 + ci_in) * Cout + co;
+      for (int s = 0; s < splits; ++s) acc += src[(long long)s * per_split];
+    }
+    dw[((long long)co * Cin + ci) * 27 + k] = acc;
+  }
 }
 
 // dw[co][ci][tap] = sum_s partial[s][tap*cin_blocks + ci/64][ci%64][co]
@@ -419,7 +485,7 @@ static int make_act_tmap(CUtensorMap* tm, const void* base, int N, int D, int H,
 }
 
 template <int BLOCK_N, int STAGES, int EPI>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGeom& g,
+static int launch_igemm(const TmapPack& tmA, const CUtensorMap& tmB, const TmapPack& tmC, const ConvGeom& g,
                         long long tiles, int nblocks, const ToOneEpilogue& ep, cudaStream_t st) {
   constexpr int smem = STAGES * (kTileBytes + BLOCK_N * 128) + 1024 + 256;
   static bool attr_set = false;
@@ -430,10 +496,40 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
       return -1;
     attr_set = true;
   }
-  dim3 grid((unsigned)tiles, (unsigned)nblocks);
+  dim3 grid((unsigned)tiles, (unsigned)nblocks, g.mode == kTapsUpFprop ? 8u : 1u);
   conv3_igemm_kernel<BLOCK_N, STAGES, EPI><<<grid, 192, smem, st>>>(tmA, tmB, tmC, g, ep);
   SIVAE_LAUNCH_OK("conv3_igemm_kernel");
   return 0;
+}
+
+static void fill_geom(ConvGeom& g, int N, int D, int H, int W, int kch, int mode) {
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  pick_tile(W, H, D, 1, false, g.wt, g.ht, g.dt);
+  g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
+  g.rows = g.wt * g.ht * g.dt;
+  g.cin_blocks = kch / 64;
+  g.mode = mode;
+}
+
+// tensor map of the parity-(pd,ph,pw) sub-lattice of a high-res NDHWC tensor [N][2D][2H][2W][C], seen as [N][D][H][W][C]
+static int make_parity_tmap(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int C, int parity, int wt,
+                            int ht, int dt) {
+  const int pd = parity >> 2, ph = (parity >> 1) & 1, pw = parity & 1;
+  const uint64_t row = (uint64_t)C * 2;                 // bytes per voxel
+  const uint64_t sw = 2 * row, sh = 2 * (2ull * W) * row, sd = 2 * (2ull * H) * (2ull * W) * row;
+  const uint64_t sn = (2ull * D) * (2ull * H) * (2ull * W) * row;
+  const uint8_t* b = (const uint8_t*)base + (((uint64_t)pd * (2ull * H) + ph) * (2ull * W) + pw) * row;
+  uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+  uint64_t strides[4] = {sw, sh, sd, sn};
+  uint32_t box[5] = {64, (uint32_t)wt, (uint32_t)ht, (uint32_t)dt, 1};
+  return make_tmap_bf16(tm, b, 5, dims, strides, box);
+}
+
+static int make_weight_tmap(CUtensorMap* tm, const void* wpack, int taps, int rows, int kch, int block_n) {
+  uint64_t dims[3] = {(uint64_t)kch, (uint64_t)rows, (uint64_t)taps};
+  uint64_t strides[2] = {(uint64_t)kch * 2, (uint64_t)rows * kch * 2};
+  uint32_t box[3] = {64, (uint32_t)block_n, 1};
+  return make_tmap_bf16(tm, wpack, 3, dims, strides, box);
 }
 
 int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
@@ -442,34 +538,120 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
   ConvGeom g;
-  g.N = N; g.D = D; g.H = H; g.W = W;
-  pick_tile(W, H, D, 1, false, g.wt, g.ht, g.dt);
-  g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
-  g.rows = g.wt * g.ht * g.dt;
-  g.cin_blocks = Cin / 64;
+  fill_geom(g, N, D, H, W, Cin, kTapsPlain);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
   SIVAE_CHECK(tiles < (1ll << 31), "conv3_igemm: too many tiles");
   const int block_n = (Cout % 128 == 0) ? 128 : 64;
-  CUtensorMap tmA, tmB, tmC;
-  if (make_act_tmap(&tmA, x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
-  if (make_act_tmap(&tmC, y, N, D, H, W, Cout, g.wt, g.ht, g.dt)) return -1;
-  {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 27};
-    uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-    uint32_t box[3] = {64, (uint32_t)block_n, 1};
-    if (make_tmap_bf16(&tmB, wpack, 3, dims, strides, box)) return -1;
-  }
+  TmapPack tmA, tmC;
+  CUtensorMap tmB;
+  if (make_act_tmap(&tmA.m[0], x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
+  if (make_act_tmap(&tmC.m[0], y, N, D, H, W, Cout, g.wt, g.ht, g.dt)) return -1;
+  for (int i = 1; i < 8; ++i) { tmA.m[i] = tmA.m[0]; tmC.m[i] = tmC.m[0]; }
+  if (make_weight_tmap(&tmB, wpack, 27, Cout, Cin, block_n)) return -1;
   const ToOneEpilogue ep{};
   if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
   return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
 }
 
-// fp32 [C][27] (one output channel) -> bf16 [27][16][C]; row 0 = the filter (tap-flipped when `flip`), rows 1..15 zero
+// y_hi[n, 2d+pd, 2h+ph, 2w+pw, co] = conv3(upsample2(x_lo), w):  8 parity-specific 2x2x2 convolutions on the low-res grid.
+// x_lo [N][D][H][W][Cin], wup bf16 [64 = parity*8+abc][Cout][Cin], y_hi [N][2D][2H][2W][Cout].
+int upconv3_fprop(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin, int Cout,
+                  cudaStream_t st) {
+  SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
+              "upconv3_fprop: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
+  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "upconv3_fprop: empty tensor");
+  ConvGeom g;
+  fill_geom(g, N, D, H, W, Cin, kTapsUpFprop);
+  const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
+  SIVAE_CHECK(tiles < (1ll << 31), "upconv3_fprop: too many tiles");
+  const int block_n = (Cout % 128 == 0) ? 128 : 64;
+  TmapPack tmA, tmC;
+  CUtensorMap tmB;
+  if (make_act_tmap(&tmA.m[0], x_lo, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
+  for (int i = 1; i < 8; ++i) tmA.m[i] = tmA.m[0];
+  for (int p = 0; p < 8; ++p)
+    if (make_parity_tmap(&tmC.m[p], y_hi, N, D, H, W, Cout, p, g.wt, g.ht, g.dt)) return -1;
+  if (make_weight_tmap(&tmB, wup, 64, Cout, Cin, block_n)) return -1;
+  const ToOneEpilogue ep{};
+  if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
+  return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
+}
+
+// dx_lo = upsample2^T(conv3^T(dy_hi)):  one 64-tap (8 parities x 8 taps) implicit GEMM gathering dy on its parity
+// sub-lattices.  dy_hi [N][2D][2H][2W][Cout], wupT bf16 [64][Cin][Cout], dx_lo [N][D][H][W][Cin]  (D,H,W low-res).
+int upconv3_dgrad(const void* dy_hi, const void* wupT, void* dx_lo, int N, int D, int H, int W, int Cin, int Cout,
+                  cudaStream_t st) {
+  SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
+              "upconv3_dgrad: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
+  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "upconv3_dgrad: empty tensor");
+  ConvGeom g;
+  fill_geom(g, N, D, H, W, Cout, kTapsUpDgrad);
+  const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
+  SIVAE_CHECK(tiles < (1ll << 31), "upconv3_dgrad: too many tiles");
+  const int block_n = (Cin % 128 == 0) ? 128 : 64;
+  TmapPack tmA, tmC;
+  CUtensorMap tmB;
+  for (int p = 0; p < 8; ++p)
+    if (make_parity_tmap(&tmA.m[p], dy_hi, N, D, H, W, Cout, p, g.wt, g.ht, g.dt)) return -1;
+  if (make_act_tmap(&tmC.m[0], dx_lo, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
+  for (int i = 1; i < 8; ++i) tmC.m[i] = tmC.m[0];
+  if (make_weight_tmap(&tmB, wupT, 64, Cin, Cout, block_n)) return -1;
+  const ToOneEpilogue ep{};
+  if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cin / 128, ep, st);
+  return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cin / 64, ep, st);
+}
+
+// fp32 [Cout][Cin][27] -> bf16 wup[parity*8+abc][Cout][Cin] and wupT[parity*8+abc][Cin][Cout]: per axis and output
+// parity p the three taps collapse onto two low-res offsets, p=0: {k0}, {k1+k2};  p=1: {k0+k1}, {k2}.
+__global__ void pack_upconv3_weights_kernel(const float* __restrict__ w, int Cout, int Cin,
+                                            __nv_bfloat16* __restrict__ wup, __nv_bfloat16* __restrict__ wupT) {
+  const long long total = 64ll * Cout * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int pa = (int)(i / ((long long)Cin * Cout));
+    const int p = pa >> 3, abc = pa & 7;
+    const float* src = w + ((long long)co * Cin + ci) * 27;
+    float acc = 0.f;
+    for (int kd = 0; kd < 3; ++kd) {
+      const int pd = p >> 2, a = abc >> 2;
+      if ((pd == 0 ? (kd == 0 ? 0 : 1) : (kd == 2 ? 1 : 0)) != a) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ph = (p >> 1) & 1, b = (abc >> 1) & 1;
+        if ((ph == 0 ? (kh == 0 ? 0 : 1) : (kh == 2 ? 1 : 0)) != b) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int pw = p & 1, c = abc & 1;
+          if ((pw == 0 ? (kw == 0 ? 0 : 1) : (kw == 2 ? 1 : 0)) != c) continue;
+          acc += src[(kd * 3 + kh) * 3 + kw];
+        }
+      }
+    }
+    const __nv_bfloat16 v = __float2bfloat16_rn(acc);
+    if (wup) wup[((long long)pa * Cout + co) * Cin + ci] = v;
+    if (wupT) wupT[((long long)pa * Cin + ci) * Cout + co] = v;
+  }
+}
+
+int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wupT, cudaStream_t st) {
+  SIVAE_CHECK(Cout > 0 && Cin > 0, "pack_upconv3_weights: bad dims");
+  const long long total = 64ll * Cout * Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_upconv3_weights_kernel<<<blocks, 256, 0, st>>>(w, Cout, Cin, (__nv_bfloat16*)wup, (__nv_bfloat16*)wupT);
+  SIVAE_LAUNCH_OK("pack_upconv3_weights_kernel");
+  return 0;
+}
+
+// fp32 [C][27] (one output channel) -> bf16 [27][16][C]; the filter (tap-flipped when `flip`) is split into
+// row 0 = bf16(w) and row 1 = bf16(w - bf16(w)) so the two accumulator columns add up to (almost) fp32 weights
+// at no extra MMA cost (the N = 16 tile is the minimum anyway); rows 2..15 are zero.
 __global__ void pack_to1_weights_kernel(const float* __restrict__ w, int C, int flip, __nv_bfloat16* __restrict__ wp) {
   const int total = 27 * 16 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C, r = (i / C) % 16, tap = i / (16 * C);
-    wp[i] = __float2bfloat16_rn(r == 0 ? w[c * 27 + (flip ? 26 - tap : tap)] : 0.f);
+    const float v = w[c * 27 + (flip ? 26 - tap : tap)];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    wp[i] = r == 0 ? hi : r == 1 ? __float2bfloat16_rn(v - __bfloat162float(hi)) : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -486,42 +668,39 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
   pack_to1_weights_kernel<<<cdiv(27 * 16 * C, 256), 256, 0, st>>>(w, C, flip, (__nv_bfloat16*)ws);
   SIVAE_LAUNCH_OK("pack_to1_weights_kernel");
   ConvGeom g;
-  g.N = N; g.D = D; g.H = H; g.W = W;
-  pick_tile(W, H, D, 1, false, g.wt, g.ht, g.dt);
-  g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
-  g.rows = g.wt * g.ht * g.dt;
-  g.cin_blocks = C / 64;
+  fill_geom(g, N, D, H, W, C, kTapsPlain);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
   SIVAE_CHECK(tiles < (1ll << 31), "conv3_to1: too many tiles");
-  CUtensorMap tmA, tmB;
-  if (make_act_tmap(&tmA, x, N, D, H, W, C, g.wt, g.ht, g.dt)) return -1;
-  {
-    uint64_t dims[3] = {(uint64_t)C, 16, 27};
-    uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)16 * C * 2};
-    uint32_t box[3] = {64, 16, 1};
-    if (make_tmap_bf16(&tmB, ws, 3, dims, strides, box)) return -1;
-  }
+  TmapPack tmA;
+  CUtensorMap tmB;
+  if (make_act_tmap(&tmA.m[0], x, N, D, H, W, C, g.wt, g.ht, g.dt)) return -1;
+  for (int i = 1; i < 8; ++i) tmA.m[i] = tmA.m[0];
+  if (make_weight_tmap(&tmB, ws, 27, 16, C, 16)) return -1;
   ToOneEpilogue ep;
   ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = make_seed_ref(seed); ep.p = p; ep.act = act;
   return launch_igemm<16, 4, 1>(tmA, tmB, tmA, g, tiles, 1, ep, st);
 }
 
 // ---- wgrad ----
-static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradGeom& g, int& nt, int& ntiles, int& splits) {
+static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, int mode, WgradGeom& g, int& nt, int& ntiles,
+                       int& splits) {
   g.N = N; g.D = D; g.H = H; g.W = W;
   pick_tile(W, H, D, 1, true, g.wt, g.ht, g.dt);
   g.tiles_w = cdiv(W, g.wt); g.tiles_h = cdiv(H, g.ht); g.tiles_d = cdiv(D, g.dt);
   g.rows = g.wt * g.ht * g.dt;
   g.cin_blocks = Cin / 64;
-  g.units = 27 * g.cin_blocks;
-  g.pairs_total = (g.units + 1) / 2;
+  g.mode = mode;
+  g.nclasses = mode == kTapsPlain ? 1 : 8;
+  g.units_pc = (mode == kTapsPlain ? 27 : 8) * g.cin_blocks;
+  g.pairs_pc = (g.units_pc + 1) / 2;
+  g.units = g.nclasses * g.units_pc;
   nt = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
   ntiles = Cout / nt;
   g.ppc = 512 / nt;
-  g.groups = cdiv(g.pairs_total, g.ppc);
+  g.groups_pc = cdiv(g.pairs_pc, g.ppc);
   g.Cout = Cout;
   g.total_kb = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
-  int want = 148 / (g.groups * ntiles);
+  int want = 148 / (g.groups_pc * g.nclasses * ntiles);
   if (want < 1) want = 1;
   if ((long long)want > g.total_kb) want = (int)g.total_kb;
   g.kb_per_split = (g.total_kb + want - 1) / want;
@@ -529,15 +708,21 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradGeom&
   g.a_lbo = kTileBytes; g.a_sbo = 1024; g.b_lbo = kTileBytes; g.b_sbo = 1024;
 }
 
-size_t conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+static size_t wgrad_ws_bytes(int N, int D, int H, int W, int Cin, int Cout, int mode) {
   if (Cin % 64 || Cout % 64 || N <= 0) return 0;
   WgradGeom g; int nt, ntiles, splits;
-  wgrad_plan(N, D, H, W, Cin, Cout, g, nt, ntiles, splits);
+  wgrad_plan(N, D, H, W, Cin, Cout, mode, g, nt, ntiles, splits);
   return (size_t)splits * g.units * 64 * Cout * sizeof(float);
+}
+size_t conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+  return wgrad_ws_bytes(N, D, H, W, Cin, Cout, kTapsPlain);
+}
+size_t upconv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+  return wgrad_ws_bytes(N, D, H, W, Cin, Cout, kTapsUpFprop);
 }
 
 template <int NT, int A_STAGES>
-static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradGeom& g, int ntiles, int splits,
+static int launch_wgrad(const CUtensorMap& tmX, const TmapPack& tmDY, const WgradGeom& g, int ntiles, int splits,
                         float* partial, cudaStream_t st) {
   constexpr int smem = 2 * (NT / 64) * kTileBytes + A_STAGES * 2 * kTileBytes + 1024 + 256;
   static bool attr_set = false;
@@ -548,18 +733,20 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
       return -1;
     attr_set = true;
   }
-  dim3 grid((unsigned)(g.groups * ntiles), (unsigned)splits);
+  dim3 grid((unsigned)(g.groups_pc * g.nclasses * ntiles), (unsigned)splits);
   conv3_wgrad_kernel<NT, A_STAGES><<<grid, 192, smem, st>>>(tmX, tmDY, g, partial);
   SIVAE_LAUNCH_OK("conv3_wgrad_kernel");
   return 0;
 }
 
-int conv3_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
-                int Cin, int Cout, cudaStream_t st) {
+// mode kTapsPlain : x, dy on the same [N][D][H][W] lattice.
+// mode kTapsUpFprop: x is the LOW-res input [N][D][H][W][Cin], dy the HIGH-res output gradient [N][2D][2H][2W][Cout].
+static int wgrad_impl(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
+                      int Cin, int Cout, int mode, cudaStream_t st) {
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
               "conv3_wgrad: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
   WgradGeom g; int nt, ntiles, splits;
-  wgrad_plan(N, D, H, W, Cin, Cout, g, nt, ntiles, splits);
+  wgrad_plan(N, D, H, W, Cin, Cout, mode, g, nt, ntiles, splits);
   const size_t need = (size_t)splits * g.units * 64 * Cout * sizeof(float);
   SIVAE_CHECK(ws != nullptr && ws_bytes >= need, "conv3_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   // debugging knob: override the MN-major descriptor strides "a_lbo,a_sbo,b_lbo,b_sbo"
@@ -567,20 +754,44 @@ int conv3_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_by
     unsigned a, b, c, d;
     if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { g.a_lbo = a; g.a_sbo = b; g.b_lbo = c; g.b_sbo = d; }
   }
-  CUtensorMap tmX, tmDY;
+  CUtensorMap tmX;
+  TmapPack tmDY;
   if (make_act_tmap(&tmX, x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
-  if (make_act_tmap(&tmDY, dy, N, D, H, W, Cout, g.wt, g.ht, g.dt)) return -1;
+  if (mode == kTapsPlain) {
+    if (make_act_tmap(&tmDY.m[0], dy, N, D, H, W, Cout, g.wt, g.ht, g.dt)) return -1;
+    for (int i = 1; i < 8; ++i) tmDY.m[i] = tmDY.m[0];
+  } else {
+    for (int p = 0; p < 8; ++p)
+      if (make_parity_tmap(&tmDY.m[p], dy, N, D, H, W, Cout, p, g.wt, g.ht, g.dt)) return -1;
+  }
   int rc;
   if (nt == 256) rc = launch_wgrad<256, 2>(tmX, tmDY, g, ntiles, splits, (float*)ws, st);
   else if (nt == 128) rc = launch_wgrad<128, 3>(tmX, tmDY, g, ntiles, splits, (float*)ws, st);
   else rc = launch_wgrad<64, 4>(tmX, tmDY, g, ntiles, splits, (float*)ws, st);
   if (rc) return rc;
-  const long long total = (long long)g.units * 64 * Cout;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, splits, g.units, g.cin_blocks, Cin, Cout);
-  SIVAE_LAUNCH_OK("wgrad_reduce_kernel");
+  if (mode == kTapsPlain) {
+    const long long total = (long long)g.units * 64 * Cout;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, splits, g.units, g.cin_blocks, Cin, Cout);
+    SIVAE_LAUNCH_OK("wgrad_reduce_kernel");
+  } else {
+    const long long total = 27ll * Cin * Cout;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_up_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, splits, g.cin_blocks, Cin, Cout);
+    SIVAE_LAUNCH_OK("wgrad_reduce_up_kernel");
+  }
   return 0;
+}
+
+int conv3_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
+                int Cin, int Cout, cudaStream_t st) {
+  return wgrad_impl(x, dy, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, kTapsPlain, st);
+}
+int upconv3_wgrad(const void* x_lo, const void* dy_hi, float* dw, void* ws, size_t ws_bytes, int N, int D, int H, int W,
+                  int Cin, int Cout, cudaStream_t st) {
+  return wgrad_impl(x_lo, dy_hi, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, kTapsUpFprop, st);
 }
 
 int pack_conv3_weights(const float* w, int Cout, int Cin, void* wf, void* wd, cudaStream_t st) {

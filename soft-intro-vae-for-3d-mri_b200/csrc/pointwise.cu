@@ -172,12 +172,14 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
   const int cpc = C >> 3;
   const long long nvox_in = (long long)N * D * H * W;
   const long long items = (MODE == SIVAE_RESAMPLE_AVGPOOL2 ? nvox_in / 8 : nvox_in) * cpc;
+  // 256 threads and C/8 | 256: a thread's channel chunk never changes across the grid-stride loop
+  const int chunk = (int)(threadIdx.x % cpc);
+  float sc[8], sh[8];
+  ldf8(scale + chunk * 8, sc);
+  ldf8(shift + chunk * 8, sh);
+#pragma unroll 2
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(i % cpc);
     const long long v = i / cpc;
-    float sc[8], sh[8];
-    ldf8(scale + chunk * 8, sc);
-    ldf8(shift + chunk * 8, sh);
     if (MODE == SIVAE_RESAMPLE_NONE) {
       float a[8];
       act_chunk(y, res, sc, sh, v * C + chunk * 8, slope, mask, p, seed, a);
@@ -319,12 +321,14 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16
   const unsigned long long seed = resolve_seed(sref);
   const int cpc = C >> 3;
   const long long items = (long long)N * D * H * W * cpc;
+  const int chunk = (int)(threadIdx.x % cpc);   // loop-invariant (C/8 | 256)
+  float mu[8], is[8], ga[8], be[8], c1[8], c2[8];
+  ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+  ldf8(coef + chunk * 8, c1); ldf8(coef + C + chunk * 8, c2);
+#pragma unroll 2
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(i % cpc);
     const long long v = i / cpc;
-    float mu[8], is[8], ga[8], be[8], c1[8], c2[8], dt[8], xh[8], o[8];
-    ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
-    ldf8(coef + chunk * 8, c1); ldf8(coef + C + chunk * 8, c2);
+    float dt[8], xh[8], o[8];
     bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
@@ -360,11 +364,12 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, flo
 // ------------------------------------------------------------------------------------------------
 static int grid_for(long long items, int threads) {
   long long b = (items + threads - 1) / threads;
-  if (b > 148ll * 16) b = 148ll * 16;
+  if (b > 148ll * 8) b = 148ll * 8;
   if (b < 1) b = 1;
   return (int)b;
 }
 static bool channels_ok(int C) { return C >= 8 && (C % 8) == 0 && (kBnThreads % (C / 8)) == 0; }
+// the fused forward / backward-apply kernels keep a thread's channel chunk fixed across their grid-stride loop
 
 size_t bn_workspace_bytes(int C) { return ((size_t)kBnMaxBlocks * 2 * C + 2 * (size_t)C) * sizeof(float); }
 
@@ -402,7 +407,7 @@ static int check_resample(const char* who, int D, int H, int W, int resample) {
 int bn_act_fwd(const void* y, const float* scale, const float* shift, const void* res, void* out, int N, int D, int H,
                int W, int C, float slope, int resample, const uint8_t* mask, float p, unsigned long long seed,
                cudaStream_t st) {
-  SIVAE_CHECK(C >= 8 && C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
+  SIVAE_CHECK(channels_ok(C), "bn_act_fwd: unsupported channel count %d", C);
   SIVAE_CHECK(p >= 0.f && p < 1.f, "bn_act_fwd: dropout p=%f out of range", p);
   if (check_resample("bn_act_fwd", D, H, W, resample)) return -2;
   const long long nvox = (long long)N * D * H * W;

@@ -100,8 +100,9 @@ def _bn_coeffs(y, gamma, beta, bn: BnState):
 _pack_cache = {}
 
 
-def _packed(weight: torch.Tensor):
-    key = id(weight)
+def _packed(weight: torch.Tensor, up: bool = False):
+    """-> (forward pack, data-gradient pack): plain 27-tap packs, or the upsample-folded 64-slab packs."""
+    key = (id(weight), up)
     hit = _pack_cache.get(key)
     if hit is not None:
         ref, ptr, ver, packs = hit
@@ -110,40 +111,48 @@ def _packed(weight: torch.Tensor):
     if len(_pack_cache) > 512:
         for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
             del _pack_cache[k]
-    packs = K.pack_conv3_weights(weight.detach().contiguous())
+    w = weight.detach().contiguous()
+    packs = K.pack_upconv3_weights(w) if up else K.pack_conv3_weights(w)
     _pack_cache[key] = (weakref.ref(weight), weight.data_ptr(), weight._version, packs)
     return packs
 
 
 class _ConvBnAct(torch.autograd.Function):
+    """``pre_up``: a nearest Upsample(2) sits in front of the convolution (UpsampleBuildingkBlock, models.py:58-59);
+    it is folded into the convolution (8 output parities x 8 pre-summed taps) instead of being materialised."""
+
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int):
-        wf, wd = _packed(weight)
-        y = K.conv3_igemm(x, wf)
+    def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int, pre_up: bool):
+        wf, wd = _packed(weight, pre_up)
+        y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
         mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
         out = K.bn_act_fwd(y, scale, shift, res, slope, resample)
         # x is only needed for the weight gradient: frozen-parameter passes (dgrad-only) do not keep it
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
-        ctx.cfg = (slope, resample, bn.training)
+        ctx.cfg = (slope, resample, bn.training, pre_up)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, y, res, mean, invstd, gamma, beta, wd = ctx.saved_tensors
-        slope, resample, training = ctx.cfg
+        slope, resample, training, pre_up = ctx.cfg
         if not training:
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference hot path")
         need_x, need_w, need_g, need_b, need_res = ctx.needs_input_grad[:5]
         dconv, dres, dgamma, dbeta = K.bn_act_bwd(g.contiguous(), y, res, mean, invstd, gamma, beta, slope, resample,
                                                   need_dres=bool(need_res and res is not None),
                                                   need_affine=bool(need_g or need_b))
-        dx = K.conv3_igemm(dconv, wd) if need_x else None
-        dw = K.conv3_wgrad(x, dconv) if need_w else None
-        return dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), dres, None, None, None
+        dx = dw = None
+        if need_x:
+            dx = K.upconv3_dgrad(dconv, wd) if pre_up else K.conv3_igemm(dconv, wd)
+        if need_w:
+            dw = K.upconv3_wgrad(x, dconv) if pre_up else K.conv3_wgrad(x, dconv)
+        return dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), dres, None, None, None, None
 
 
-def conv_bn_act(x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int = K.RESAMPLE_NONE):
-    return _ConvBnAct.apply(x, weight, gamma, beta, res, bn, slope, resample)
+def conv_bn_act(x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int = K.RESAMPLE_NONE,
+                pre_up: bool = False):
+    return _ConvBnAct.apply(x, weight, gamma, beta, res, bn, slope, resample, pre_up)
 
 
 class _StemBnAct(torch.autograd.Function):

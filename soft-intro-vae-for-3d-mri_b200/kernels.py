@@ -37,6 +37,11 @@ _SIGNATURES = {
     "sivae_conv3_igemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_conv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_conv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_pack_upconv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "sivae_upconv3_fprop": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_upconv3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_upconv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "sivae_upconv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_conv3_to1_workspace_bytes": (_sz, [_i]),
     "sivae_conv3_to1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp, _sz, _vp]),
     "sivae_bn_workspace_bytes": (_sz, [_i]),
@@ -129,7 +134,7 @@ class KernelTimer:
 
     active = None
 
-    def __init__(self, names=("conv3_igemm", "conv3_wgrad")):
+    def __init__(self, names=("conv3_igemm", "conv3_wgrad", "conv3_to1", "upconv3_fprop", "upconv3_dgrad", "upconv3_wgrad")):
         self.names = set(names)
         self.records = []   # (name, work, start_event, end_event)
 
@@ -236,6 +241,65 @@ def conv3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     _timed("conv3_wgrad", (flops, (n, d, h, w, ci, co)),
            lambda: _check(lib.sivae_conv3_wgrad(_p(x), _p(dy), _p(dw), _p(ws), ws.numel(), n, d, h, w, ci, co,
                                                 _stream(x)), "sivae_conv3_wgrad"))
+    return dw
+
+
+# ---- nearest-Upsample(2) folded into the 3x3x3 convolution (8 output parities x 8 pre-summed taps) ----
+def pack_upconv3_weights(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [Co,Ci,3,3,3] -> (wup bf16 [64,Co,Ci], wupT bf16 [64,Ci,Co]); index = parity*8 + abc."""
+    _req(w, torch.float32, "weight")
+    co, ci = w.shape[0], w.shape[1]
+    wup = torch.empty(64, co, ci, dtype=torch.bfloat16, device=w.device)
+    wupT = torch.empty(64, ci, co, dtype=torch.bfloat16, device=w.device)
+    _check(_L().sivae_pack_upconv3_weights(_p(w), co, ci, _p(wup), _p(wupT), _stream(w)), "sivae_pack_upconv3_weights")
+    return wup, wupT
+
+
+def upconv3_fprop(x_lo: torch.Tensor, wup: torch.Tensor) -> torch.Tensor:
+    """y_hi = conv3(upsample2(x_lo), w) without materialising the upsampled tensor."""
+    _req(x_lo, torch.bfloat16, "x_lo")
+    _req(wup, torch.bfloat16, "wup")
+    n, d, h, w, ci = x_lo.shape
+    co = wup.shape[1]
+    assert wup.shape == (64, co, ci)
+    y = torch.empty(n, 2 * d, 2 * h, 2 * w, co, dtype=torch.bfloat16, device=x_lo.device)
+    flops = 2.0 * 27 * ci * co * n * d * h * w * 8      # reference-equivalent (the kernel executes 8/27 of it)
+    _timed("upconv3_fprop", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(_L().sivae_upconv3_fprop(_p(x_lo), _p(wup), _p(y), n, d, h, w, ci, co, _stream(x_lo)),
+                          "sivae_upconv3_fprop"))
+    return y
+
+
+def upconv3_dgrad(dy_hi: torch.Tensor, wupT: torch.Tensor) -> torch.Tensor:
+    """dx_lo = upsample2^T(conv3^T(dy_hi))."""
+    _req(dy_hi, torch.bfloat16, "dy_hi")
+    _req(wupT, torch.bfloat16, "wupT")
+    n, d2, h2, w2, co = dy_hi.shape
+    ci = wupT.shape[1]
+    assert wupT.shape == (64, ci, co) and d2 % 2 == 0 and h2 % 2 == 0 and w2 % 2 == 0
+    d, h, w = d2 // 2, h2 // 2, w2 // 2
+    dx = torch.empty(n, d, h, w, ci, dtype=torch.bfloat16, device=dy_hi.device)
+    flops = 2.0 * 27 * ci * co * n * d * h * w * 8
+    _timed("upconv3_dgrad", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(_L().sivae_upconv3_dgrad(_p(dy_hi), _p(wupT), _p(dx), n, d, h, w, ci, co, _stream(dy_hi)),
+                          "sivae_upconv3_dgrad"))
+    return dx
+
+
+def upconv3_wgrad(x_lo: torch.Tensor, dy_hi: torch.Tensor) -> torch.Tensor:
+    """dw fp32 [Co,Ci,3,3,3] of conv3(upsample2(x_lo), w) given dy_hi."""
+    _req(x_lo, torch.bfloat16, "x_lo")
+    _req(dy_hi, torch.bfloat16, "dy_hi")
+    n, d, h, w, ci = x_lo.shape
+    co = dy_hi.shape[-1]
+    assert tuple(dy_hi.shape[:4]) == (n, 2 * d, 2 * h, 2 * w)
+    lib = _L()
+    ws = _workspace(x_lo.device, lib.sivae_upconv3_wgrad_workspace_bytes(n, d, h, w, ci, co), "wgrad")
+    dw = torch.empty(co, ci, 3, 3, 3, dtype=torch.float32, device=x_lo.device)
+    flops = 2.0 * 27 * ci * co * n * d * h * w * 8
+    _timed("upconv3_wgrad", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(lib.sivae_upconv3_wgrad(_p(x_lo), _p(dy_hi), _p(dw), _p(ws), ws.numel(), n, d, h, w, ci, co,
+                                                  _stream(x_lo)), "sivae_upconv3_wgrad"))
     return dw
 
 

@@ -82,10 +82,10 @@ def _conv3_weight(conv: nn.Conv3d) -> torch.Tensor:
     return _pad_dim(_pad_dim(w, 0, _cpad(w.shape[0])), 1, _cpad(w.shape[1]))
 
 
-def _fused_conv_bn_act(x, conv: nn.Conv3d, bn: nn.BatchNorm3d, res, slope: float, resample: int):
+def _fused_conv_bn_act(x, conv: nn.Conv3d, bn: nn.BatchNorm3d, res, slope: float, resample: int, pre_up: bool = False):
     b = _BnBinding(bn)
     gamma, beta = b.params()
-    out = F.conv_bn_act(x, _conv3_weight(conv), gamma, beta, res, b.state(), slope, resample)
+    out = F.conv_bn_act(x, _conv3_weight(conv), gamma, beta, res, b.state(), slope, resample, pre_up)
     b.commit()
     return out
 
@@ -142,12 +142,12 @@ class BuildingBlock(nn.Module):
                                       "projection here, which no shipped block_setting does (SURVEY Q1)")
         else:
             res = None
-        if self.stride == 1:
-            mode = K.RESAMPLE_NONE
-        else:
-            mode = K.RESAMPLE_UPSAMPLE2 if self._upsample else K.RESAMPLE_AVGPOOL2
+        # AvgPool3d(2) is fused behind the first convolution's BN/activation; Upsample(2) is folded into the
+        # second convolution itself (never materialised)
+        mode = K.RESAMPLE_AVGPOOL2 if (self.stride == 2 and not self._upsample) else K.RESAMPLE_NONE
         a = _fused_conv_bn_act(x, self.block[0], self.block[1], None, self.slope, mode)
-        return _fused_conv_bn_act(a, self.block[4], self.block[5], res, self.slope, K.RESAMPLE_NONE)
+        return _fused_conv_bn_act(a, self.block[4], self.block[5], res, self.slope, K.RESAMPLE_NONE,
+                                  pre_up=(self.stride == 2 and self._upsample))
 
 
 class UpsampleBuildingkBlock(BuildingBlock):

@@ -98,3 +98,62 @@ def test_linearity_at_headline_size():
     assert torch.equal(y2.float(), y1.float() * 2)
     sub = S.conv3_igemm(x1[:, 30:50].contiguous(), wf)                # interior planes 31..48 are halo-free
     _check_bf16(y1[:, 31:49], sub[:, 1:19], "headline sub-block")
+
+
+# ---------------------------------------------------------------- Upsample(2) folded into the convolution
+UP_SHAPES = [
+    (1, 4, 4, 8, 64, 64),       # low-res extents; exact tiles
+    (2, 5, 6, 5, 128, 64),      # D3b-like channel change, ragged
+    (1, 10, 12, 10, 256, 128),  # D2b at the headline resolution
+    (1, 3, 5, 7, 64, 64),       # all odd
+    (1, 1, 1, 1, 64, 128),      # single low-res voxel -> 2x2x2 outputs
+]
+
+
+def _upsample(x):  # NDHWC nearest x2
+    return x.repeat_interleave(2, 1).repeat_interleave(2, 2).repeat_interleave(2, 3)
+
+
+def test_pack_upconv_weights():
+    wt = torch.randn(128, 64, 3, 3, 3, device=DEV)
+    wup, wupT = K.pack_upconv3_weights(wt)
+    sup, supT = S.pack_upconv3_weights(wt)
+    # fp32 summation order may differ by an ulp before the bf16 rounding
+    assert float((wup.float() - sup.float()).abs().max()) <= 2 ** -7 * float(sup.float().abs().max())
+    assert (wup != sup).float().mean() < 1e-3
+    assert torch.equal(wupT, wup.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("shape", UP_SHAPES)
+def test_upconv_fprop(shape):
+    n, d, h, w, ci, co = shape
+    x, wt = _mk(*shape)
+    wup, _ = K.pack_upconv3_weights(wt)
+    got = K.upconv3_fprop(x, wup)
+    _check_bf16(got, S.upconv3_fprop(x, wup), f"upconv fprop vs folded spec {shape}")
+    # and against the definition: conv3d over the materialised nearest-upsampled tensor with the fp32 weights
+    # (differs only by the bf16 rounding of the pre-summed weights)
+    ref = torch.nn.functional.conv3d(_upsample(x).float().permute(0, 4, 1, 2, 3), wt, None, 1, 1).permute(0, 2, 3, 4, 1)
+    err = float((got.float() - ref).abs().max())
+    assert err <= 0.03 * float(ref.abs().max()) + 1e-3, (shape, err)
+
+
+@pytest.mark.parametrize("shape", UP_SHAPES)
+def test_upconv_dgrad(shape):
+    n, d, h, w, ci, co = shape
+    _, wt = _mk(*shape)
+    dy = torch.randn(n, 2 * d, 2 * h, 2 * w, co, device=DEV).to(torch.bfloat16)
+    _, wupT = K.pack_upconv3_weights(wt)
+    _check_bf16(K.upconv3_dgrad(dy, wupT), S.upconv3_dgrad(dy, wupT), f"upconv dgrad {shape}")
+
+
+@pytest.mark.parametrize("shape", UP_SHAPES)
+def test_upconv_wgrad(shape):
+    n, d, h, w, ci, co = shape
+    x, _ = _mk(*shape)
+    dy = torch.randn(n, 2 * d, 2 * h, 2 * w, co, device=DEV).to(torch.bfloat16)
+    got = K.upconv3_wgrad(x, dy)
+    ref = S.upconv3_wgrad(x, dy)
+    assert torch.isfinite(got).all()
+    err, scale = float((got - ref).abs().max()), float(ref.abs().max())
+    assert err <= 2e-3 * scale + 1e-5, f"upconv wgrad {shape}: max err {err:.4e} vs scale {scale:.4e}"
