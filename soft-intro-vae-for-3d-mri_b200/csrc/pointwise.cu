@@ -16,6 +16,10 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -83,14 +87,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const __nv_bfloat1
   const int chunk = threadIdx.x % cpc;
   const int lanes_v = kBnThreads / cpc;
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long v = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v < nvox; v += (long long)gridDim.x * lanes_v) {
-    float f[8];
-    ld8(y + v * C + chunk * 8, f);
+  const long long stride = (long long)gridDim.x * lanes_v;
+  for (long long v0 = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v0 < nvox; v0 += stride * 4) {
+    uint4 raw[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s1[k] += f[k];
-      s2[k] += f[k] * f[k];
-    }
+    for (int u = 0; u < 4; ++u)
+      if (v0 + u * stride < nvox) raw[u] = *reinterpret_cast<const uint4*>(y + (v0 + u * stride) * C + chunk * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v0 + u * stride < nvox) {
+        const float2 a = unpack_bf16x2(raw[u].x), b = unpack_bf16x2(raw[u].y), c = unpack_bf16x2(raw[u].z),
+                     d = unpack_bf16x2(raw[u].w);
+        const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += f[k];
+          s2[k] += f[k] * f[k];
+        }
+      }
   }
   block_reduce_channels(s1, s2, C, cpc, partial);
 }
@@ -177,7 +191,45 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
   float sc[8], sh[8];
   ldf8(scale + chunk * 8, sc);
   ldf8(shift + chunk * 8, sh);
-#pragma unroll 2
+  if constexpr (MODE == SIVAE_RESAMPLE_NONE) {
+    // streaming case: issue the loads of 4 voxels before consuming them
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < items; i0 += stride * 4) {
+      uint4 ry[4], rr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < items) {
+          const long long e0 = (i / cpc) * C + chunk * 8;
+          ry[u] = *reinterpret_cast<const uint4*>(y + e0);
+          if (res != nullptr) rr[u] = *reinterpret_cast<const uint4*>(res + e0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < items) {
+          const long long e0 = (i / cpc) * C + chunk * 8;
+          float f[8], ks[8], a[8];
+          unpack8(ry[u], f);
+          if (res != nullptr) {
+            float r[8];
+            unpack8(rr[u], r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]) + r[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+          }
+          drop8(mask, p, seed, e0, ks);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[k] = (f[k] > 0.f ? f[k] : slope * f[k]) * ks[k];
+          st8(out + e0, a);
+        }
+      }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const long long v = i / cpc;
     if (MODE == SIVAE_RESAMPLE_NONE) {
@@ -268,8 +320,66 @@ __device__ __forceinline__ void bwd_chunk(const __nv_bfloat16* __restrict__ g, c
   }
 }
 
+// Split load / compute form of bwd_chunk for the streaming modes (NONE, AVGPOOL2): a thread first issues the 16-byte
+// loads of kBwdUnroll voxels, then consumes them, so ~4x more bytes are in flight per thread (HBM latency hiding).
+static constexpr int kBwdUnroll = 2;
+struct BwdRaw {
+  uint4 y, g, r;
+  uint2 m;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(kBnThreads)
+__device__ __forceinline__ void bwd_load(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                         const __nv_bfloat16* __restrict__ res, const uint8_t* __restrict__ mask,
+                                         long long v, int chunk, int D, int H, int W, int C, BwdRaw& raw) {
+  const long long e0 = v * C + chunk * 8;
+  raw.y = *reinterpret_cast<const uint4*>(y + e0);
+  if (MODE == SIVAE_RESAMPLE_NONE) {
+    raw.g = *reinterpret_cast<const uint4*>(g + e0);
+  } else {
+    const int w = (int)(v % W);
+    const int h = (int)((v / W) % H);
+    const int d = (int)((v / ((long long)W * H)) % D);
+    const long long n = v / ((long long)W * H * D);
+    const long long vo = ((n * (D / 2) + d / 2) * (H / 2) + h / 2) * (W / 2) + w / 2;
+    raw.g = *reinterpret_cast<const uint4*>(g + vo * C + chunk * 8);
+  }
+  if (res != nullptr) raw.r = *reinterpret_cast<const uint4*>(res + e0);
+  if (mask != nullptr) raw.m = *reinterpret_cast<const uint2*>(mask + e0);
+}
+
+template <int MODE>
+__device__ __forceinline__ void bwd_compute(const BwdRaw& raw, bool has_res, const uint8_t* mask, float p,
+                                            unsigned long long seed, long long e0, const float (&mean)[8],
+                                            const float (&invstd)[8], const float (&gam)[8], const float (&bet)[8],
+                                            float slope, float (&dt)[8], float (&xh)[8]) {
+  float f[8], gp[8], r[8], ks[8];
+  unpack8(raw.y, f);
+  unpack8(raw.g, gp);
+  if (has_res) {
+    unpack8(raw.r, r);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = 0.f;
+  }
+  if (mask != nullptr) {
+    const float inv = 1.f / (1.f - p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = (((k < 4 ? raw.m.x : raw.m.y) >> ((k & 3) * 8)) & 0xffu) ? inv : 0.f;
+  } else {
+    drop8(nullptr, p, seed, e0, ks);
+  }
+  const float gs = MODE == SIVAE_RESAMPLE_AVGPOOL2 ? 0.125f : 1.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    xh[k] = (f[k] - mean[k]) * invstd[k];
+    const float t = fmaf(xh[k], gam[k], bet[k]) + r[k];
+    dt[k] = gp[k] * gs * ks[k] * (t > 0.f ? 1.f : slope);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads, 2)
 bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                          const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -284,13 +394,38 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
   float mu[8], is[8], ga[8], be[8];
   ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long v = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v < nvox; v += (long long)gridDim.x * lanes_v) {
-    float dt[8], xh[8];
-    bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
+  const long long stride = (long long)gridDim.x * lanes_v;
+  if constexpr (MODE == SIVAE_RESAMPLE_UPSAMPLE2) {
+    for (long long v = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v < nvox; v += stride) {
+      float dt[8], xh[8];
+      bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s1[k] += dt[k];
-      s2[k] += dt[k] * xh[k];
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += dt[k];
+        s2[k] += dt[k] * xh[k];
+      }
+    }
+  } else {
+    for (long long v0 = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v0 < nvox; v0 += stride * kBwdUnroll) {
+      BwdRaw raw[kBwdUnroll];
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const long long v = v0 + u * stride;
+        if (v < nvox) bwd_load<MODE>(g, y, res, mask, v, chunk, D, H, W, C, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const long long v = v0 + u * stride;
+        if (v < nvox) {
+          float dt[8], xh[8];
+          bwd_compute<MODE>(raw[u], res != nullptr, mask, p, seed, v * C + chunk * 8, mu, is, ga, be, slope, dt, xh);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            s1[k] += dt[k];
+            s2[k] += dt[k] * xh[k];
+          }
+        }
+      }
     }
   }
   block_reduce_channels(s1, s2, C, cpc, partial);
@@ -311,7 +446,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                         const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -325,15 +460,39 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16
   float mu[8], is[8], ga[8], be[8], c1[8], c2[8];
   ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
   ldf8(coef + chunk * 8, c1); ldf8(coef + C + chunk * 8, c2);
-#pragma unroll 2
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const long long v = i / cpc;
-    float dt[8], xh[8], o[8];
-    bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if constexpr (MODE == SIVAE_RESAMPLE_UPSAMPLE2) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += stride) {
+      const long long v = i / cpc;
+      float dt[8], xh[8], o[8];
+      bwd_chunk<MODE>(g, y, res, mu, is, ga, be, v, chunk, N, D, H, W, C, slope, mask, p, seed, dt, xh);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
-    st8(dconv + v * C + chunk * 8, o);
-    if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
+      for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
+      st8(dconv + v * C + chunk * 8, o);
+      if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
+    }
+  } else {
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < items; i0 += stride * kBwdUnroll) {
+      BwdRaw raw[kBwdUnroll];
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < items) bwd_load<MODE>(g, y, res, mask, i / cpc, chunk, D, H, W, C, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < items) {
+          const long long v = i / cpc;
+          float dt[8], xh[8], o[8];
+          bwd_compute<MODE>(raw[u], res != nullptr, mask, p, seed, v * C + chunk * 8, mu, is, ga, be, slope, dt, xh);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
+          st8(dconv + v * C + chunk * 8, o);
+          if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
+        }
+      }
+    }
   }
 }
 

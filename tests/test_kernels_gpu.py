@@ -141,10 +141,10 @@ def test_cn_to_c1(C, T, flip, act):
     b = torch.randn(1, device=DEV)
     mask = (torch.rand(2, 5, 7, 37, device=DEV) > 0.35).to(torch.uint8) if act else None
     got = K.cn_to_c1(x, w, b, flip, act, mask, 0.35 if act else 0.0, 0)
-    # the 3x3x3 case runs on tcgen05 with bf16-rounded weights (fp32 accumulation); 1x1 stays fp32 SIMT
-    wq = w.to(torch.bfloat16).float() if T == 27 else w
-    ref = S.cn_to_c1(x, wq, b, flip, act, mask, 0.35 if act else 0.0, 0)
-    assert_f32_close(got, ref, "cn_to_c1", 5e-5)
+    # the 3x3x3 case runs on tcgen05 with split-bf16 weights (hi + lo ~ 16 mantissa bits, fp32 accumulation);
+    # the 1x1 case stays fp32 SIMT
+    ref = S.cn_to_c1(x, w, b, flip, act, mask, 0.35 if act else 0.0, 0)
+    assert_f32_close(got, ref, "cn_to_c1", 1e-4 if T == 27 else 2e-5)
     # the direct (SIMT) C ABI entry point stays available and exact in fp32
     import ctypes
     lib = K.load_library()

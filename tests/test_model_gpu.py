@@ -53,7 +53,7 @@ def test_eval_forward_vs_golden(golden_dir):
         ref = g["eval"][name].to(DEV)
         assert a.shape == ref.shape and a.dtype == torch.float32
         err = float((a - ref).abs().max())
-        assert err <= 0.03 * float(ref.abs().max()) + 1e-3, (name, err, float(ref.abs().max()))
+        assert err <= 0.06 * float(ref.abs().max()) + 1e-3, (name, err, float(ref.abs().max()))
         assert _cos(a, ref) > 0.999, name
 
 
