@@ -158,7 +158,7 @@ def run_ours(args):
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
     net.to(dev).train()
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph
     opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
     opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
     red_e = P.GradReducer(net.encoder.parameters()) if world > 1 else None
@@ -179,9 +179,22 @@ def run_ours(args):
         return T.soft_intro_train_step(net, real_dev, noise_dev, opt_e, opt_d, hp, red_e, red_d)
 
     graphed = None
+    graph_note = None
     if use_graph:
-        # whole-step CUDA graph (sivae_b200.graph): ~1150 launches per step collapse into one replay
-        graphed = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real_dev, noise_dev, hp, warmup=2)
+        # whole-step CUDA graph (sivae_b200.graph): ~1500 launches per step collapse into one replay; with N > 1
+        # the bucketed NCCL all-reduces are captured as well.  If the capture is refused the step runs eagerly.
+        try:
+            graphed = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real_dev, noise_dev, hp, warmup=2,
+                                                        reducer_e=red_e, reducer_d=red_d)
+        except Exception as ex:  # noqa: BLE001
+            graph_note = f"capture failed, ran eagerly: {type(ex).__name__}: {str(ex)[:120]}"
+            graphed = None
+            torch.cuda.synchronize()
+        if world > 1:
+            ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                graphed = None
 
     def step_resident():
         if graphed is not None:
@@ -272,7 +285,8 @@ def run_ours(args):
                                    "one E+D train step incl. 2 Adam steps",
                        "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
-                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP, "cuda_graph": graphed is not None},
+                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP, "cuda_graph": graphed is not None,
+                       "cuda_graph_note": graph_note},
             "clocks": clocks, "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
                                       "d2h_bytes_per_step": int(res.numel() * 4)},

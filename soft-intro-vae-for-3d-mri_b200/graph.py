@@ -24,7 +24,7 @@ from . import trainer as T
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer_e, optimizer_d, real_example: torch.Tensor, noise_example: torch.Tensor,
-                 hp: Optional[T.StepHyper] = None, warmup: int = 3):
+                 hp: Optional[T.StepHyper] = None, warmup: int = 3, reducer_e=None, reducer_d=None):
         for opt in (optimizer_e, optimizer_d):
             for g in opt.param_groups:
                 if not g.get("capturable", False):
@@ -36,14 +36,17 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(self.real.device))
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
-                T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp)
+                T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp,
+                                        reducer_e, reducer_d)
         torch.cuda.current_stream(self.real.device).wait_stream(side)
         torch.cuda.synchronize(self.real.device)
         # every weight must be (re)packed inside the graph at its first use: drop packs made by the warm-up
         F._pack_cache.clear()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp)
+        # with gradient reducers the NCCL all-reduces (launched from grad hooks) are captured too
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.out = T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp,
+                                               reducer_e, reducer_d)
         F._pack_cache.clear()   # the captured packs live in the graph's private pool; do not reuse them eagerly
 
     def __call__(self, real_batch: torch.Tensor, noise_batch: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -39,7 +39,7 @@ def init_distributed(backend: Optional[str] = None) -> tuple:
 
 
 class _Bucket:
-    __slots__ = ("params", "offsets", "flat", "pending", "work", "launched")
+    __slots__ = ("params", "offsets", "flat", "views", "pending", "work", "launched")
 
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = params
@@ -49,6 +49,7 @@ class _Bucket:
             self.offsets.append(n)
             n += p.numel()
         self.flat = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        self.views = [self.flat[o: o + p.numel()].view(p.shape) for o, p in zip(self.offsets, params)]
         self.pending = set()
         self.work = None
         self.launched = False
@@ -104,15 +105,12 @@ class GradReducer:
         if b.launched:
             return
         b.launched = True
-        any_grad = False
-        for p, off in zip(b.params, b.offsets):
-            dst = b.flat[off: off + p.numel()]
-            if p.grad is not None:
-                dst.copy_(p.grad.reshape(-1))
-                any_grad = True
-            else:
-                dst.zero_()
-        if self.world > 1 and (any_grad or self._expected is None):
+        have = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None]
+        if len(have) != len(b.params):
+            b.flat.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])     # one multi-tensor kernel
+        if self.world > 1 and (have or self._expected is None):
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _on_grad(self, p):
@@ -136,9 +134,10 @@ class GradReducer:
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
-            for p, off in zip(b.params, b.offsets):
-                if p.grad is not None:
-                    p.grad.copy_(b.flat[off: off + p.numel()].reshape(p.grad.shape) * inv)
+            have = [(p.grad, v) for v, p in zip(b.views, b.params) if p.grad is not None]
+            if have:
+                b.flat.mul_(inv)
+                torch._foreach_copy_([g for g, _ in have], [v for _, v in have])
         self._arm()
 
     def remove(self):
