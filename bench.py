@@ -158,7 +158,9 @@ def run_ours(args):
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
     net.to(dev).train()
-    use_graph = not args.no_graph
+    # N > 1 runs eagerly: capturing the hook-launched NCCL all-reduces inside the whole-step graph deadlocked on
+    # this stack (torch 2.11 / NCCL 2.28), and the step is GPU-bound anyway (multi-GPU section)
+    use_graph = not args.no_graph and world == 1
     opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
     opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
     red_e = P.GradReducer(net.encoder.parameters()) if world > 1 else None
