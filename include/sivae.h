@@ -156,6 +156,13 @@ int sivae_bn_act_bwd(const void* g_bf16, const void* y_bf16, const void* res_bf1
 int sivae_c1_to_cn(const float* x1, const float* w, const float* bias, void* y_bf16,
                    int N, int D, int H, int W, int C, int T, int flip, int accumulate, void* stream);
 
+/* The 3x3x3, C = 64 case of sivae_c1_to_cn on tensor cores (encoder stem Conv3d(1,64,3), models/models.py:92, and the
+ * input gradient of the decoder tail): the im2col of the one-channel fp32 input is built in shared memory and multiplied
+ * on tcgen05 with a bf16 hi/lo split of both operands (~fp32 products), bf16 NDHWC output.  No accumulate mode. */
+size_t sivae_c1_to_c64_workspace_bytes(void);
+int sivae_c1_to_c64(const float* x1, const float* w, const float* bias, void* y_bf16,
+                    int N, int D, int H, int W, int flip, void* workspace, size_t workspace_bytes, void* stream);
+
 /* y[v] = act( bias[0] + sum_{t,c} w[c][t] * x[v + delta(t)][c] )     x bf16 NDHWC, y fp32 [N][D][H][W]
  *   act = 0: identity; act = 1: ReLU followed by dropout (mask / Philox(seed) / p as above).        */
 int sivae_cn_to_c1(const void* x_bf16, const float* w, const float* bias, float* y,
@@ -168,6 +175,12 @@ size_t sivae_wgrad_c1_workspace_bytes(int N, int D, int H, int W, int C, int T);
 int sivae_wgrad_c1(const void* xc_bf16, const float* x1, float* dw, float* sum_c, float* sum_1,
                    int N, int D, int H, int W, int C, int T, int flip,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The 3x3x3, C = 64 case of sivae_wgrad_c1 on tensor cores (split-K GEMM over voxels; the one-channel operand's im2col
+ * is built in shared memory with a bf16 hi/lo split, the 64-channel operand streams through TMA).  dw fp32 [64][27]. */
+size_t sivae_wgrad_c64_workspace_bytes(void);
+int sivae_wgrad_c64(const void* xc_bf16, const float* x1, float* dw, float* sum_c, float* sum_1,
+                    int N, int D, int H, int W, int flip, void* workspace, size_t workspace_bytes, void* stream);
 
 /* backward of ReLU+Dropout on the decoder output: dy[i] = out[i] > 0 ? g[i]/(1-p) : 0 */
 int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n, float p, void* stream);

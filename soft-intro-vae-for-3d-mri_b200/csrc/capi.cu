@@ -70,6 +70,10 @@ int upconv3_dgrad(const void*, const void*, void*, int, int, int, int, int, int,
 size_t upconv3_wgrad_workspace_bytes(int, int, int, int, int, int);
 int upconv3_wgrad(const void*, const void*, float*, void*, size_t, int, int, int, int, int, int, cudaStream_t);
 int pack_upconv3_weights(const float*, int, int, void*, void*, cudaStream_t);
+size_t wgrad_c1_tc_workspace_bytes();
+int wgrad_c1_tc(const void*, const float*, float*, float*, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t c1_to_c64_workspace_bytes();
+int c1_to_c64_tc(const float*, const float*, const float*, void*, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t conv3_to1_workspace_bytes(int);
 int conv3_to1(const void*, const float*, const float*, float*, int, int, int, int, int, int, int, const uint8_t*, float,
               unsigned long long, void*, size_t, cudaStream_t);
@@ -165,6 +169,16 @@ size_t sivae_upconv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, 
 int sivae_upconv3_wgrad(const void* x_lo, const void* dy_hi, float* dw, void* ws, size_t ws_bytes, int N, int D, int H,
                         int W, int Cin, int Cout, void* stream) {
   return upconv3_wgrad(x_lo, dy_hi, dw, ws, ws_bytes, N, D, H, W, Cin, Cout, ST(stream));
+}
+size_t sivae_wgrad_c64_workspace_bytes(void) { return wgrad_c1_tc_workspace_bytes(); }
+int sivae_wgrad_c64(const void* xc, const float* x1, float* dw, float* sum_c, float* sum_1, int N, int D, int H, int W,
+                    int flip, void* ws, size_t ws_bytes, void* stream) {
+  return wgrad_c1_tc(xc, x1, dw, sum_c, sum_1, N, D, H, W, flip, ws, ws_bytes, ST(stream));
+}
+size_t sivae_c1_to_c64_workspace_bytes(void) { return c1_to_c64_workspace_bytes(); }
+int sivae_c1_to_c64(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
+                    void* ws, size_t ws_bytes, void* stream) {
+  return c1_to_c64_tc(x1, w, bias, y, N, D, H, W, flip, ws, ws_bytes, ST(stream));
 }
 size_t sivae_conv3_to1_workspace_bytes(int C) { return conv3_to1_workspace_bytes(C); }
 int sivae_conv3_to1(const void* x, const float* w, const float* bias, float* y, int N, int D, int H, int W, int C,

@@ -642,6 +642,521 @@ int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wup
   return 0;
 }
 
+// =================================================================================================
+// C = 64 -> 1 channel, 3x3x3: "all taps as GEMM columns" variant.
+// P[v_in][tap] = sum_c x[v_in][c] * w[c][tap] is one tiny GEMM per input voxel (N = 27 taps), so the input tile is
+// fetched ONCE instead of once per tap; the convolution is then out[v] = sum_tap P[v + delta(tap)][tap], a 27-term
+// gather from shared memory.  A CTA owns 16 x 8 x 1 outputs and loads the 18 x 10 x 3 input halo box (540 voxel rows,
+// one TMA), runs 5 M-tiles x (hi + lo weight slabs) of UMMA 128x32x16, spills P to shared memory (aliasing the input
+// buffer) and reduces.  L2->SMEM traffic drops 27 x 16 KB -> 69 KB per 128 outputs.
+// =================================================================================================
+static constexpr int kHW = 16, kHH = 8;                        // outputs per CTA (w, h); d = 1
+static constexpr int kHBW = kHW + 2, kHBH = kHH + 2, kHBD = 3; // input halo box
+static constexpr int kHRows = kHBW * kHBH * kHBD;              // 540
+static constexpr int kHMTiles = (kHRows + 127) / 128;          // 5
+static constexpr int kPStride = 29;                            // floats per P row (odd: conflict-free gather)
+
+__global__ void __launch_bounds__(192)
+conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int N, int D,
+                      int H, int W, int tiles_w, int tiles_h, const ToOneEpilogue ep) {
+  constexpr int A_BYTES = kHMTiles * kTileBytes;   // 80 KB (rows 540..639 are never written nor used)
+  constexpr int B_BYTES = 32 * 128;                // one 32-tap x 64-channel slab
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + 2 * B_BYTES);
+  uint64_t* tmem_full_bar = full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* P = reinterpret_cast<float*>(smem);       // [640][kPStride] aliases the A buffer after the MMAs
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long id = blockIdx.x;
+  const int tw = (int)(id % tiles_w); id /= tiles_w;
+  const int th = (int)(id % tiles_h); id /= tiles_h;
+  const int d0 = (int)(id % D);
+  const int n = (int)(id / D);
+  const int w0 = tw * kHW, h0 = th * kHH;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    mbar_init(full_bar, 1);
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(full_bar, (uint32_t)kHRows * 128u + 2u * B_BYTES);
+      tma_load_5d(smem, &tmA, full_bar, 0, w0 - 1, h0 - 1, d0 - 1, n);
+      tma_load_3d(smem_b, &tmB, full_bar, 0, 0, 0);
+      tma_load_3d(smem_b + B_BYTES, &tmB, full_bar, 0, 0, 1);
+    }
+  } else if (warp_id == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
+    mbar_wait(full_bar, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem_b);
+#pragma unroll 1
+      for (int m = 0; m < kHMTiles; ++m)
+#pragma unroll
+        for (int part = 0; part < 2; ++part)     // hi then lo weight slab into the same accumulator
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)(m * 32), make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
+                      make_smem_desc(b_addr + part * B_BYTES + k * 32, 16, 1024), idesc, (part | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp_id & 3;
+#pragma unroll 1
+    for (int m = 0; m < kHMTiles; ++m) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 32), v);
+      tmem_ld_wait();
+      float* dst = P + (size_t)(m * 128 + q * 32 + lane) * kPStride;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v[t]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int t128 = (warp_id - 2) * 32 + lane;          // one output voxel per epilogue thread
+    const int ow = t128 % kHW, oh = t128 / kHW;
+    const int w = w0 + ow, h = h0 + oh;
+    if (w < W && h < H) {
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const int row = ((t / 9) * kHBH + oh + (t / 3) % 3) * kHBW + ow + t % 3;
+        acc += P[row * kPStride + t];
+      }
+      const long long vox = (((long long)n * D + d0) * H + h) * W + w;
+      float r = acc + (ep.bias ? ep.bias[0] : 0.f);
+      if (ep.act == 1) {
+        r = fmaxf(r, 0.f);
+        const float inv_keep = 1.f / (1.f - ep.p);
+        if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
+        else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+      }
+      ep.y[vox] = r;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// fp32 [64][27] -> bf16 [2][32][64]: slab 0 = bf16(w) per tap row (rows 27..31 zero), slab 1 = bf16(w - bf16(w))
+__global__ void pack_to1_halo_weights_kernel(const float* __restrict__ w, int flip, __nv_bfloat16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * 32 * 64) return;
+  const int c = i % 64, tap = (i / 64) % 32, part = i / (64 * 32);
+  float v = 0.f;
+  if (tap < 27) v = w[c * 27 + (flip ? 26 - tap : tap)];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  wp[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// =================================================================================================
+// 1 -> 64 channels, 3x3x3 (encoder stem Conv3d(1,64,3), models/models.py:92; input gradient of the decoder tail):
+// y[v][c] = bias[c] + sum_tap w[c][tap] * x1[v + delta(tap)] as a tensor-core GEMM whose A operand (the im2col of
+// the one-channel fp32 input) is BUILT IN SHARED MEMORY by the CTA's threads: M = 128 voxels (16 x 8 x 1), N = 64,
+// K = 128 = [x_hi(32) | x_lo(32) | x_hi(32) | 0] against B = [w_hi | w_hi | w_lo | 0]  (bf16 split of both operands:
+// x_hi*w_hi + x_lo*w_hi + x_hi*w_lo recovers ~16 mantissa bits of the fp32 product).  Epilogue as conv3_igemm.
+// HBM-bound on the 128 B/voxel output write instead of FMA-bound (1728 FMA/voxel on CUDA cores).
+// =================================================================================================
+__global__ void __launch_bounds__(160)
+c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
+                    int tiles_w, int tiles_h) {
+  constexpr int A_BYTES = 2 * kTileBytes;          // two 64-wide K blocks of the 128-row A tile
+  constexpr int B_BYTES = 2 * 64 * 128;            // [2 K blocks][64 channels][64]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + A_BYTES;
+  float* xs = reinterpret_cast<float*>(smem_b + B_BYTES);          // halo (kHRows floats)
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(xs + ((kHRows + 3) & ~3));
+  uint64_t* tmem_full_bar = b_full + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warps 0-3: builders + epilogue, warp 4: TMA + MMA
+  long long id = blockIdx.x;
+  const int tw = (int)(id % tiles_w); id /= tiles_w;
+  const int th = (int)(id % tiles_h); id /= tiles_h;
+  const int d0 = (int)(id % D);
+  const long long n = id / D;
+  const int w0 = tw * kHW, h0 = th * kHH;
+
+  if (warp_id == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&tmB);
+      prefetch_tmap(&tmC);
+      mbar_init(b_full, 1);
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, B_BYTES);
+      tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
+      tma_load_3d(smem_b + 64 * 128, &tmB, b_full, 0, 0, 1);
+    }
+    __syncwarp();
+    asm volatile("bar.sync 2, 160;" ::: "memory");        // A tile built (builders fenced to the async proxy)
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    mbar_wait(b_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem_b);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, make_smem_desc(a_addr + kb * kTileBytes + k * 32, 16, 1024),
+                    make_smem_desc(b_addr + kb * 64 * 128 + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---- stage the fp32 halo, then build this thread's A row (one output voxel) ----
+    for (int i = threadIdx.x; i < kHRows; i += 128) {
+      const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
+      const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+      float v = 0.f;
+      if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+        v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+      xs[i] = v;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int row = threadIdx.x;                          // 0..127
+    const int ow = row % kHW, oh = row / kHW;
+    uint32_t hi[16], lo[16];                              // 32 bf16 each: taps 0..26, then zeros
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = 0.f, b = 0.f;
+      if (2 * j < 27) a = xs[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
+      if (2 * j + 1 < 27) b = xs[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+      lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+    }
+    uint8_t* r0 = smem + row * 128;                       // K block 0: [x_hi | x_lo]
+    uint8_t* r1 = smem + kTileBytes + row * 128;          // K block 1: [x_hi | 0]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+      const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = vh;
+      *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = vl;
+      *reinterpret_cast<uint4*>(r1 + ((c ^ (row & 7)) << 4)) = vh;
+      *reinterpret_cast<uint4*>(r1 + (((4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 2, 160;" ::: "memory");
+    // ---- epilogue ----
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    uint8_t* out_stage = smem;                            // A tile is dead once the MMAs have completed
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp_id * 32) << 16) + (uint32_t)(j * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]) + (bias ? __ldg(bias + j * 32 + c * 8 + e) : 0.f);
+        uint4 pk;
+        pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
+        pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out_stage + row * 128 + (((j * 4 + c) ^ (row & 7)) << 4)) = pk;
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+      tma_store_5d(&tmC, out_stage, 0, w0, h0, d0, (int)n);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 4) tmem_dealloc(tmem_base, 64);
+}
+
+// fp32 [64][27] -> bf16 [2][64][64]: K block 0 = [w_hi(32) | w_hi(32)], K block 1 = [w_lo(32) | 0]  (tap-flipped if `flip`)
+__global__ void pack_c1_to_c64_weights_kernel(const float* __restrict__ w, int flip, __nv_bfloat16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * 64 * 64) return;
+  const int k = i % 64, c = (i / 64) % 64, kb = i / (64 * 64);
+  const int tap = k % 32;
+  float v = 0.f;
+  if (tap < 27) v = w[c * 27 + (flip ? 26 - tap : tap)];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16 o = __float2bfloat16_rn(0.f);
+  if (kb == 0) o = hi;
+  else if (k < 32) o = lo;
+  wp[i] = o;
+}
+
+size_t c1_to_c64_workspace_bytes() { return (size_t)2 * 64 * 64 * sizeof(__nv_bfloat16); }
+
+int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  SIVAE_CHECK(ws && ws_bytes >= c1_to_c64_workspace_bytes(), "c1_to_c64: workspace too small");
+  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "c1_to_c64: empty tensor");
+  pack_c1_to_c64_weights_kernel<<<32, 256, 0, st>>>(w, flip, (__nv_bfloat16*)ws);
+  SIVAE_LAUNCH_OK("pack_c1_to_c64_weights_kernel");
+  CUtensorMap tmB, tmC;
+  {
+    uint64_t dims[3] = {64, 64, 2};
+    uint64_t strides[2] = {128, 64 * 128};
+    uint32_t box[3] = {64, 64, 1};
+    if (make_tmap_bf16(&tmB, ws, 3, dims, strides, box)) return -1;
+  }
+  if (make_act_tmap(&tmC, y, N, D, H, W, 64, kHW, kHH, 1)) return -1;
+  const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
+  const long long ctas = (long long)tiles_w * tiles_h * D * N;
+  SIVAE_CHECK(ctas < (1ll << 31), "c1_to_c64: too many tiles");
+  constexpr int smem = 2 * kTileBytes + 2 * 64 * 128 + ((kHRows + 3) & ~3) * 4 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                   "cudaFuncSetAttribute(c1_to_c64_tc)"))
+      return -1;
+    attr_set = true;
+  }
+  c1_to_c64_tc_kernel<<<(unsigned)ctas, 160, smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h);
+  SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
+  return 0;
+}
+
+// =================================================================================================
+// Weight gradient of the thin 3x3x3 convolutions with C = 64 (encoder stem, decoder tail) on tensor cores:
+//   dw[c][tap] = sum_v xc[v][c] * x1[v + delta(tap)],   sum_c[c] = sum_v xc[v][c],   sum_1 = sum_v x1[v].
+// GEMM D[m][c] += A[v][m] * B[v][c] over voxel rows v (K), both operands MN-major: B = the NDHWC tile of xc straight
+// from TMA, A = [x_hi(tap 0..26), 1.0, 0.. | x_lo(tap 0..26), 0..] built in shared memory from the fp32 halo of x1
+// (rows 0..26: hi products, row 27: sum_c, rows 32..58: lo products; rows 64..127 of the M=128 MMA are don't-care).
+// Persistent CTAs stride over 16x8x1 voxel tiles; fp32 partials per CTA, deterministic finalize.
+// =================================================================================================
+static constexpr int kWg1Stages = 2;
+
+__global__ void __launch_bounds__(192)
+wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmXC, int N, int D, int H, int W,
+                   int tiles_w, int tiles_h, long long total_tiles, float* __restrict__ partial) {
+  constexpr int A_STAGE = 2 * kTileBytes;   // chunk 0 built, chunk 1 (M rows 64..127) never read back
+  constexpr int B_STAGE = kTileBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kWg1Stages * A_STAGE;
+  float* xs = reinterpret_cast<float*>(smem_b + kWg1Stages * B_STAGE);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(xs + ((kHRows + 3) & ~3));
+  uint64_t* b_full = a_full + kWg1Stages;
+  uint64_t* empty = b_full + kWg1Stages;       // stage (A and B) released by the MMA commit
+  uint64_t* tmem_full_bar = empty + kWg1Stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* red = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // 4 floats: per-warp sum_1
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 0-3 builders/epilogue, 4 TMA, 5 MMA
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long my_tiles = first < total_tiles ? (total_tiles - first + step - 1) / step : 0;
+
+  if (warp_id == 4 && lane == 0) {
+    prefetch_tmap(&tmXC);
+    for (int s = 0; s < kWg1Stages; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_id == 5) tmem_alloc(tmem_ptr_smem, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](long long id, int& w0, int& h0, int& d0, long long& n) {
+    const int tw = (int)(id % tiles_w); id /= tiles_w;
+    const int th = (int)(id % tiles_h); id /= tiles_h;
+    d0 = (int)(id % D);
+    n = id / D;
+    w0 = tw * kHW; h0 = th * kHH;
+  };
+
+  if (warp_id == 4) {
+    if (lane == 0) {
+      for (long long it = 0; it < my_tiles; ++it) {
+        const int s = (int)(it % kWg1Stages);
+        mbar_wait(&empty[s], (uint32_t)((it / kWg1Stages) & 1) ^ 1u);
+        int w0, h0, d0; long long n;
+        decode(first + it * step, w0, h0, d0, n);
+        mbar_expect_tx(&b_full[s], B_STAGE);
+        tma_load_5d(smem_b + s * B_STAGE, &tmXC, &b_full[s], 0, w0, h0, d0, (int)n);
+      }
+    }
+  } else if (warp_id == 5) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % kWg1Stages);
+      const uint32_t ph = (uint32_t)((it / kWg1Stages) & 1);
+      mbar_wait(&a_full[s], ph);
+      mbar_wait(&b_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE), b_addr = smem_u32(smem_b + s * B_STAGE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 voxel rows per UMMA
+          umma_bf16(tmem_base, make_smem_desc(a_addr + k * 2048, kTileBytes, 1024),
+                    make_smem_desc(b_addr + k * 2048, kTileBytes, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+        if (it == my_tiles - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int row = threadIdx.x;                          // voxel row of the tile
+    const int ow = row % kHW, oh = row / kHW;
+    float s1 = 0.f;
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % kWg1Stages);
+      int w0, h0, d0; long long n;
+      decode(first + it * step, w0, h0, d0, n);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous iteration's halo reads are done
+      for (int i = threadIdx.x; i < kHRows; i += 128) {
+        const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
+        const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+        float v = 0.f;
+        if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+          v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+        xs[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = 0.f, b = 0.f;
+        if (2 * j < 27) a = xs[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
+        if (2 * j + 1 < 27) b = xs[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
+        if (2 * j + 1 == 27) b = 1.0f;                     // row 27 of D accumulates sum_v xc[v][c]
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+      }
+      s1 += xs[(1 * kHBH + oh + 1) * kHBW + ow + 1];       // centre tap; zero outside the volume
+      mbar_wait(&empty[s], (uint32_t)((it / kWg1Stages) & 1) ^ 1u);
+      uint8_t* r0 = smem_a + s * A_STAGE + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
+    }
+    // ---- epilogue: rows 0..63 of D -> partial[cta][m][c]; per-CTA sum_1 ----
+    s1 = warp_sum(s1);
+    if (lane == 0) red[warp_id] = s1;
+    float* dst = partial + (long long)blockIdx.x * (64 * 64 + 4);   // 16-byte aligned stride
+    if (my_tiles > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      uint32_t v[32];
+      if (my_tiles > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp_id * 32) << 16) + (uint32_t)(j * 32), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (warp_id < 2) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(dst + row * 64 + j * 32 + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) dst[64 * 64] = red[0] + red[1] + red[2] + red[3];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 5) tmem_dealloc(tmem_base, 64);
+}
+
+__global__ void wgrad_c1_tc_finalize_kernel(const float* __restrict__ partial, int nctas, int flip, float* dw,
+                                            float* sum_c, float* sum_1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 27*64 (dw), then 64 (sum_c), then 1
+  const int per = 64 * 64 + 4;
+  if (i < 27 * 64) {
+    const int t = i / 64, c = i % 64;
+    const int m = flip ? 26 - t : t;
+    double a = 0.0;
+    for (int b = 0; b < nctas; ++b)
+      a += (double)partial[(long long)b * per + m * 64 + c] + (double)partial[(long long)b * per + (32 + m) * 64 + c];
+    dw[c * 27 + t] = (float)a;
+  } else if (i < 27 * 64 + 64) {
+    const int c = i - 27 * 64;
+    double a = 0.0;
+    for (int b = 0; b < nctas; ++b) a += (double)partial[(long long)b * per + 27 * 64 + c];
+    if (sum_c) sum_c[c] = (float)a;
+  } else if (i == 27 * 64 + 64) {
+    double a = 0.0;
+    for (int b = 0; b < nctas; ++b) a += (double)partial[(long long)b * per + 64 * 64];
+    if (sum_1) sum_1[0] = (float)a;
+  }
+}
+
+static constexpr int kWg1Ctas = 148 * 2;
+size_t wgrad_c1_tc_workspace_bytes() { return (size_t)kWg1Ctas * (64 * 64 + 4) * sizeof(float); }
+
+int wgrad_c1_tc(const void* xc, const float* x1, float* dw, float* sum_c, float* sum_1, int N, int D, int H, int W,
+                int flip, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SIVAE_CHECK(ws && ws_bytes >= wgrad_c1_tc_workspace_bytes(), "wgrad_c1_tc: workspace too small");
+  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "wgrad_c1_tc: empty tensor");
+  CUtensorMap tmXC;
+  if (make_act_tmap(&tmXC, xc, N, D, H, W, 64, kHW, kHH, 1)) return -1;
+  const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
+  const long long total = (long long)tiles_w * tiles_h * D * N;
+  const int ctas = (int)(total < kWg1Ctas ? total : kWg1Ctas);
+  constexpr int smem = kWg1Stages * (2 * kTileBytes + kTileBytes) + ((kHRows + 3) & ~3) * 4 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(wgrad_c1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                   "cudaFuncSetAttribute(wgrad_c1_tc)"))
+      return -1;
+    attr_set = true;
+  }
+  wgrad_c1_tc_kernel<<<ctas, 192, smem, st>>>(x1, tmXC, N, D, H, W, tiles_w, tiles_h, total, (float*)ws);
+  SIVAE_LAUNCH_OK("wgrad_c1_tc_kernel");
+  wgrad_c1_tc_finalize_kernel<<<cdiv(27 * 64 + 64 + 1, 128), 128, 0, st>>>((const float*)ws, ctas, flip, dw, sum_c, sum_1);
+  SIVAE_LAUNCH_OK("wgrad_c1_tc_finalize_kernel");
+  return 0;
+}
+
 // fp32 [C][27] (one output channel) -> bf16 [27][16][C]; the filter (tap-flipped when `flip`) is split into
 // row 0 = bf16(w) and row 1 = bf16(w - bf16(w)) so the two accumulator columns add up to (almost) fp32 weights
 // at no extra MMA cost (the N = 16 tile is the minimum anyway); rows 2..15 are zero.
@@ -665,6 +1180,35 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
   SIVAE_CHECK(p >= 0.f && p < 1.f, "conv3_to1: dropout p=%f out of range", p);
   SIVAE_CHECK(ws && ws_bytes >= conv3_to1_workspace_bytes(C), "conv3_to1: workspace too small");
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_to1: empty tensor");
+  if (C == 64 && getenv("SIVAE_TO1_TAPWISE") == nullptr) {
+    // halo variant: the input tile is fetched once, all 27 taps are GEMM columns
+    pack_to1_halo_weights_kernel<<<16, 256, 0, st>>>(w, flip, (__nv_bfloat16*)ws);
+    SIVAE_LAUNCH_OK("pack_to1_halo_weights_kernel");
+    CUtensorMap tmA, tmB;
+    if (make_act_tmap(&tmA, x, N, D, H, W, 64, kHBW, kHBH, kHBD)) return -1;
+    {
+      uint64_t dims[3] = {64, 32, 2};
+      uint64_t strides[2] = {128, 32 * 128};
+      uint32_t box[3] = {64, 32, 1};
+      if (make_tmap_bf16(&tmB, ws, 3, dims, strides, box)) return -1;
+    }
+    ToOneEpilogue ep;
+    ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = make_seed_ref(seed); ep.p = p; ep.act = act;
+    const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
+    const long long ctas = (long long)tiles_w * tiles_h * D * N;
+    SIVAE_CHECK(ctas < (1ll << 31), "conv3_to1: too many tiles");
+    constexpr int smem = kHMTiles * kTileBytes + 2 * 32 * 128 + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (check_cuda(cudaFuncSetAttribute(conv3_to1_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                     "cudaFuncSetAttribute(conv3_to1_halo)"))
+        return -1;
+      attr_set = true;
+    }
+    conv3_to1_halo_kernel<<<(unsigned)ctas, 192, smem, st>>>(tmA, tmB, N, D, H, W, tiles_w, tiles_h, ep);
+    SIVAE_LAUNCH_OK("conv3_to1_halo_kernel");
+    return 0;
+  }
   pack_to1_weights_kernel<<<cdiv(27 * 16 * C, 256), 256, 0, st>>>(w, C, flip, (__nv_bfloat16*)ws);
   SIVAE_LAUNCH_OK("pack_to1_weights_kernel");
   ConvGeom g;

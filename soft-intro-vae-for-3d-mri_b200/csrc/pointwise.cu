@@ -45,14 +45,14 @@ __device__ __forceinline__ void drop8(const uint8_t* mask, float p, unsigned lon
 #pragma unroll
     for (int k = 0; k < 8; ++k) ks[k] = (((k < 4 ? m.x : m.y) >> ((k & 3) * 8)) & 0xffu) ? inv : 0.f;
   } else {
-    // e0 is a multiple of 8: two Philox blocks cover the 8 elements
+    // e0 is a multiple of 8: one Philox block (8 x 16 random bits) covers the 8 elements, same stream as philox_keep
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const unsigned long long b = (unsigned long long)e0 >> 2;
-    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u), key);
-    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(b + 1), (uint32_t)((b + 1) >> 32), 0u, 0u), key);
-    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const unsigned long long b = (unsigned long long)e0 >> 3;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t thr = drop_threshold(p);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ks[k] = ((float)(w[k] >> 8) * (1.0f / 16777216.0f) >= p) ? inv : 0.f;
+    for (int k = 0; k < 8; ++k) ks[k] = (((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) >= thr) ? inv : 0.f;
   }
 }
 

@@ -260,12 +260,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ unsigned long long resolve_seed(const SeedRef& r) {
   return r.ctr ? r.seed + (*r.ctr) * 0x9E3779B97F4A7C15ull : r.seed;
 }
-// keep-decision for element `idx` of a dropout call identified by `seed`: uniform[0,1) >= p
+// Dropout decisions use 16 random bits each (p is quantised to 1/65536): one Philox4x32-10 block serves 8 elements.
+__device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.0f); }
+// keep-decision for element `idx` of a dropout call identified by `seed`: uniform16 >= p*65536
 __device__ __forceinline__ bool philox_keep(unsigned long long seed, unsigned long long idx, float p) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, 0u),
+  const unsigned long long b = idx >> 3;
+  uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), 0u, 0u),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
+  const int k = (int)(idx & 7);
+  const uint32_t w = (k >> 1) == 0 ? r.x : (k >> 1) == 1 ? r.y : (k >> 1) == 2 ? r.z : r.w;
+  return ((w >> ((k & 1) * 16)) & 0xffffu) >= drop_threshold(p);
 }
 
 }  // namespace sivae

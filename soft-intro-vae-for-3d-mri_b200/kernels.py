@@ -50,9 +50,13 @@ _SIGNATURES = {
     "sivae_bn_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i,
                               _vp, _f, _u64, _vp, _sz, _vp]),
     "sivae_c1_to_cn": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_c1_to_c64_workspace_bytes": (_sz, []),
+    "sivae_c1_to_c64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_cn_to_c1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp]),
     "sivae_wgrad_c1_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_wgrad_c1": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sivae_wgrad_c64_workspace_bytes": (_sz, []),
+    "sivae_wgrad_c64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_relu_drop_bwd": (_i, [_vp, _vp, _vp, _ll, _f, _vp]),
     "sivae_reparam_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _ll, _vp]),
     "sivae_reparam_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
@@ -380,6 +384,13 @@ def c1_to_cn(x1, w, bias, flip: bool = False, out: Optional[torch.Tensor] = None
         out = torch.empty(n, d, h, ww, c, dtype=torch.bfloat16, device=x1.device)
     else:
         _req(out, torch.bfloat16, "out")
+    if t == 27 and c == 64 and not acc:
+        # tensor-core path: im2col built in shared memory, hi/lo bf16 split of both operands
+        lib = _L()
+        ws = _workspace(x1.device, lib.sivae_c1_to_c64_workspace_bytes(), "c1c64")
+        _check(lib.sivae_c1_to_c64(_p(x1), _p(w), _p(bias), _p(out), n, d, h, ww, int(flip), _p(ws), ws.numel(),
+                                   _stream(x1)), "sivae_c1_to_c64")
+        return out
     _check(_L().sivae_c1_to_cn(_p(x1), _p(w), _p(bias), _p(out), n, d, h, ww, c, t, int(flip), int(acc), _stream(x1)),
            "sivae_c1_to_cn")
     return out
@@ -415,10 +426,15 @@ def wgrad_c1(xc, x1, taps: int, flip: bool = False):
     _req(x1, torch.float32, "x1")
     n, d, h, ww, c = xc.shape
     lib = _L()
-    ws = _workspace(xc.device, lib.sivae_wgrad_c1_workspace_bytes(n, d, h, ww, c, taps), "wgrad_c1")
     dw = torch.empty(c, taps, dtype=torch.float32, device=xc.device)
     sum_c = torch.empty(c, dtype=torch.float32, device=xc.device)
     sum_1 = torch.empty(1, dtype=torch.float32, device=xc.device)
+    if taps == 27 and c == 64:
+        ws = _workspace(xc.device, lib.sivae_wgrad_c64_workspace_bytes(), "wgrad_c64")
+        _check(lib.sivae_wgrad_c64(_p(xc), _p(x1), _p(dw), _p(sum_c), _p(sum_1), n, d, h, ww, int(flip), _p(ws),
+                                   ws.numel(), _stream(xc)), "sivae_wgrad_c64")
+        return dw, sum_c, sum_1
+    ws = _workspace(xc.device, lib.sivae_wgrad_c1_workspace_bytes(n, d, h, ww, c, taps), "wgrad_c1")
     _check(lib.sivae_wgrad_c1(_p(xc), _p(x1), _p(dw), _p(sum_c), _p(sum_1), n, d, h, ww, c, taps, int(flip), _p(ws),
                               ws.numel(), _stream(xc)), "sivae_wgrad_c1")
     return dw, sum_c, sum_1
