@@ -218,6 +218,163 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
 }
 
 // =================================================================================================
+// fprop / dgrad, Cin = 64, "kw-copy" variant: A-tile reuse across taps.
+//
+// The tap-by-tap kernel above re-fetches a 16 KB input tile for each of the 27 taps (L2 -> SMEM bound, profiles/r01a).
+// Here a CTA owns TWO output tiles (the same wt x ht patch at depths d0 and d0+1) and, for each kw shift, loads ONE
+// tall box {64ch, wt, ht+2, 4 d-planes} (<= 80 KB).  Because wt*128 B is a multiple of the 1024-byte swizzle atom,
+// the A operand of tap (kd, kh) for tile j is the same buffer at byte offset ((kd+j)*(ht+2) + kh) * wt * 128: nine
+// taps x two tiles are served by descriptor arithmetic alone.  Each weight slab is used by both tiles.
+// L2 -> SMEM bytes per 128 outputs: 27*16 KB + 27*8 KB = 648 KB  ->  3*80/2 + 27*8/2 = 228 KB.
+// 7 warps: A producer, MMA issuer, B producer, 4 epilogue warps.
+// =================================================================================================
+struct KwGeom {
+  int N, D, H, W;
+  int wt, ht;           // 16x8 or 8x16 (wt*ht == 128)
+  int tiles_w, tiles_h, tiles_d;   // tiles_d = ceil(D/2)
+};
+
+template <int BLOCK_N, int B_STAGES>
+__global__ void __launch_bounds__(224, 1)
+conv3_kwcopy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const KwGeom g) {
+  constexpr int A_BUF = 640 * 128;                 // tall box, at most 16 x 10 x 4 rows
+  constexpr int B_BYTES = BLOCK_N * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + 2 * A_BUF;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + B_STAGES * B_BYTES);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + B_STAGES;
+  uint64_t* tmem_full_bar = b_empty + B_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long id = blockIdx.x;
+  const int tw = (int)(id % g.tiles_w); id /= g.tiles_w;
+  const int th = (int)(id % g.tiles_h); id /= g.tiles_h;
+  const int td = (int)(id % g.tiles_d);
+  const int n = (int)(id / g.tiles_d);
+  const int w0 = tw * g.wt, h0 = th * g.ht, d0 = td * 2;
+  const int nb = blockIdx.y;
+  const int plane_rows = g.wt * (g.ht + 2);        // rows per d-plane of the tall box
+  const uint32_t a_tx = (uint32_t)plane_rows * 4u * 128u;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    // ===== A producer: one tall box per kw shift, two buffers =====
+    if (lane == 0) {
+      for (int kw = 0; kw < 3; ++kw) {
+        const int s = kw & 1;
+        mbar_wait(&a_empty[s], ((uint32_t)(kw >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&a_full[s], a_tx);
+        tma_load_5d(smem + s * A_BUF, &tmA, &a_full[s], 0, w0 + kw - 1, h0 - 1, d0 - 1, n);
+      }
+    }
+  } else if (warp_id == 2) {
+    // ===== B producer: weight slab of tap (kd, kh, kw) in MMA order =====
+    if (lane == 0) {
+      int it = 0;
+      for (int kw = 0; kw < 3; ++kw)
+        for (int kdh = 0; kdh < 9; ++kdh, ++it) {
+          const int s = it % B_STAGES;
+          mbar_wait(&b_empty[s], ((uint32_t)(it / B_STAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&b_full[s], B_BYTES);
+          tma_load_3d(smem_b + s * B_BYTES, &tmB, &b_full[s], 0, nb * BLOCK_N, kdh * 3 + kw);
+        }
+    }
+  } else if (warp_id == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    int it = 0;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int as = kw & 1;
+      mbar_wait(&a_full[as], (uint32_t)(kw >> 1) & 1u);
+      const uint32_t a_base = smem_u32(smem + as * A_BUF);
+      for (int kdh = 0; kdh < 9; ++kdh, ++it) {
+        const int bs = it % B_STAGES;
+        mbar_wait(&b_full[bs], (uint32_t)(it / B_STAGES) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const int kd = kdh / 3, kh = kdh - kd * 3;
+          const uint32_t b_addr = smem_u32(smem_b + bs * B_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t a_addr = a_base + (uint32_t)(((kd + j) * (g.ht + 2) + kh) * g.wt) * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + (uint32_t)(j * BLOCK_N), make_smem_desc(a_addr + k * 32, 16, 1024),
+                        make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&b_empty[bs]);
+          if (kdh == 8) umma_commit(&a_empty[as]);
+          if (it == 26) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2) =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    uint8_t* out_stage = smem;                      // both A buffers are idle now
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+      for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BLOCK_N + c32 * 32), v);
+        tmem_ld_wait();
+        uint8_t* tile = out_stage + (j * (BLOCK_N / 64) + (c32 >> 1)) * kTileBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
+          const int chunk = (c32 & 1) * 4 + c;
+          *reinterpret_cast<uint4*>(tile + ((chunk ^ (row & 7)) << 4)) = pk;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp_id == 3 && lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (d0 + j < g.D) {
+#pragma unroll
+          for (int jb = 0; jb < BLOCK_N / 64; ++jb)
+            tma_store_5d(&tmC, out_stage + (j * (BLOCK_N / 64) + jb) * kTileBytes, nb * BLOCK_N + jb * 64, w0, h0, d0 + j, n);
+        }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+// =================================================================================================
 // wgrad
 // =================================================================================================
 struct WgradGeom {
@@ -537,6 +694,52 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64, "conv3_igemm: Cin=%d must be a multiple of 64", Cin);
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
+  if (Cin == 64 && getenv("SIVAE_CONV_TAPWISE") == nullptr) {
+    // kw-copy variant when the (w,h) planes tile well with 16x8 or 8x16 patches and depth pairs
+    KwGeom kg;
+    kg.N = N; kg.D = D; kg.H = H; kg.W = W;
+    const double e1 = (double)W * H / ((double)cdiv(W, 16) * 16 * cdiv(H, 8) * 8);
+    const double e2 = (double)W * H / ((double)cdiv(W, 8) * 8 * cdiv(H, 16) * 16);
+    kg.wt = e1 >= e2 ? 16 : 8;
+    kg.ht = e1 >= e2 ? 8 : 16;
+    const double eff = (e1 >= e2 ? e1 : e2) * ((double)D / (2.0 * cdiv(D, 2)));
+    if (eff >= 0.8) {
+      kg.tiles_w = cdiv(W, kg.wt); kg.tiles_h = cdiv(H, kg.ht); kg.tiles_d = cdiv(D, 2);
+      const long long ctas = (long long)kg.tiles_w * kg.tiles_h * kg.tiles_d * N;
+      SIVAE_CHECK(ctas < (1ll << 31), "conv3_igemm: too many tiles");
+      const int bn = (Cout % 128 == 0) ? 128 : 64;
+      CUtensorMap tA, tB, tC;
+      {
+        uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+        uint64_t strides[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
+        uint32_t box[5] = {64, (uint32_t)kg.wt, (uint32_t)(kg.ht + 2), 4, 1};
+        if (make_tmap_bf16(&tA, x, 5, dims, strides, box)) return -1;
+      }
+      if (make_act_tmap(&tC, y, N, D, H, W, Cout, kg.wt, kg.ht, 1)) return -1;
+      if (make_weight_tmap(&tB, wpack, 27, Cout, 64, bn)) return -1;
+      if (bn == 64) {
+        constexpr int smem = 2 * 640 * 128 + 4 * 64 * 128 + 1024 + 256;
+        static bool set64 = false;
+        if (!set64) {
+          if (check_cuda(cudaFuncSetAttribute(conv3_kwcopy_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              smem), "cudaFuncSetAttribute(conv3_kwcopy<64>)")) return -1;
+          set64 = true;
+        }
+        conv3_kwcopy_kernel<64, 4><<<dim3((unsigned)ctas, (unsigned)(Cout / 64)), 224, smem, st>>>(tA, tB, tC, kg);
+      } else {
+        constexpr int smem = 2 * 640 * 128 + 3 * 128 * 128 + 1024 + 256;
+        static bool set128 = false;
+        if (!set128) {
+          if (check_cuda(cudaFuncSetAttribute(conv3_kwcopy_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              smem), "cudaFuncSetAttribute(conv3_kwcopy<128>)")) return -1;
+          set128 = true;
+        }
+        conv3_kwcopy_kernel<128, 3><<<dim3((unsigned)ctas, (unsigned)(Cout / 128)), 224, smem, st>>>(tA, tB, tC, kg);
+      }
+      SIVAE_LAUNCH_OK("conv3_kwcopy_kernel");
+      return 0;
+    }
+  }
   ConvGeom g;
   fill_geom(g, N, D, H, W, Cin, kTapsPlain);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
