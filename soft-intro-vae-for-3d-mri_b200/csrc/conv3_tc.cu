@@ -694,8 +694,10 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64, "conv3_igemm: Cin=%d must be a multiple of 64", Cin);
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
-  if (Cin == 64 && getenv("SIVAE_CONV_TAPWISE") == nullptr) {
-    // kw-copy variant when the (w,h) planes tile well with 16x8 or 8x16 patches and depth pairs
+  if (Cin == 64 && getenv("SIVAE_CONV_KWCOPY") != nullptr) {
+    // EXPERIMENTAL, opt-in (parity-tested, but measured SLOWER than the tap-by-tap kernel: 1.83 ms vs 1.28 ms on
+    // 64->64 @ 8x80x96x80 -- the two 80 KB A buffers leave only a 4-deep 32 KB weight ring, which is latency-bound;
+    // see DESIGN.md section 9).  kw-copy variant when the (w,h) planes tile well with 16x8 or 8x16 patches.
     KwGeom kg;
     kg.N = N; kg.D = D; kg.H = H; kg.W = W;
     const double e1 = (double)W * H / ((double)cdiv(W, 16) * 16 * cdiv(H, 8) * 8);

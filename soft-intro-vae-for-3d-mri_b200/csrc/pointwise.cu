@@ -4,6 +4,8 @@
 //                                                              models/models.py:15-22,39-41,53-60,94-95,121-122
 // One thread owns a fixed group of 8 channels (one 16-byte vector) and walks voxels, so per-channel
 // reductions need no atomics: registers -> shared-memory tree -> per-block partials -> fp64 finalize.
+#include <cstdlib>
+
 #include "sivae_common.cuh"
 
 namespace sivae {
@@ -523,7 +525,8 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, flo
 // ------------------------------------------------------------------------------------------------
 static int grid_for(long long items, int threads) {
   long long b = (items + threads - 1) / threads;
-  if (b > 148ll * 8) b = 148ll * 8;
+  static const long long cap = getenv("SIVAE_PW_BLOCKS") ? atoll(getenv("SIVAE_PW_BLOCKS")) : 148ll * 8;
+  if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
 }
