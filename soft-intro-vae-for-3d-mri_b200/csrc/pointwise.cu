@@ -195,23 +195,24 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
   ldf8(shift + chunk * 8, sh);
   if constexpr (MODE == SIVAE_RESAMPLE_NONE) {
     // streaming case: issue the loads of 4 voxels before consuming them
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < items; i0 += stride * 4) {
+    // item i covers elements [8i, 8i+8): (i / cpc) * C + (i % cpc) * 8 == 8 * i, no division needed; 32-bit indices
+    const unsigned stride = gridDim.x * blockDim.x, nitems = (unsigned)items;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nitems; i0 += stride * 4) {
       uint4 ry[4], rr[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < items) {
-          const long long e0 = (i / cpc) * C + chunk * 8;
+        const unsigned i = i0 + u * stride;
+        if (i < nitems) {
+          const size_t e0 = (size_t)i * 8;
           ry[u] = *reinterpret_cast<const uint4*>(y + e0);
           if (res != nullptr) rr[u] = *reinterpret_cast<const uint4*>(res + e0);
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < items) {
-          const long long e0 = (i / cpc) * C + chunk * 8;
+        const unsigned i = i0 + u * stride;
+        if (i < nitems) {
+          const long long e0 = (long long)i * 8;
           float f[8], ks[8], a[8];
           unpack8(ry[u], f);
           if (res != nullptr) {
@@ -339,11 +340,11 @@ __device__ __forceinline__ void bwd_load(const __nv_bfloat16* __restrict__ g, co
   if (MODE == SIVAE_RESAMPLE_NONE) {
     raw.g = *reinterpret_cast<const uint4*>(g + e0);
   } else {
-    const int w = (int)(v % W);
-    const int h = (int)((v / W) % H);
-    const int d = (int)((v / ((long long)W * H)) % D);
-    const long long n = v / ((long long)W * H * D);
-    const long long vo = ((n * (D / 2) + d / 2) * (H / 2) + h / 2) * (W / 2) + w / 2;
+    const unsigned vv = (unsigned)v;               // host guarantees nvox < 2^31
+    const unsigned w = vv % (unsigned)W, t1 = vv / (unsigned)W;
+    const unsigned h = t1 % (unsigned)H, t2 = t1 / (unsigned)H;
+    const unsigned d = t2 % (unsigned)D, n = t2 / (unsigned)D;
+    const size_t vo = (((size_t)n * (D / 2) + d / 2) * (H / 2) + h / 2) * (W / 2) + w / 2;
     raw.g = *reinterpret_cast<const uint4*>(g + vo * C + chunk * 8);
   }
   if (res != nullptr) raw.r = *reinterpret_cast<const uint4*>(res + e0);
@@ -474,18 +475,19 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16
       if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
     }
   } else {
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < items; i0 += stride * kBwdUnroll) {
+    const unsigned ucpc = (unsigned)cpc, ustride = (unsigned)stride, nitems = (unsigned)items;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nitems; i0 += ustride * kBwdUnroll) {
       BwdRaw raw[kBwdUnroll];
 #pragma unroll
       for (int u = 0; u < kBwdUnroll; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < items) bwd_load<MODE>(g, y, res, mask, i / cpc, chunk, D, H, W, C, raw[u]);
+        const unsigned i = i0 + u * ustride;
+        if (i < nitems) bwd_load<MODE>(g, y, res, mask, (long long)(i / ucpc), chunk, D, H, W, C, raw[u]);
       }
 #pragma unroll
       for (int u = 0; u < kBwdUnroll; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < items) {
-          const long long v = i / cpc;
+        const unsigned i = i0 + u * ustride;
+        if (i < nitems) {
+          const long long v = (long long)(i / ucpc);
           float dt[8], xh[8], o[8];
           bwd_compute<MODE>(raw[u], res != nullptr, mask, p, seed, v * C + chunk * 8, mu, is, ga, be, slope, dt, xh);
 #pragma unroll
@@ -574,6 +576,7 @@ int bn_act_fwd(const void* y, const float* scale, const float* shift, const void
   if (check_resample("bn_act_fwd", D, H, W, resample)) return -2;
   const long long nvox = (long long)N * D * H * W;
   SIVAE_CHECK(nvox > 0, "bn_act_fwd: empty tensor");
+  SIVAE_CHECK(nvox * (C / 8) < (1ll << 31), "bn_act_fwd: tensor too large for 32-bit item indices");
   const long long items = (resample == SIVAE_RESAMPLE_AVGPOOL2 ? nvox / 8 : nvox) * (C / 8);
   const int blocks = grid_for(items, 256);
   const __nv_bfloat16 *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
@@ -597,6 +600,7 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   SIVAE_CHECK(ws && ws_bytes >= bn_workspace_bytes(C), "bn_act_bwd: workspace too small");
   const long long nvox = (long long)N * D * H * W;
   SIVAE_CHECK(nvox > 0, "bn_act_bwd: empty tensor");
+  SIVAE_CHECK(nvox * (C / 8) < (1ll << 31), "bn_act_bwd: tensor too large for 32-bit item indices");
   const int blocks = reduce_blocks(nvox, C);
   float* partial = (float*)ws;
   float* coef = partial + (size_t)kBnMaxBlocks * 2 * C;

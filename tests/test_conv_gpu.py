@@ -18,9 +18,9 @@ SHAPES = [
     (1, 20, 24, 20, 64, 128),     # headline mid resolution
     (1, 5, 7, 9, 128, 64),        # every extent odd: overhanging boxes on all sides
     (1, 1, 1, 1, 64, 64),         # single voxel
-    (1, 7, 16, 40, 64, 64),       # kw-copy kernel: 8x16 patches, odd depth (half-empty last depth pair)
-    (2, 4, 24, 32, 64, 128),      # kw-copy kernel, N = 128 variant, batch 2
-    (1, 6, 30, 44, 64, 64),       # kw-copy kernel with ragged W and H (clipped stores, OOB-filled loads)
+    (1, 7, 16, 40, 64, 64),       # shapes the opt-in kw-copy kernel takes (SIVAE_CONV_KWCOPY=1): 8x16 patches, odd depth
+    (2, 4, 24, 32, 64, 128),      # ... its N = 128 variant, batch 2
+    (1, 6, 30, 44, 64, 64),       # ... ragged W and H (clipped stores, OOB-filled loads)
 ]
 
 

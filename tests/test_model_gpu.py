@@ -170,7 +170,7 @@ def test_headline_step_vs_oracle(shape):
     for k in sorted(terms):
         if k in ref_terms:
             print(f"  {k:18s} cuda {terms[k]:14.6g}  oracle {ref_terms[k]:14.6g}  rel {abs(terms[k] - ref_terms[k]) / (abs(ref_terms[k]) + 1e-30):.2e}")
-    _check_terms(terms, ref_terms, first=1e-3, second=5e-3, kl=2e-2, exp_rel=1e-2)
+    _check_terms(terms, ref_terms, first=1e-3, second=5e-3, kl=5e-2, exp_rel=1e-2)
     allref = {**gE, **gD}
     worst = min((_cos(grads[k], v), k) for k, v in allref.items()
                 if not k.endswith("blocks.0.0.bias") and k != "decoder.blocks.0.0.weight" and v.numel() >= 16)
