@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
       act_chunk(y, res, sc, sh, v * C + chunk * 8, slope, mask, p, seed, a);
       st8(out + v * C + chunk * 8, a);
     } else if (MODE == SIVAE_RESAMPLE_AVGPOOL2) {
-      const int Wo = W / 2, Ho = H / 2, Do = D / 2;
-      const int wo = (int)(v % Wo);
-      const int ho = (int)((v / Wo) % Ho);
-      const int dd = (int)((v / ((long long)Wo * Ho)) % Do);
-      const long long n = v / ((long long)Wo * Ho * Do);
+      const unsigned Wo = W / 2, Ho = H / 2, Do = D / 2, vv = (unsigned)v;   // 32-bit: host checks item count < 2^31
+      const unsigned wo = vv % Wo, t1 = vv / Wo;
+      const unsigned ho = t1 % Ho, t2 = t1 / Ho;
+      const unsigned dd = t2 % Do;
+      const long long n = t2 / Do;
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -408,6 +408,35 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
         s2[k] += dt[k] * xh[k];
       }
     }
+  } else if (MODE == SIVAE_RESAMPLE_AVGPOOL2 && res == nullptr && mask == nullptr && p <= 0.f) {
+    // walk POOLED voxels: one index decomposition and one g load serve the 8 children, whose y loads are all in flight
+    const unsigned Wo = W / 2, Ho = H / 2, Do = D / 2;
+    const unsigned nvo = (unsigned)(nvox / 8);
+    for (unsigned vo = blockIdx.x * lanes_v + threadIdx.x / cpc; vo < nvo; vo += (unsigned)stride) {
+      const unsigned wo = vo % Wo, t1 = vo / Wo;
+      const unsigned ho = t1 % Ho, t2 = t1 / Ho;
+      const unsigned dd = t2 % Do, n = t2 / Do;
+      const size_t v000 = (((size_t)n * D + 2 * dd) * H + 2 * ho) * W + 2 * wo;
+      uint4 ry[8];
+      float gp[8];
+      ld8(g + (size_t)vo * C + chunk * 8, gp);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        ry[q] = *reinterpret_cast<const uint4*>(y + (v000 + ((size_t)(q >> 2) * H + ((q >> 1) & 1)) * W + (q & 1)) * C + chunk * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float f[8];
+        unpack8(ry[q], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (f[k] - mu[k]) * is[k];
+          const float t = fmaf(xh, ga[k], be[k]);
+          const float dt = gp[k] * 0.125f * (t > 0.f ? 1.f : slope);
+          s1[k] += dt;
+          s2[k] += dt * xh;
+        }
+      }
+    }
   } else {
     for (long long v0 = (long long)blockIdx.x * lanes_v + threadIdx.x / cpc; v0 < nvox; v0 += stride * kBwdUnroll) {
       BwdRaw raw[kBwdUnroll];
@@ -473,6 +502,35 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16
       for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
       st8(dconv + v * C + chunk * 8, o);
       if (dres != nullptr) st8(dres + v * C + chunk * 8, dt);
+    }
+  } else if (MODE == SIVAE_RESAMPLE_AVGPOOL2 && res == nullptr && mask == nullptr && p <= 0.f && dres == nullptr) {
+    const unsigned Wo = W / 2, Ho = H / 2, Do = D / 2, ucpc = (unsigned)cpc;
+    const unsigned npooled = (unsigned)(items / 8);
+    for (unsigned io = blockIdx.x * blockDim.x + threadIdx.x; io < npooled; io += (unsigned)stride) {
+      const unsigned vo = io / ucpc;
+      const unsigned wo = vo % Wo, t1 = vo / Wo;
+      const unsigned ho = t1 % Ho, t2 = t1 / Ho;
+      const unsigned dd = t2 % Do, n = t2 / Do;
+      const size_t v000 = (((size_t)n * D + 2 * dd) * H + 2 * ho) * W + 2 * wo;
+      uint4 ry[8];
+      float gp[8];
+      ld8(g + (size_t)vo * C + chunk * 8, gp);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        ry[q] = *reinterpret_cast<const uint4*>(y + (v000 + ((size_t)(q >> 2) * H + ((q >> 1) & 1)) * W + (q & 1)) * C + chunk * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float f[8], o[8];
+        unpack8(ry[q], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (f[k] - mu[k]) * is[k];
+          const float t = fmaf(xh, ga[k], be[k]);
+          const float dt = gp[k] * 0.125f * (t > 0.f ? 1.f : slope);
+          o[k] = ga[k] * is[k] * (dt - c1[k] - xh * c2[k]);
+        }
+        st8(dconv + (v000 + ((size_t)(q >> 2) * H + ((q >> 1) & 1)) * W + (q & 1)) * C + chunk * 8, o);
+      }
     }
   } else {
     const unsigned ucpc = (unsigned)cpc, ustride = (unsigned)stride, nitems = (unsigned)items;
