@@ -463,6 +463,130 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
   block_reduce_channels(s1, s2, C, cpc, partial);
 }
 
+// ---- lean kernels for the common case: no resample, no residual, no dropout --------------------------------------
+// Folded per-channel constants keep the register count low enough for 4 voxels (128 B) in flight per thread at
+// >= 2 CTAs/SM, which is what the HBM latency-bandwidth product needs (~64 KB in flight per SM).
+//   t = y*S + T (S = gamma*invstd, T = beta - mean*S);  xhat = y*invstd + M2 (M2 = -mean*invstd);  dt = g * act'(t)
+template <bool DROP>
+__global__ void __launch_bounds__(kBnThreads, 2)
+bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, long long nvox, int C,
+                           float slope, float p, const SeedRef sref, float* __restrict__ partial) {
+  const unsigned long long seed = DROP ? resolve_seed(sref) : 0ull;
+  const int cpc = C >> 3;
+  const int chunk = threadIdx.x % cpc;
+  const int lanes_v = kBnThreads / cpc;
+  float S[8], T[8], IS[8], M2[8];
+  {
+    float mu[8], ga[8], be[8];
+    ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, IS); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      S[k] = ga[k] * IS[k];
+      T[k] = be[k] - mu[k] * S[k];
+      M2[k] = -mu[k] * IS[k];
+    }
+  }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const unsigned stride = gridDim.x * lanes_v, nv = (unsigned)nvox;
+  for (unsigned v0 = blockIdx.x * lanes_v + threadIdx.x / cpc; v0 < nv; v0 += stride * 4) {
+    uint4 ry[4], rg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned v = v0 + u * stride;
+      if (v < nv) {
+        const size_t e0 = (size_t)v * C + chunk * 8;
+        ry[u] = *reinterpret_cast<const uint4*>(y + e0);
+        rg[u] = *reinterpret_cast<const uint4*>(g + e0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v0 + u * stride < nv) {
+        float f[8], gp[8];
+        unpack8(ry[u], f);
+        unpack8(rg[u], gp);
+        if (DROP) {
+          float ks[8];
+          drop8(nullptr, p, seed, (long long)((size_t)(v0 + u * stride) * C + chunk * 8), ks);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gp[k] *= ks[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float t = fmaf(f[k], S[k], T[k]);
+          const float dt = t > 0.f ? gp[k] : gp[k] * slope;
+          s1[k] += dt;
+          s2[k] = fmaf(dt, fmaf(f[k], IS[k], M2[k]), s2[k]);
+        }
+      }
+    }
+  }
+  block_reduce_channels(s1, s2, C, cpc, partial);
+}
+
+// dconv = A*dt + y*U + V with A = gamma*invstd, U = -A*invstd*c2, V = A*(mean*invstd*c2 - c1)
+template <bool DROP>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ coef, __nv_bfloat16* __restrict__ dconv, long long items, int C,
+                          float slope, float p, const SeedRef sref) {
+  const unsigned long long seed = DROP ? resolve_seed(sref) : 0ull;
+  const int cpc = C >> 3;
+  const int chunk = (int)(threadIdx.x % cpc);
+  float S[8], T[8], A[8], U[8], V[8];
+  {
+    float mu[8], is[8], ga[8], be[8], c1[8], c2[8];
+    ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+    ldf8(coef + chunk * 8, c1); ldf8(coef + C + chunk * 8, c2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      S[k] = ga[k] * is[k];
+      T[k] = be[k] - mu[k] * S[k];
+      A[k] = S[k];
+      U[k] = -A[k] * is[k] * c2[k];
+      V[k] = A[k] * (mu[k] * is[k] * c2[k] - c1[k]);
+    }
+  }
+  const unsigned stride = gridDim.x * blockDim.x, nitems = (unsigned)items;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nitems; i0 += stride * 4) {
+    uint4 ry[4], rg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nitems) {
+        ry[u] = *reinterpret_cast<const uint4*>(y + (size_t)i * 8);
+        rg[u] = *reinterpret_cast<const uint4*>(g + (size_t)i * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nitems) {
+        float f[8], gp[8], o[8];
+        unpack8(ry[u], f);
+        unpack8(rg[u], gp);
+        if (DROP) {
+          float ks[8];
+          drop8(nullptr, p, seed, (long long)((size_t)i * 8), ks);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gp[k] *= ks[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float t = fmaf(f[k], S[k], T[k]);
+          const float dt = t > 0.f ? gp[k] : gp[k] * slope;
+          o[k] = fmaf(A[k], dt, fmaf(f[k], U[k], V[k]));
+        }
+        st8(dconv + (size_t)i * 8, o);
+      }
+    }
+  }
+}
+
 // coef[0][c] = sum(dt)/n, coef[1][c] = sum(dt*xhat)/n ; dgamma = sum(dt*xhat), dbeta = sum(dt)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long nvox,
                                        float* __restrict__ coef, float* dgamma, float* dbeta) {
@@ -663,6 +787,21 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   float* partial = (float*)ws;
   float* coef = partial + (size_t)kBnMaxBlocks * 2 * C;
   const __nv_bfloat16 *gg = (const __nv_bfloat16*)g, *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
+  const bool plain = resample == SIVAE_RESAMPLE_NONE && res == nullptr && mask == nullptr && dres == nullptr;
+  if (plain) {
+    const SeedRef sr = make_seed_ref(seed);
+    const long long items = nvox * (C / 8);
+    const int ablk = grid_for(items, 256 * 4);
+    if (p > 0.f) bn_bwd_reduce_plain_kernel<true><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, partial);
+    else bn_bwd_reduce_plain_kernel<false><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, partial);
+    SIVAE_LAUNCH_OK("bn_bwd_reduce_plain_kernel");
+    bn_bwd_finalize_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, blocks, C, nvox, coef, dgamma, dbeta);
+    SIVAE_LAUNCH_OK("bn_bwd_finalize_kernel");
+    if (p > 0.f) bn_bwd_apply_plain_kernel<true><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr);
+    else bn_bwd_apply_plain_kernel<false><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr);
+    SIVAE_LAUNCH_OK("bn_bwd_apply_plain_kernel");
+    return 0;
+  }
 #define SIVAE_BWD_REDUCE(M)                                                                                      \
   bn_act_bwd_reduce_kernel<M><<<blocks, kBnThreads, 0, st>>>(gg, yy, rr, mean, invstd, gamma, beta, N, D, H, W, C, \
                                                              slope, mask, p, make_seed_ref(seed), partial)

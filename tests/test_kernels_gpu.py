@@ -115,6 +115,16 @@ def test_philox_dropout_is_consistent_and_calibrated():
                                               need_dres=True)
     assert torch.equal(dres != 0, a != 0)
     assert abs(float(dbeta.sum()) / a.numel() - 1.0) < 0.02
+    # the lean kernels (taken when no dres is requested) regenerate the same Philox mask as the generic ones
+    yr = bf(*y.shape)
+    gr = bf(*y.shape)
+    gam, bet = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    mean, invstd, _, _ = S.bn_train_coeffs(yr, gam, bet, None, None, None, 0.1, 1e-5)
+    d1, _, dg1, db1 = K.bn_act_bwd(gr, yr, None, mean, invstd, gam, bet, 0.2, 0, None, p, 99, need_dres=True)
+    d2, _, dg2, db2 = K.bn_act_bwd(gr, yr, None, mean, invstd, gam, bet, 0.2, 0, None, p, 99, need_dres=False)
+    assert_bf16_close(d2, d1, "lean vs generic dconv under Philox dropout")
+    assert_f32_close(dg2, dg1, "dgamma", 1e-4)
+    assert_f32_close(db2, db1, "dbeta", 1e-4)
 
 
 # ------------------------------------------------------------------------------------------- thin convs
