@@ -158,13 +158,15 @@ def run_ours(args):
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
     net.to(dev).train()
-    # N > 1 runs eagerly: capturing the hook-launched NCCL all-reduces inside the whole-step graph deadlocked on
-    # this stack (torch 2.11 / NCCL 2.28), and the step is GPU-bound anyway (multi-GPU section)
-    use_graph = not args.no_graph and world == 1
+    # N = 1: the whole step is one CUDA graph.  N > 1: three graphs with the two NCCL gradient all-reduces issued
+    # between the replays (parallel.FlatGradReducer; graph.GraphedTrainStep).  --no-graph: eager step, and for
+    # N > 1 the bucketed reducer that overlaps NCCL with backward (parallel.GradReducer).
+    use_graph = not args.no_graph
     opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
     opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
-    red_e = P.GradReducer(net.encoder.parameters()) if world > 1 else None
-    red_d = P.GradReducer(net.decoder.parameters()) if world > 1 else None
+    Reducer = P.FlatGradReducer if use_graph else P.GradReducer
+    red_e = Reducer(net.encoder.parameters()) if world > 1 else None
+    red_d = Reducer(net.decoder.parameters()) if world > 1 else None
     hp = T.StepHyper()
     torch.manual_seed(1234 + rank)                          # disjoint synthetic shards / noise per rank
     F.manual_seed(1234 + rank)
@@ -183,8 +185,8 @@ def run_ours(args):
     graphed = None
     graph_note = None
     if use_graph:
-        # whole-step CUDA graph (sivae_b200.graph): ~1500 launches per step collapse into one replay; with N > 1
-        # the bucketed NCCL all-reduces are captured as well.  If the capture is refused the step runs eagerly.
+        # whole-step CUDA graph (sivae_b200.graph): ~1500 launches per step collapse into one replay (three replays
+        # + two NCCL calls with N > 1).  If the capture is refused the step runs eagerly.
         try:
             graphed = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real_dev, noise_dev, hp, warmup=2,
                                                         reducer_e=red_e, reducer_d=red_d)
@@ -248,6 +250,16 @@ def run_ours(args):
             torch.cuda.synchronize()
         launches = (K.launch_count() - n0) * args.steps
     ksum = kt.summary()
+    if rank == 0 and args.kernel_table:
+        # per kernel family / per shape table of the live CUDA-event timings (profiles/*_kernel_table.txt)
+        rows = []
+        for name, d in ksum.items():
+            for shape, v in d["by_shape"].items():
+                rows.append((v["ms"], name, shape, v["launches"], v["work"]))
+        with open(args.kernel_table, "w") as f:
+            f.write("ms_total  launches  ms_each  TFLOP/s(ref-equiv)  kernel  shape(N,D,H,W,Ci,Co)\n")
+            for ms_, name, shape, n_, work in sorted(rows, reverse=True):
+                f.write(f"{ms_:8.3f}  {n_:3d}  {ms_ / n_:8.4f}  {work / (ms_ * 1e-3) / 1e12:8.1f}  {name}  {shape}\n")
     for _ in range(1):
         step_e2e()
     ms_e2e, res = timed(step_e2e, args.steps)
@@ -317,6 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=LOCAL_BATCH, help="local batch per GPU (headline: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel/per-shape timing table here")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

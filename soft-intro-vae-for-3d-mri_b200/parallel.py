@@ -146,6 +146,58 @@ class GradReducer:
         self._hooks = []
 
 
+class FlatGradReducer:
+    """Gradient averaging with the ``.grad`` tensors of one parameter group living as views of ONE flat fp32
+    buffer, so the exchange of a phase is a single NCCL all-reduce(avg) on a fixed address.
+
+    This is the reducer of the CUDA-graph path (``graph.GraphedTrainStep`` with N > 1): backward accumulates
+    straight into the flat buffer inside the captured graph, ``finish()`` runs *between* graph replays on the
+    same stream, and the optimiser step of the next graph reads the averaged views.  Nothing is copied in or
+    out.  The price is no overlap with backward -- the exchange is 28 MB per phase (< 0.2 ms over NVLink
+    against a ~45 ms phase).
+
+    The flat buffer is built on the first ``finish()`` from the parameters that actually received a gradient
+    (the unused projection convs keep ``grad is None``, SURVEY Q1/Q2, so Adam keeps skipping them).  The
+    training step must then clear gradients with ``zero_grad(set_to_none=False)`` --
+    ``needs_persistent_grads`` tells the trainer.
+    """
+
+    needs_persistent_grads = True
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params]
+        self.flat = None
+        self.used: List[torch.nn.Parameter] = []
+
+    def _build(self):
+        self.used = [p for p in self.params if p.grad is not None]
+        if not self.used:
+            return
+        n = sum(p.numel() for p in self.used)
+        self.flat = torch.empty(n, dtype=self.used[0].grad.dtype, device=self.used[0].device)
+        o = 0
+        with torch.no_grad():
+            for p in self.used:
+                v = self.flat[o: o + p.numel()].view(p.shape)
+                v.copy_(p.grad)
+                p.grad = v
+                o += p.numel()
+
+    def finish(self):
+        """Call between ``loss.backward()`` and ``optimizer.step()``."""
+        if self.flat is None:
+            self._build()
+        if self.flat is None or self.world == 1:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
+
+
 def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
     """Make parameters and buffers identical on every rank (DataParallel keeps replica 0's)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

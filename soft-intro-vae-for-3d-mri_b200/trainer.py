@@ -73,20 +73,19 @@ def _set_requires_grad(module: nn.Module, flag: bool):
         p.requires_grad = flag
 
 
-def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer_d, hp: Optional[StepHyper] = None,
-                          reducer_e=None, reducer_d=None) -> Dict[str, torch.Tensor]:
-    """One iteration of utils/my_trainer.py:236-325 (E update then D update), without host syncs.
+def _zero_grad(optimizer, reducer):
+    # a FlatGradReducer keeps ``.grad`` as views of its flat exchange buffer: clear in place, do not drop them
+    optimizer.zero_grad(set_to_none=not getattr(reducer, "needs_persistent_grads", False))
 
-    ``reducer_e`` / ``reducer_d`` are optional ``parallel.GradReducer`` objects: their
-    ``finish()`` is called between ``backward()`` and ``optimizer.step()`` (bucketed NCCL all-reduce
-    launched from grad hooks during backward).  Returns the loss terms as device tensors.
-    """
+
+def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional[StepHyper] = None, reducer_e=None):
+    """Update-E half of one iteration, utils/my_trainer.py:242-287, up to and including ``lossE.backward()``
+    (the caller reduces the gradients across ranks, then calls ``optimizer_e.step()``).
+    -> (loss terms, z detached for the D phase :298)."""
     hp = hp or StepHyper()
     scale = hp.scale if hp.scale is not None else 8.0 / float(real_batch[0].numel())
-    beta_rec, beta_neg, beta_kl, gamma_r = hp.beta_rec, hp.beta_neg, hp.beta_kl, hp.gamma_r
+    beta_rec, beta_neg, beta_kl = hp.beta_rec, hp.beta_neg, hp.beta_kl
     F.begin_step(real_batch.device)          # new dropout epoch (device-side counter; CUDA-graph safe)
-
-    # ================= Update E (:242-289): encoder trainable, decoder frozen =================
     _set_requires_grad(model.encoder, True)
     _set_requires_grad(model.decoder, False)
     fake = model.decode(noise_batch)
@@ -105,15 +104,19 @@ def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer
     exp_elbo_rec = (-2 * scale * (beta_rec * loss_rec_rec + beta_neg * rec_kl_e)).exp().mean()
     lossE = scale * (beta_rec * loss_rec + beta_kl * lossE_real_kl) + 0.5 * (exp_elbo_fake + exp_elbo_rec)
     lossE = lossE * 10
-    optimizer_e.zero_grad()
+    _zero_grad(optimizer_e, reducer_e)
     lossE.backward()
-    if reducer_e is not None:
-        reducer_e.finish()
-    optimizer_e.step()
     out = dict(lossE=lossE.detach(), loss_rec=loss_rec.detach(), kl_real=lossE_real_kl.detach(),
                exp_elbo_fake=exp_elbo_fake.detach(), exp_elbo_rec=exp_elbo_rec.detach())
+    return out, z.detach()
 
-    # ================= Update D (:291-325): decoder trainable, encoder frozen =================
+
+def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optional[StepHyper] = None,
+                       reducer_d=None):
+    """Update-D half, utils/my_trainer.py:291-323, up to and including ``lossD.backward()``."""
+    hp = hp or StepHyper()
+    scale = hp.scale if hp.scale is not None else 8.0 / float(real_batch[0].numel())
+    beta_rec, beta_kl, gamma_r = hp.beta_rec, hp.beta_kl, hp.gamma_r
     _set_requires_grad(model.encoder, False)
     _set_requires_grad(model.decoder, True)
     fake = model.decode(noise_batch)
@@ -132,13 +135,28 @@ def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer
     lossD = scale * (beta_rec * loss_rec + 0.5 * beta_kl * (rec_kl + fake_kl)
                      + gamma_r * 0.5 * beta_rec * (loss_rec_rec + loss_fake_rec))
     lossD = lossD * 10
-    optimizer_d.zero_grad()
+    _zero_grad(optimizer_d, reducer_d)
     lossD.backward()
+    return dict(lossD=lossD.detach(), loss_rec_d=loss_rec.detach(), rec_kl=rec_kl.detach(), fake_kl=fake_kl.detach(),
+                loss_rec_rec_d=loss_rec_rec.detach(), loss_fake_rec_d=loss_fake_rec.detach())
+
+
+def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer_d, hp: Optional[StepHyper] = None,
+                          reducer_e=None, reducer_d=None) -> Dict[str, torch.Tensor]:
+    """One iteration of utils/my_trainer.py:236-325 (E update then D update), without host syncs.
+
+    ``reducer_e`` / ``reducer_d`` are optional ``parallel.GradReducer`` / ``FlatGradReducer`` objects: their
+    ``finish()`` is called between ``backward()`` and ``optimizer.step()``.  Returns the loss terms as device
+    tensors.
+    """
+    out, z = soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp, reducer_e)
+    if reducer_e is not None:
+        reducer_e.finish()
+    optimizer_e.step()
+    out.update(soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp, reducer_d))
     if reducer_d is not None:
         reducer_d.finish()
     optimizer_d.step()
-    out.update(lossD=lossD.detach(), loss_rec_d=loss_rec.detach(), rec_kl=rec_kl.detach(), fake_kl=fake_kl.detach(),
-               loss_rec_rec_d=loss_rec_rec.detach(), loss_fake_rec_d=loss_fake_rec.detach())
     return out
 
 
