@@ -17,6 +17,20 @@
 
 namespace sivae {
 
+// SM count of the current device (persistent kernels launch one CTA per SM); B200: 148.
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+
 static constexpr int kTileRows = 128;            // UMMA M (fprop) / max voxel rows per box
 static constexpr int kTileBytes = kTileRows * 128;  // one 128-row x 64-channel bf16 tile
 
@@ -208,7 +222,7 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
       for (int jb = 0; jb < BLOCK_N / 64; ++jb)
         tma_store_5d(&tmC.m[parity], out_stage + jb * kTileBytes, nb * BLOCK_N + jb * 64, w0, h0, d0, n);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read_all();
     }
     }  // EPI == 0
   }
@@ -218,160 +232,420 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
 }
 
 // =================================================================================================
-// fprop / dgrad, Cin = 64, "kw-copy" variant: A-tile reuse across taps.
+// fprop / dgrad, Cin = 64: persistent "kw-slab" kernel -- input tiles are reused across taps.
 //
-// The tap-by-tap kernel above re-fetches a 16 KB input tile for each of the 27 taps (L2 -> SMEM bound, profiles/r01a).
-// Here a CTA owns TWO output tiles (the same wt x ht patch at depths d0 and d0+1) and, for each kw shift, loads ONE
-// tall box {64ch, wt, ht+2, 4 d-planes} (<= 80 KB).  Because wt*128 B is a multiple of the 1024-byte swizzle atom,
-// the A operand of tap (kd, kh) for tile j is the same buffer at byte offset ((kd+j)*(ht+2) + kh) * wt * 128: nine
-// taps x two tiles are served by descriptor arithmetic alone.  Each weight slab is used by both tiles.
-// L2 -> SMEM bytes per 128 outputs: 27*16 KB + 27*8 KB = 648 KB  ->  3*80/2 + 27*8/2 = 228 KB.
+// The tap-by-tap kernel above re-fetches a 16 KB input tile and an 8 KB weight slab for each of the 27 taps of every
+// 128-voxel tile (648 KB of L2 -> SMEM traffic per tile: L2-bandwidth bound, profiles/r01a).  Here one work item is a
+// PAIR of output tiles -- the same 8(w) x 16(h) patch at depths d0 and d0+1 -- and for each kw shift the producer
+// loads ONE tall box {64 ch, 8 w, 18 h, 4 d} (72 KB).  Because a w-run of 8 voxels is exactly one 1024-byte swizzle
+// atom, the A operand of tap (kd, kh) of tile j is the same buffer at byte offset ((kd + j) * 18 + kh) * 1024: nine taps
+// x two tiles are served by descriptor arithmetic alone, and each weight slab feeds both tiles.
+//   L2 -> SMEM bytes per 128 outputs: 27*16 KB + 27*8 KB = 648 KB  ->  (3*72 KB + 27*8 KB) / 2 = 216 KB.
+// The CTA is persistent (one per SM, static round-robin over work items) with everything double-buffered so that no
+// role ever drains: two A boxes (the box of the next kw / next item streams in while the current one is multiplied),
+// a deep ring of weight slabs, two TMEM accumulator stages (epilogue of item i overlaps the MMAs of item i+1) and two
+// output staging tiles for the TMA stores.
 // 7 warps: A producer, MMA issuer, B producer, 4 epilogue warps.
 // =================================================================================================
 struct KwGeom {
   int N, D, H, W;
-  int wt, ht;           // 16x8 or 8x16 (wt*ht == 128)
-  int tiles_w, tiles_h, tiles_d;   // tiles_d = ceil(D/2)
+  int tiles_w, tiles_h, tiles_d;   // patches of 8 x 16, depth pairs: tiles_d = ceil(D/2)
+  int nblk;                        // Cout / 64
+  long long items;                 // tiles_w * tiles_h * tiles_d * N * nblk
 };
 
-template <int BLOCK_N, int B_STAGES>
+static constexpr int kKwW = 8, kKwH = 16;
+static constexpr int kKwBoxRows = kKwW * (kKwH + 2) * 4;     // 576 voxel rows per tall box
+static constexpr int kKwABytes = kKwBoxRows * 128;           // 73,728
+static constexpr int kKwBStages = 6;
+static constexpr int kKwBBytes = 64 * 128;                   // one 64 x 64 weight slab
+static constexpr int kKwSmem = 2 * kKwABytes + kKwBStages * kKwBBytes + 2 * kTileBytes + 1024 + 256;
+
 __global__ void __launch_bounds__(224, 1)
-conv3_kwcopy_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const KwGeom g) {
-  constexpr int A_BUF = 640 * 128;                 // tall box, at most 16 x 10 x 4 rows
-  constexpr int B_BYTES = BLOCK_N * 128;
+conv3_kw64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const KwGeom g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + 2 * A_BUF;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + B_STAGES * B_BYTES);
+  uint8_t* smem_b = smem + 2 * kKwABytes;
+  uint8_t* smem_o = smem_b + kKwBStages * kKwBBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_o + 2 * kTileBytes);
   uint64_t* a_empty = a_full + 2;
   uint64_t* b_full = a_empty + 2;
-  uint64_t* b_empty = b_full + B_STAGES;
-  uint64_t* tmem_full_bar = b_empty + B_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* b_empty = b_full + kKwBStages;
+  uint64_t* acc_full = b_empty + kKwBStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long id = blockIdx.x;
-  const int tw = (int)(id % g.tiles_w); id /= g.tiles_w;
-  const int th = (int)(id % g.tiles_h); id /= g.tiles_h;
-  const int td = (int)(id % g.tiles_d);
-  const int n = (int)(id / g.tiles_d);
-  const int w0 = tw * g.wt, h0 = th * g.ht, d0 = td * 2;
-  const int nb = blockIdx.y;
-  const int plane_rows = g.wt * (g.ht + 2);        // rows per d-plane of the tall box
-  const uint32_t a_tx = (uint32_t)plane_rows * 4u * 128u;
 
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
+    }
+    for (int s = 0; s < kKwBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     fence_barrier_init();
   }
-  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 256);   // 2 stages x 2 tiles x 64 fp32 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // work item -> (output-channel block, patch origin, depth pair, sample); nb fastest so both halves of a wide Cout
+  // hit the same input box in L2 back to back
+  auto decode = [&](long long item, int& nb, int& w0, int& h0, int& d0, int& n) {
+    nb = (int)(item % g.nblk); item /= g.nblk;
+    const int tw = (int)(item % g.tiles_w); item /= g.tiles_w;
+    const int th = (int)(item % g.tiles_h); item /= g.tiles_h;
+    const int td = (int)(item % g.tiles_d);
+    n = (int)(item / g.tiles_d);
+    w0 = tw * kKwW; h0 = th * kKwH; d0 = td * 2;
+  };
+
   if (warp_id == 0) {
-    // ===== A producer: one tall box per kw shift, two buffers =====
+    // ===== A producer: one tall box per kw shift, two buffers, running ahead across work items =====
     if (lane == 0) {
-      for (int kw = 0; kw < 3; ++kw) {
-        const int s = kw & 1;
-        mbar_wait(&a_empty[s], ((uint32_t)(kw >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&a_full[s], a_tx);
-        tma_load_5d(smem + s * A_BUF, &tmA, &a_full[s], 0, w0 + kw - 1, h0 - 1, d0 - 1, n);
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        int nb, w0, h0, d0, n;
+        decode(item, nb, w0, h0, d0, n);
+        for (int kw = 0; kw < 3; ++kw, ++it) {
+          const int s = it & 1;
+          mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[s], kKwABytes);
+          tma_load_5d(smem + s * kKwABytes, &tmA, &a_full[s], 0, w0 + kw - 1, h0 - 1, d0 - 1, n);
+        }
       }
     }
   } else if (warp_id == 2) {
     // ===== B producer: weight slab of tap (kd, kh, kw) in MMA order =====
     if (lane == 0) {
-      int it = 0;
-      for (int kw = 0; kw < 3; ++kw)
-        for (int kdh = 0; kdh < 9; ++kdh, ++it) {
-          const int s = it % B_STAGES;
-          mbar_wait(&b_empty[s], ((uint32_t)(it / B_STAGES) & 1u) ^ 1u);
-          mbar_expect_tx(&b_full[s], B_BYTES);
-          tma_load_3d(smem_b + s * B_BYTES, &tmB, &b_full[s], 0, nb * BLOCK_N, kdh * 3 + kw);
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int nb = (int)(item % g.nblk);
+        for (int kw = 0; kw < 3; ++kw)
+          for (int kdh = 0; kdh < 9; ++kdh, ++it) {
+            const int s = it % kKwBStages;
+            mbar_wait(&b_empty[s], ((it / kKwBStages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], kKwBBytes);
+            tma_load_3d(smem_b + s * kKwBBytes, &tmB, &b_full[s], 0, nb * 64, kdh * 3 + kw);
+          }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 128u;
+      for (int kw = 0; kw < 3; ++kw, ++a_it) {
+        const uint32_t s = a_it & 1;
+        mbar_wait(&a_full[s], (a_it >> 1) & 1u);
+        const uint32_t a_base = smem_u32(smem + s * kKwABytes);
+        for (int kdh = 0; kdh < 9; ++kdh, ++b_it) {
+          const uint32_t bs = b_it % kKwBStages;
+          mbar_wait(&b_full[bs], (b_it / kKwBStages) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const int kd = kdh / 3, kh = kdh - kd * 3;
+            const uint32_t b_addr = smem_u32(smem_b + bs * kKwBBytes);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t a_addr = a_base + (uint32_t)((kd + j) * (kKwH + 2) + kh) * 1024u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem + (uint32_t)(j * 64), make_smem_desc(a_addr + k * 32, 16, 1024),
+                          make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kw | kdh | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[bs]);
+            if (kdh == 8) {
+              umma_commit(&a_empty[s]);
+              if (kw == 2) umma_commit(&acc_full[as]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2): TMEM -> bf16 -> swizzled smem -> TMA store =====
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (warp_id == 3 && lane == 0);
+    uint32_t acc_it = 0, st_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      int nb, w0, h0, d0, n;
+      decode(item, nb, w0, h0, d0, n);
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_full[as], (acc_it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j, ++st_it) {
+        uint8_t* tile = smem_o + (st_it & 1) * kTileBytes;
+        // the store issued two tiles ago read this staging buffer: it must have drained before it is overwritten
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 128u + (uint32_t)(j * 64);
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
+        tmem_ld_wait();
+        if (j == 1) {   // both tiles of this accumulator stage are in registers: hand the stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        uint8_t* dst = tile + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v0[c * 8 + 0]), __uint_as_float(v0[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v0[c * 8 + 2]), __uint_as_float(v0[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v0[c * 8 + 4]), __uint_as_float(v0[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v0[c * 8 + 6]), __uint_as_float(v0[c * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = pk;
+          pk.x = pack_bf16x2(__uint_as_float(v1[c * 8 + 0]), __uint_as_float(v1[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v1[c * 8 + 2]), __uint_as_float(v1[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v1[c * 8 + 4]), __uint_as_float(v1[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v1[c * 8 + 6]), __uint_as_float(v1[c * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + (((4 + c) ^ (row & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (d0 + j < g.D) tma_store_5d(&tmC, tile, nb * 64, w0, h0, d0 + j, n);
+          tma_store_commit();   // a (possibly empty) group per tile keeps the wait_group arithmetic uniform
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// =================================================================================================
+// fprop / dgrad, Cin = Cout = 64: persistent "kd-fused" kernel -- three depth taps share one A read.
+//
+// Measured (profiles/r01c): with N = 64 the tcgen05 pipe is bound by SHARED-MEMORY OPERAND READS, not by L2 or the
+// MMA floor.  One UMMA 128x64x16 reads 4 KB of A + 2 KB of B = 192 B per floor-cycle against a 128 B/cycle tensor-core
+// read port (l1tex__data_pipe_tc_wavefronts_mem_shared at 64 % of peak when the tensor pipe is 43 % active) -- which is
+// why halving the L2 traffic (conv3_kw64_kernel) bought nothing.  The fix is more MACs per operand byte:
+//
+// an input tile of plane p, shifted by (kh, kw), feeds output plane p+1 through tap kd=0, plane p through kd=1 and
+// plane p-1 through kd=2, always on the SAME (h, w) rows = the same TMEM lanes.  So a CTA keeps the accumulators of
+// P = 4 consecutive output planes side by side in TMEM, in DESCENDING plane order (plane i of the chunk at column
+// 64*(P-1-i)), and issues ONE UMMA 128 x 192 x 16 per input tile and K step against the stacked weight slab
+// [kd=0 | kd=1 | kd=2] (192 rows): D columns [c, c+192) are exactly the accumulators of planes p+1, p, p-1.
+// A is read once for three taps: 4 KB + 6 KB per 3 x 128x64x16 MACs instead of 3 x 6 KB (1.8x fewer operand bytes);
+// chunk-edge tiles use the N = 128 / 64 sub-slabs.  The very first contribution to every accumulator (tap kd=0 of
+// pass (kh,kw)=(0,0)) is issued separately with accumulate = 0.
+//   work item  = 8(w) x 16(h) patch x 4 planes;   9 (kh,kw) passes x 6 input tiles of 16 KB, 9 x 24 KB of weights.
+//   L2 -> SMEM = (54*16 + 9*24) KB / 4 tiles = 270 KB per 128 outputs (tap-by-tap kernel: 648 KB).
+// Persistent, one CTA per SM; A ring 6 x 16 KB, B ring 3 x 24 KB, two TMEM stages of 256 columns (the epilogue of
+// item i overlaps the MMAs of item i+1), two output staging tiles for the TMA stores.
+// 7 warps: A producer, MMA issuer, B producer, 4 epilogue warps.
+// =================================================================================================
+struct KdGeom {
+  int N, D, H, W;
+  int tiles_w, tiles_h, tiles_d;   // 8 x 16 patches, chunks of 4 planes
+  long long items;
+};
+static constexpr int kKdP = 4;                       // output planes per work item
+static constexpr int kKdAStages = 6;
+static constexpr int kKdBStages = 3;
+static constexpr int kKdBBytes = 3 * 64 * 128;       // [kd=0 | kd=1 | kd=2] slabs of one (kh, kw)
+static constexpr int kKdSmem = kKdAStages * kTileBytes + kKdBStages * kKdBBytes + 2 * kTileBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(224, 1)
+conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const KdGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + kKdAStages * kTileBytes;
+  uint8_t* smem_o = smem_b + kKdBStages * kKdBBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_o + 2 * kTileBytes);
+  uint64_t* a_empty = a_full + kKdAStages;
+  uint64_t* b_full = a_empty + kKdAStages;
+  uint64_t* b_empty = b_full + kKdBStages;
+  uint64_t* acc_full = b_empty + kKdBStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    for (int s = 0; s < kKdAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kKdBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 512);   // 2 stages x 4 planes x 64 fp32 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](long long item, int& w0, int& h0, int& d0, int& n) {
+    const int tw = (int)(item % g.tiles_w); item /= g.tiles_w;
+    const int th = (int)(item % g.tiles_h); item /= g.tiles_h;
+    const int td = (int)(item % g.tiles_d);
+    n = (int)(item / g.tiles_d);
+    w0 = tw * kKwW; h0 = th * kKwH; d0 = td * kKdP;
+  };
+
+  if (warp_id == 0) {
+    // ===== A producer: per (kh, kw) pass the P + 2 input planes of the chunk, one 16 KB tile each =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        for (int pass = 0; pass < 9; ++pass) {
+          const int kh = pass / 3, kw = pass - kh * 3;
+          for (int t = 0; t < kKdP + 2; ++t, ++it) {
+            const int s = it % kKdAStages;
+            mbar_wait(&a_empty[s], ((it / kKdAStages) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[s], kTileBytes);
+            tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], 0, w0 + kw - 1, h0 + kh - 1, d0 - 1 + t, n);
+          }
+        }
+      }
+    }
+  } else if (warp_id == 2) {
+    // ===== B producer: the three kd slabs of one (kh, kw), stacked =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x)
+        for (int pass = 0; pass < 9; ++pass, ++it) {
+          const int s = it % kKdBStages;
+          mbar_wait(&b_empty[s], ((it / kKdBStages) & 1u) ^ 1u);
+          mbar_expect_tx(&b_full[s], kKdBBytes);
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+            tma_load_3d(smem_b + s * kKdBBytes + kd * (64 * 128), &tmB, &b_full[s], 0, 0, kd * 9 + pass);
         }
     }
   } else if (warp_id == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-    int it = 0;
-    for (int kw = 0; kw < 3; ++kw) {
-      const int as = kw & 1;
-      mbar_wait(&a_full[as], (uint32_t)(kw >> 1) & 1u);
-      const uint32_t a_base = smem_u32(smem + as * A_BUF);
-      for (int kdh = 0; kdh < 9; ++kdh, ++it) {
-        const int bs = it % B_STAGES;
-        mbar_wait(&b_full[bs], (uint32_t)(it / B_STAGES) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const int kd = kdh / 3, kh = kdh - kd * 3;
-          const uint32_t b_addr = smem_u32(smem_b + bs * B_BYTES);
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256u;
+      for (int pass = 0; pass < 9; ++pass, ++b_it) {
+        const uint32_t bs = b_it % kKdBStages;
+        mbar_wait(&b_full[bs], (b_it / kKdBStages) & 1u);
+        const uint32_t b_base = smem_u32(smem_b + bs * kKdBBytes);
+        for (int t = 0; t < kKdP + 2; ++t, ++a_it) {
+          const uint32_t sa = a_it % kKdAStages;
+          mbar_wait(&a_full[sa], (a_it / kKdAStages) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + sa * kTileBytes);
+            // input plane t of the chunk feeds output plane i = t - kd through tap kd, 0 <= i < P
+            int kd_lo = t - (kKdP - 1); if (kd_lo < 0) kd_lo = 0;
+            const int kd_hi = t < 2 ? t : 2;
+            if (pass == 0 && kd_lo == 0) {
+              // first contribution to output plane i = t: overwrite
+              const uint32_t col = (uint32_t)(64 * (kKdP - 1 - t));
+              constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t a_addr = a_base + (uint32_t)(((kd + j) * (g.ht + 2) + kh) * g.wt) * 128u;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
+                          make_smem_desc(b_base + k * 32, 16, 1024), idesc64, k != 0 ? 1u : 0u);
+              kd_lo = 1;
+            }
+            if (kd_lo <= kd_hi) {
+              const int nun = kd_hi - kd_lo + 1;                                  // stacked taps: 1..3
+              const uint32_t col = (uint32_t)(64 * (kKdP - 1 - (t - kd_lo)));    // highest output plane first
+              const uint32_t idesc = make_idesc_bf16(128, 64 * nun, 0, 0);
+              const uint32_t b_addr = b_base + (uint32_t)kd_lo * (64u * 128u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + (uint32_t)(j * BLOCK_N), make_smem_desc(a_addr + k * 32, 16, 1024),
-                        make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (it | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
+                          make_smem_desc(b_addr + k * 32, 16, 1024), idesc, 1u);
+            }
+            umma_commit(&a_empty[sa]);
+            if (t == kKdP + 1) {
+              umma_commit(&b_empty[bs]);
+              if (pass == 8) umma_commit(&acc_full[as]);
+            }
           }
-          umma_commit(&b_empty[bs]);
-          if (kdh == 8) umma_commit(&a_empty[as]);
-          if (it == 26) umma_commit(tmem_full_bar);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
-    // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2) =====
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2): TMEM -> bf16 -> swizzled smem -> TMA store =====
     const int q = warp_id & 3;
     const int row = q * 32 + lane;
-    uint8_t* out_stage = smem;                      // both A buffers are idle now
+    const bool issuer = (warp_id == 3 && lane == 0);
+    uint32_t acc_it = 0, st_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      int w0, h0, d0, n;
+      decode(item, w0, h0, d0, n);
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_full[as], (acc_it >> 1) & 1u);
+      tc_fence_after();
 #pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-#pragma unroll 1
-      for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BLOCK_N + c32 * 32), v);
+      for (int i = 0; i < kKdP; ++i, ++st_it) {
+        uint8_t* tile = smem_o + (st_it & 1) * kTileBytes;
+        // the store issued two tiles ago read this staging buffer: it must have drained before it is overwritten
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256u + (uint32_t)(64 * (kKdP - 1 - i));
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
         tmem_ld_wait();
-        uint8_t* tile = out_stage + (j * (BLOCK_N / 64) + (c32 >> 1)) * kTileBytes + row * 128;
+        if (i == kKdP - 1) {   // the whole accumulator stage is in registers / staged: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        uint8_t* dst = tile + row * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
-          pk.y = pack_bf16x2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
-          pk.z = pack_bf16x2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
-          pk.w = pack_bf16x2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
-          const int chunk = (c32 & 1) * 4 + c;
-          *reinterpret_cast<uint4*>(tile + ((chunk ^ (row & 7)) << 4)) = pk;
+          pk.x = pack_bf16x2(__uint_as_float(v0[c * 8 + 0]), __uint_as_float(v0[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v0[c * 8 + 2]), __uint_as_float(v0[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v0[c * 8 + 4]), __uint_as_float(v0[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v0[c * 8 + 6]), __uint_as_float(v0[c * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = pk;
+          pk.x = pack_bf16x2(__uint_as_float(v1[c * 8 + 0]), __uint_as_float(v1[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v1[c * 8 + 2]), __uint_as_float(v1[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v1[c * 8 + 4]), __uint_as_float(v1[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v1[c * 8 + 6]), __uint_as_float(v1[c * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + (((4 + c) ^ (row & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (d0 + i < g.D) tma_store_5d(&tmC, tile, 0, w0, h0, d0 + i, n);
+          tma_store_commit();   // a (possibly empty) group per tile keeps the wait_group arithmetic uniform
         }
       }
     }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp_id == 3 && lane == 0) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (d0 + j < g.D) {
-#pragma unroll
-          for (int jb = 0; jb < BLOCK_N / 64; ++jb)
-            tma_store_5d(&tmC, out_stage + (j * (BLOCK_N / 64) + jb) * kTileBytes, nb * BLOCK_N + jb * 64, w0, h0, d0 + j, n);
-        }
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+    if (issuer) tma_store_wait_read_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_id == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if (warp_id == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // =================================================================================================
@@ -552,6 +826,169 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp_id == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =================================================================================================
+// wgrad, Cin = 64: persistent "kw-slab" split-K kernel (the wgrad twin of conv3_kw64_kernel).
+//
+// The generic kernel above fetches one tap-shifted 16 KB input tile per (tap, voxel box): 27 x 16 KB + dy per 128 voxels,
+// and with one CTA per SM its 4-deep ring cannot keep enough bytes in flight (511 TFLOP/s on 64->64 @ 8x80x96x80).
+// Here a CTA owns ONE kw shift (blockIdx.x % 3) and a contiguous range of work items; an item is the pair of 8 x 16
+// voxel patches at depths d0, d0+1.  Per item it loads one tall input box {64 ch, 8 w, 18 h, 4 d} (72 KB) and the two
+// dy tiles; the 9 (kd, kh) taps x 2 tiles are MN-major A operands at byte offset ((kd + j) * 18 + kh) * 1024 inside the
+// box.  Units are paired into M = 128 MMAs through the descriptor's leading-dimension offset:
+//     acc 0..2: (kd,0)+(kd,1)  LBO = 1 patch row;   acc 3: (0,2)+(1,2)  LBO = 18 patch rows;
+//     acc 4   : (1,2)+(2,2)    (first half is a duplicate and is dropped by the epilogue).
+// 5 accumulators x 64 fp32 columns stay in TMEM across the whole K range; fp32 partials go to the same
+// [split][tap][ci][Cout] workspace layout as the generic kernel, so wgrad_reduce_kernel finishes the job.
+//   L2 -> SMEM bytes per 128 voxels: 27*16 + 2*16 = 464 KB  ->  3 * (72 + 32) / 2 = 156 KB.
+// =================================================================================================
+struct WgKwGeom {
+  int N, D, H, W;
+  int tiles_w, tiles_h, tiles_d;
+  int ntiles;                 // Cout / 64
+  int Cout;
+  long long items, items_per_split;
+};
+static constexpr int kWgKwBStages = 4;
+static constexpr int kWgKwSmem = 2 * kKwABytes + kWgKwBStages * kTileBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(224, 1)   // 7 warps: X producer, MMA issuer, dy producer, 4 epilogue warps
+conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                        const WgKwGeom g, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + 2 * kKwABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgKwBStages * kTileBytes);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + kWgKwBStages;
+  uint64_t* tmem_full_bar = b_empty + kWgKwBStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kw = blockIdx.x % 3;
+  const int ntile = blockIdx.x / 3;
+  const long long it0 = (long long)blockIdx.y * g.items_per_split;
+  const long long it1 = min(g.items, it0 + g.items_per_split);
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDY);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWgKwBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](long long item, int& w0, int& h0, int& d0, int& n) {
+    const int tw = (int)(item % g.tiles_w); item /= g.tiles_w;
+    const int th = (int)(item % g.tiles_h); item /= g.tiles_h;
+    const int td = (int)(item % g.tiles_d);
+    n = (int)(item / g.tiles_d);
+    w0 = tw * kKwW; h0 = th * kKwH; d0 = td * 2;
+  };
+
+  if (warp_id == 0) {
+    // ===== X producer: the tall box of this CTA's kw shift =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = it0; item < it1; ++item, ++it) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        const int s = it & 1;
+        mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&a_full[s], kKwABytes);
+        tma_load_5d(smem + s * kKwABytes, &tmX, &a_full[s], 0, w0 + kw - 1, h0 - 1, d0 - 1, n);
+      }
+    }
+  } else if (warp_id == 2) {
+    // ===== dy producer: the two output-gradient tiles of the item (depth d0 + 1 may be out of range: zero fill) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = it0; item < it1; ++item) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        for (int j = 0; j < 2; ++j, ++it) {
+          const int s = it % kWgKwBStages;
+          mbar_wait(&b_empty[s], ((it / kWgKwBStages) & 1u) ^ 1u);
+          mbar_expect_tx(&b_full[s], kTileBytes);
+          tma_load_5d(smem_b + s * kTileBytes, &tmDY, &b_full[s], ntile * 64, w0, h0, d0 + j, n);
+        }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    uint32_t a_it = 0, b_it = 0;
+    for (long long item = it0; item < it1; ++item, ++a_it) {
+      const uint32_t s = a_it & 1;
+      mbar_wait(&a_full[s], (a_it >> 1) & 1u);
+      const uint32_t a_base = smem_u32(smem + s * kKwABytes);
+      for (int j = 0; j < 2; ++j, ++b_it) {
+        const uint32_t bs = b_it % kWgKwBStages;
+        mbar_wait(&b_full[bs], (b_it / kWgKwBStages) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_addr = smem_u32(smem_b + bs * kTileBytes);
+          const bool first = (item == it0 && j == 0);
+#pragma unroll
+          for (int acc = 0; acc < 5; ++acc) {
+            // base unit (kd, kh) and the pair's leading-dimension offset (in 1024-byte patch rows)
+            const int kd = acc < 3 ? acc : acc - 3;
+            const int kh = acc < 3 ? 0 : 2;
+            const uint32_t lbo = acc < 3 ? 1024u : (uint32_t)(kKwH + 2) * 1024u;
+            const uint32_t a_addr = a_base + (uint32_t)((kd + j) * (kKwH + 2) + kh) * 1024u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // 16 voxel rows (2048 B) per UMMA
+              umma_bf16(tmem_base + (uint32_t)(acc * 64), make_smem_desc(a_addr + k * 2048, lbo, 1024),
+                        make_smem_desc(b_addr + k * 2048, kTileBytes, 1024), idesc, (first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&b_empty[bs]);
+          if (j == 1) {
+            umma_commit(&a_empty[s]);
+            if (item == it1 - 1) umma_commit(tmem_full_bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> fp32 partials [split][tap][ci][Cout] =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    const int half = row >> 6, ci = row & 63;
+#pragma unroll 1
+    for (int acc = 0; acc < 5; ++acc) {
+      int kd, kh;
+      if (acc < 3) { kd = acc; kh = half; }
+      else if (acc == 3) { kd = half; kh = 2; }
+      else { kd = 1 + half; kh = 2; }
+      const int tap = (kd * 3 + kh) * 3 + kw;
+      float* dst = partial + (((long long)blockIdx.y * 27 + tap) * 64 + ci) * g.Cout + ntile * 64;
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + j * 32), v);
+        tmem_ld_wait();
+        if (!(acc == 4 && half == 0)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(dst + j * 32 + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // upsample-fused mode: dw[co][ci][k] = sum_s sum_parity partial[s][(parity*8 + abc(k,parity))*cin_blocks + ci/64][ci%64][co]
 // (the transpose of the weight pre-summation: every 3x3x3 tap receives exactly one contribution per output parity)
 __global__ void wgrad_reduce_up_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
@@ -694,51 +1131,67 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64, "conv3_igemm: Cin=%d must be a multiple of 64", Cin);
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
-  if (Cin == 64 && getenv("SIVAE_CONV_KWCOPY") != nullptr) {
-    // EXPERIMENTAL, opt-in (parity-tested, but measured SLOWER than the tap-by-tap kernel: 1.83 ms vs 1.28 ms on
-    // 64->64 @ 8x80x96x80 -- the two 80 KB A buffers leave only a 4-deep 32 KB weight ring, which is latency-bound;
-    // see DESIGN.md section 9).  kw-copy variant when the (w,h) planes tile well with 16x8 or 8x16 patches.
+  // Cin = Cout = 64: persistent kd-fused kernel when 8 x 16 x 4 chunks tile the volume well (SIVAE_CONV_KD=0 disables
+  // it, =force takes it for every 64 -> 64 shape -- the parity tests use both).
+  if (Cin == 64 && Cout == 64) {
+    const char* kdenv = getenv("SIVAE_CONV_KD");
+    const bool off = kdenv != nullptr && kdenv[0] == '0';
+    const bool force = kdenv != nullptr && kdenv[0] == 'f';
+    KdGeom kg;
+    kg.N = N; kg.D = D; kg.H = H; kg.W = W;
+    kg.tiles_w = cdiv(W, kKwW); kg.tiles_h = cdiv(H, kKwH); kg.tiles_d = cdiv(D, kKdP);
+    kg.items = (long long)kg.tiles_w * kg.tiles_h * kg.tiles_d * N;
+    const double eff = ((double)W * H * D) / ((double)kg.tiles_w * kKwW * kg.tiles_h * kKwH * kg.tiles_d * kKdP);
+    if (!off && (force || (eff >= 0.8 && kg.items >= 2 * num_sms()))) {
+      CUtensorMap tA, tB, tC;
+      if (make_act_tmap(&tA, x, N, D, H, W, 64, kKwW, kKwH, 1)) return -1;
+      if (make_act_tmap(&tC, y, N, D, H, W, 64, kKwW, kKwH, 1)) return -1;
+      if (make_weight_tmap(&tB, wpack, 27, 64, 64, 64)) return -1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(conv3_kd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKdSmem),
+                       "cudaFuncSetAttribute(conv3_kd3)")) return -1;
+        attr_set = true;
+      }
+      const unsigned ctas = (unsigned)(kg.items < (long long)num_sms() ? kg.items : (long long)num_sms());
+      conv3_kd3_kernel<<<ctas, 224, kKdSmem, st>>>(tA, tB, tC, kg);
+      SIVAE_LAUNCH_OK("conv3_kd3_kernel");
+      return 0;
+    }
+  }
+  // Cin = 64: persistent kw-slab kernel.  OPT-IN (SIVAE_CONV_KW=1 when 8 x 16 x 2 patches tile the volume well, =force for
+  // every Cin = 64 shape): parity-tested, but it cut L2 traffic 3x without getting faster than the tap-by-tap kernel
+  // (1.31 vs 1.26 ms on 64->64 @ 8x80x96x80) -- the evidence that these layers are bound by shared-memory operand
+  // reads, which the kd-fused kernel above addresses.
+  if (Cin == 64 && getenv("SIVAE_CONV_KW") != nullptr) {
+    const char* kwenv = getenv("SIVAE_CONV_KW");
+    const bool off = kwenv[0] == '0';
+    const bool force = kwenv[0] == 'f';
     KwGeom kg;
     kg.N = N; kg.D = D; kg.H = H; kg.W = W;
-    const double e1 = (double)W * H / ((double)cdiv(W, 16) * 16 * cdiv(H, 8) * 8);
-    const double e2 = (double)W * H / ((double)cdiv(W, 8) * 8 * cdiv(H, 16) * 16);
-    kg.wt = e1 >= e2 ? 16 : 8;
-    kg.ht = e1 >= e2 ? 8 : 16;
-    const double eff = (e1 >= e2 ? e1 : e2) * ((double)D / (2.0 * cdiv(D, 2)));
-    if (eff >= 0.8) {
-      kg.tiles_w = cdiv(W, kg.wt); kg.tiles_h = cdiv(H, kg.ht); kg.tiles_d = cdiv(D, 2);
-      const long long ctas = (long long)kg.tiles_w * kg.tiles_h * kg.tiles_d * N;
-      SIVAE_CHECK(ctas < (1ll << 31), "conv3_igemm: too many tiles");
-      const int bn = (Cout % 128 == 0) ? 128 : 64;
+    kg.tiles_w = cdiv(W, kKwW); kg.tiles_h = cdiv(H, kKwH); kg.tiles_d = cdiv(D, 2);
+    kg.nblk = Cout / 64;
+    kg.items = (long long)kg.tiles_w * kg.tiles_h * kg.tiles_d * N * kg.nblk;
+    const double eff = ((double)W * H * D) / ((double)kg.tiles_w * kKwW * kg.tiles_h * kKwH * kg.tiles_d * 2);
+    if (!off && (force || (eff >= 0.8 && kg.items >= 148))) {
       CUtensorMap tA, tB, tC;
       {
         uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
         uint64_t strides[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
-        uint32_t box[5] = {64, (uint32_t)kg.wt, (uint32_t)(kg.ht + 2), 4, 1};
+        uint32_t box[5] = {64, (uint32_t)kKwW, (uint32_t)(kKwH + 2), 4, 1};
         if (make_tmap_bf16(&tA, x, 5, dims, strides, box)) return -1;
       }
-      if (make_act_tmap(&tC, y, N, D, H, W, Cout, kg.wt, kg.ht, 1)) return -1;
-      if (make_weight_tmap(&tB, wpack, 27, Cout, 64, bn)) return -1;
-      if (bn == 64) {
-        constexpr int smem = 2 * 640 * 128 + 4 * 64 * 128 + 1024 + 256;
-        static bool set64 = false;
-        if (!set64) {
-          if (check_cuda(cudaFuncSetAttribute(conv3_kwcopy_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              smem), "cudaFuncSetAttribute(conv3_kwcopy<64>)")) return -1;
-          set64 = true;
-        }
-        conv3_kwcopy_kernel<64, 4><<<dim3((unsigned)ctas, (unsigned)(Cout / 64)), 224, smem, st>>>(tA, tB, tC, kg);
-      } else {
-        constexpr int smem = 2 * 640 * 128 + 3 * 128 * 128 + 1024 + 256;
-        static bool set128 = false;
-        if (!set128) {
-          if (check_cuda(cudaFuncSetAttribute(conv3_kwcopy_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              smem), "cudaFuncSetAttribute(conv3_kwcopy<128>)")) return -1;
-          set128 = true;
-        }
-        conv3_kwcopy_kernel<128, 3><<<dim3((unsigned)ctas, (unsigned)(Cout / 128)), 224, smem, st>>>(tA, tB, tC, kg);
+      if (make_act_tmap(&tC, y, N, D, H, W, Cout, kKwW, kKwH, 1)) return -1;
+      if (make_weight_tmap(&tB, wpack, 27, Cout, 64, 64)) return -1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(conv3_kw64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem),
+                       "cudaFuncSetAttribute(conv3_kw64)")) return -1;
+        attr_set = true;
       }
-      SIVAE_LAUNCH_OK("conv3_kwcopy_kernel");
+      const unsigned ctas = (unsigned)(kg.items < (long long)num_sms() ? kg.items : (long long)num_sms());
+      conv3_kw64_kernel<<<ctas, 224, kKwSmem, st>>>(tA, tB, tC, kg);
+      SIVAE_LAUNCH_OK("conv3_kw64_kernel");
       return 0;
     }
   }
@@ -1099,7 +1552,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     if (threadIdx.x == 0) {
       tma_store_5d(&tmC, out_stage, 0, w0, h0, d0, (int)n);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read_all();
     }
   }
   tc_fence_before();
@@ -1457,11 +1910,38 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, int mode, 
   g.a_lbo = kTileBytes; g.a_sbo = 1024; g.b_lbo = kTileBytes; g.b_sbo = 1024;
 }
 
+// Plan of the persistent kw-slab wgrad kernel; returns false when the generic kernel should run instead
+// (SIVAE_WGRAD_KW=0 disables it, =force takes it for every Cin = 64 plain-mode shape).
+static bool wgrad_kw_plan(int N, int D, int H, int W, int Cin, int Cout, int mode, WgKwGeom& g, int& splits) {
+  if (mode != kTapsPlain || Cin != 64 || Cout % 64 != 0) return false;
+  const char* e = getenv("SIVAE_WGRAD_KW");
+  if (e != nullptr && e[0] == '0') return false;
+  const bool force = e != nullptr && e[0] == 'f';
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.tiles_w = cdiv(W, kKwW); g.tiles_h = cdiv(H, kKwH); g.tiles_d = cdiv(D, 2);
+  g.ntiles = Cout / 64;
+  g.Cout = Cout;
+  g.items = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
+  const double eff = ((double)W * H * D) / ((double)g.tiles_w * kKwW * g.tiles_h * kKwH * g.tiles_d * 2);
+  int want = num_sms() / (3 * g.ntiles);
+  if (want < 1) want = 1;
+  if ((long long)want > g.items) want = (int)g.items;
+  g.items_per_split = (g.items + want - 1) / want;
+  splits = (int)((g.items + g.items_per_split - 1) / g.items_per_split);
+  return force || (eff >= 0.8 && g.items_per_split >= 8);
+}
+
 static size_t wgrad_ws_bytes(int N, int D, int H, int W, int Cin, int Cout, int mode) {
   if (Cin % 64 || Cout % 64 || N <= 0) return 0;
   WgradGeom g; int nt, ntiles, splits;
   wgrad_plan(N, D, H, W, Cin, Cout, mode, g, nt, ntiles, splits);
-  return (size_t)splits * g.units * 64 * Cout * sizeof(float);
+  size_t need = (size_t)splits * g.units * 64 * Cout * sizeof(float);
+  WgKwGeom kg; int ksplits;
+  if (wgrad_kw_plan(N, D, H, W, Cin, Cout, mode, kg, ksplits)) {
+    const size_t kneed = (size_t)ksplits * 27 * 64 * Cout * sizeof(float);
+    if (kneed > need) need = kneed;
+  }
+  return need;
 }
 size_t conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
   return wgrad_ws_bytes(N, D, H, W, Cin, Cout, kTapsPlain);
@@ -1494,6 +1974,35 @@ static int wgrad_impl(const void* x, const void* dy, float* dw, void* ws, size_t
                       int Cin, int Cout, int mode, cudaStream_t st) {
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
               "conv3_wgrad: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
+  {
+    WgKwGeom kg; int ksplits;
+    if (wgrad_kw_plan(N, D, H, W, Cin, Cout, mode, kg, ksplits)) {
+      const size_t kneed = (size_t)ksplits * 27 * 64 * Cout * sizeof(float);
+      SIVAE_CHECK(ws != nullptr && ws_bytes >= kneed, "conv3_wgrad: workspace too small (%zu < %zu)", ws_bytes, kneed);
+      CUtensorMap tX, tDY;
+      {
+        uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+        uint64_t strides[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
+        uint32_t box[5] = {64, (uint32_t)kKwW, (uint32_t)(kKwH + 2), 4, 1};
+        if (make_tmap_bf16(&tX, x, 5, dims, strides, box)) return -1;
+      }
+      if (make_act_tmap(&tDY, dy, N, D, H, W, Cout, kKwW, kKwH, 1)) return -1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(conv3_wgrad_kw64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kWgKwSmem), "cudaFuncSetAttribute(conv3_wgrad_kw64)")) return -1;
+        attr_set = true;
+      }
+      conv3_wgrad_kw64_kernel<<<dim3(3u * (unsigned)kg.ntiles, (unsigned)ksplits), 224, kWgKwSmem, st>>>(tX, tDY, kg,
+                                                                                                      (float*)ws);
+      SIVAE_LAUNCH_OK("conv3_wgrad_kw64_kernel");
+      const long long total = 27ll * 64 * Cout;
+      int blocks = (int)((total + 255) / 256);
+      wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, ksplits, 27, 1, Cin, Cout);
+      SIVAE_LAUNCH_OK("wgrad_reduce_kernel");
+      return 0;
+    }
+  }
   WgradGeom g; int nt, ntiles, splits;
   wgrad_plan(N, D, H, W, Cin, Cout, mode, g, nt, ntiles, splits);
   const size_t need = (size_t)splits * g.units * 64 * Cout * sizeof(float);

@@ -155,6 +155,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* 
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Wait only until the bulk stores have READ their shared-memory source: enough before a CTA exits (its smem may be
+// handed to the next CTA); the global writes themselves complete asynchronously and are ordered by kernel completion.
+__device__ __forceinline__ void tma_store_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

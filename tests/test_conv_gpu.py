@@ -18,10 +18,32 @@ SHAPES = [
     (1, 20, 24, 20, 64, 128),     # headline mid resolution
     (1, 5, 7, 9, 128, 64),        # every extent odd: overhanging boxes on all sides
     (1, 1, 1, 1, 64, 64),         # single voxel
-    (1, 7, 16, 40, 64, 64),       # shapes the opt-in kw-copy kernel takes (SIVAE_CONV_KWCOPY=1): 8x16 patches, odd depth
-    (2, 4, 24, 32, 64, 128),      # ... its N = 128 variant, batch 2
+    (1, 7, 16, 40, 64, 64),       # 8x16 patches of the persistent kw-slab kernel, odd depth (half-empty depth pair)
+    (2, 4, 24, 32, 64, 128),      # ... two output-channel blocks, batch 2
     (1, 6, 30, 44, 64, 64),       # ... ragged W and H (clipped stores, OOB-filled loads)
+    (3, 12, 32, 24, 64, 64),      # ... more work items than one wave of a small grid would take
 ]
+# Cin = 64 shapes run several ways: the library's own choice ("auto": the persistent kd-fused kernel for well-tiling
+# 64 -> 64 shapes, else tap-by-tap), the kd-fused kernel forced for every 64 -> 64 shape incl. ragged / tiny ones
+# (SIVAE_CONV_KD=force), tap-by-tap forced (SIVAE_CONV_KD=0) and the opt-in kw-slab kernel forced (SIVAE_CONV_KW=force).
+KW_MODES = ["auto", "force", "0"]
+CONV_MODES = {"auto": {}, "kd_force": {"SIVAE_CONV_KD": "force"}, "tapwise": {"SIVAE_CONV_KD": "0"},
+              "kw_force": {"SIVAE_CONV_KD": "0", "SIVAE_CONV_KW": "force"}}
+
+
+@pytest.fixture(params=list(CONV_MODES))
+def kwmode(request):
+    import os
+    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW")
+    old = {k: os.environ.get(k) for k in keys}
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(CONV_MODES[request.param])
+    yield request.param
+    for k in keys:
+        os.environ.pop(k, None)
+        if old[k] is not None:
+            os.environ[k] = old[k]
 
 
 @pytest.fixture(autouse=True)
@@ -57,16 +79,20 @@ def test_pack_weights_exact():
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_fprop(shape):
+def test_fprop(shape, kwmode):
+    if kwmode != "auto" and shape[4] != 64:
+        pytest.skip("kernel choice only exists for Cin = 64")
     x, wt = _mk(*shape)
     wf, _ = K.pack_conv3_weights(wt)
     _check_bf16(K.conv3_igemm(x, wf), S.conv3_igemm(x, wf), f"fprop {shape}")
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_dgrad_is_conv_transpose(shape):
+def test_dgrad_is_conv_transpose(shape, kwmode):
     """dgrad = the same kernel on the flipped/transposed pack; checked against autograd of F.conv3d."""
     n, d, h, w, ci, co = shape
+    if kwmode != "auto" and co != 64:
+        pytest.skip("kernel choice only exists for (GEMM-K) channels = 64")
     x, wt = _mk(*shape)
     dy = torch.randn(n, d, h, w, co, device=DEV).to(torch.bfloat16)
     _, wd = K.pack_conv3_weights(wt)
@@ -77,9 +103,26 @@ def test_dgrad_is_conv_transpose(shape):
     _check_bf16(got, xin.grad.permute(0, 2, 3, 4, 1), f"dgrad {shape}")
 
 
+@pytest.fixture(params=KW_MODES)
+def wgmode(request):
+    import os
+    old = os.environ.get("SIVAE_WGRAD_KW")
+    if request.param == "auto":
+        os.environ.pop("SIVAE_WGRAD_KW", None)
+    else:
+        os.environ["SIVAE_WGRAD_KW"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("SIVAE_WGRAD_KW", None)
+    else:
+        os.environ["SIVAE_WGRAD_KW"] = old
+
+
 @pytest.mark.parametrize("shape", SHAPES)
-def test_wgrad(shape):
+def test_wgrad(shape, wgmode):
     n, d, h, w, ci, co = shape
+    if wgmode != "auto" and ci != 64:
+        pytest.skip("kernel choice only exists for Cin = 64")
     x, _ = _mk(*shape)
     dy = torch.randn(n, d, h, w, co, device=DEV).to(torch.bfloat16)
     got = K.conv3_wgrad(x, dy)

@@ -8,6 +8,12 @@ reparameterisation eps and dropout keep-masks, with Adam(lr 2e-4) as utils/my_tr
   oracle : oracle/sivae_oracle.py, torch fp32 on the same GPU (TF32 off) -- the restatement pinned to the reference's
            golden vectors in tests/test_oracle_vs_golden.py
 
+  control: the same oracle under ``torch.autocast(bfloat16)`` (what stock PyTorch mixed precision gives a user of the
+           reference) -- it measures how far ANY bf16 execution of this recipe drifts from fp32.  The recipe is
+           violently sensitive: the first Adam updates move every weight by +-lr regardless of gradient magnitude
+           and the KL terms are sums of exp(logvar) (kl_real jumps by 4-6 orders of magnitude at step 1), so two
+           roundings of the same trajectory separate quickly.  Parity is therefore stated relative to the control.
+
 and the per-step loss terms are compared.  Used by tests/test_loss_curve_gpu.py (short run, asserted) and from the
 command line to write profiles/*_loss_curve.{json,md}:
 
@@ -45,7 +51,7 @@ def synthetic_volumes(n, vol, gen):
 
 
 def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setting=((64, 1, 2), (128, 1, 2), (256, 2, 2)),
-        lr=2e-4, seed=77, device="cuda", verbose=False):
+        lr=2e-4, seed=77, device="cuda", verbose=False, control=False):
     import sivae_b200
     from sivae_b200 import functional as F, trainer as T
     from oracle import sivae_oracle as O
@@ -73,6 +79,19 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
         for k in names:
             sd[k].grad = grads.get(k)                                            # unused params keep grad None
         o_opt[phase].step()
+
+    if control:
+        sd_c = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        for k in enc_names + dec_names:
+            sd_c[k] = torch.nn.Parameter(sd_c[k])
+        c_opt = {"E": torch.optim.Adam([sd_c[k] for k in enc_names], lr=lr),
+                 "D": torch.optim.Adam([sd_c[k] for k in dec_names], lr=lr)}
+
+        def apply_update_c(names, grads, phase):
+            for k in names:
+                g_ = grads.get(k)
+                sd_c[k].grad = None if g_ is None else g_.float()
+            c_opt[phase].step()
 
     opt_e = torch.optim.Adam(net.encoder.parameters(), lr=lr)
     opt_d = torch.optim.Adam(net.decoder.parameters(), lr=lr)
@@ -109,6 +128,8 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
         return out
 
     curves = {"ours": {k: [] for k in TERMS}, "oracle": {k: [] for k in TERMS}}
+    if control:
+        curves["control"] = {k: [] for k in TERMS}
     for step in range(steps):
         real = data[(step % n_batches) * batch:(step % n_batches + 1) * batch]
         noise = torch.randn(lat, device=dev, generator=g)
@@ -129,6 +150,12 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
                                                apply_update=apply_update)
         for k in TERMS:
             curves["oracle"][k].append(float(oterms[k]))
+        if control:
+            with torch.autocast(dev.type, dtype=torch.bfloat16):
+                cterms, _, _ = O.soft_intro_step_grads(sd_c, cfg, real, noise, eps, [m.float() for m in masks], ohp,
+                                                       apply_update=apply_update_c)
+            for k in TERMS:
+                curves["control"][k].append(float(cterms[k]))
         if verbose and (step % 20 == 0 or step == steps - 1):
             print(f"step {step:4d}  lossE {curves['ours']['lossE'][-1]:.5g} / {curves['oracle']['lossE'][-1]:.5g}   "
                   f"lossD {curves['ours']['lossD'][-1]:.5g} / {curves['oracle']['lossD'][-1]:.5g}   "
@@ -136,12 +163,12 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
     return curves
 
 
-def deviations(curves):
-    """Per term: median / 90th percentile / max over steps of |ours - oracle| / |oracle|, and the same for the
+def deviations(curves, arm="ours"):
+    """Per term: median / 90th percentile / max over steps of |arm - oracle| / |oracle|, and the same for the
     10-step moving averages (what a loss plot shows)."""
     out = {}
     for k in TERMS:
-        a, b = curves["ours"][k], curves["oracle"][k]
+        a, b = curves[arm][k], curves["oracle"][k]
         rel = [abs(x - y) / max(abs(y), 1e-30) for x, y in zip(a, b)]
         win = 10
         sm = []
@@ -162,8 +189,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--n-batches", type=int, default=4)
     ap.add_argument("--out", default=None, help="prefix for <out>.json / <out>.md")
+    ap.add_argument("--control", action="store_true", help="also train the oracle under bf16 autocast")
     a = ap.parse_args()
-    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True)
+    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True, control=a.control)
     dev = deviations(curves)
     lines = [f"# Loss-curve parity, {a.steps} steps, headline net, volumes {a.vol}, batch {a.batch}, "
              f"{a.n_batches} synthetic batches cycled, identical init / noise / eps / dropout masks", "",
@@ -173,6 +201,13 @@ def main():
     for k, v in dev.items():
         lines.append(f"| {k} | {v['oracle_first']:.5g} | {v['oracle_last']:.5g} | {v['ours_last']:.5g} | "
                      f"{v['median']:.2e} | {v['p90']:.2e} | {v['max']:.2e} | {v['smooth_max']:.2e} |")
+    if a.control:
+        cdev = deviations(curves, "control")
+        lines += ["", "control = the oracle under torch.autocast(bfloat16) vs the fp32 oracle (same table):", "",
+                  "| term | control last | rel.dev median | p90 | max | 10-step-mean max |", "|---|---:|---:|---:|---:|---:|"]
+        for k, v in cdev.items():
+            lines.append(f"| {k} | {v['ours_last']:.5g} | {v['median']:.2e} | {v['p90']:.2e} | {v['max']:.2e} | "
+                         f"{v['smooth_max']:.2e} |")
     print("\n".join(lines))
     if a.out:
         with open(a.out + ".json", "w") as f:
