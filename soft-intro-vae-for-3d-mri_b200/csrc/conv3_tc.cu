@@ -1301,115 +1301,165 @@ int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wup
 }
 
 // =================================================================================================
-// C = 64 -> 1 channel, 3x3x3: "all taps as GEMM columns" variant.
+// C = 64 -> 1 channel, 3x3x3: "all taps as GEMM columns", persistent.
 // P[v_in][tap] = sum_c x[v_in][c] * w[c][tap] is one tiny GEMM per input voxel (N = 27 taps), so the input tile is
 // fetched ONCE instead of once per tap; the convolution is then out[v] = sum_tap P[v + delta(tap)][tap], a 27-term
-// gather from shared memory.  A CTA owns 16 x 8 x 1 outputs and loads the 18 x 10 x 3 input halo box (540 voxel rows,
-// one TMA), runs 5 M-tiles x (hi + lo weight slabs) of UMMA 128x32x16, spills P to shared memory (aliasing the input
-// buffer) and reduces.  L2->SMEM traffic drops 27 x 16 KB -> 69 KB per 128 outputs.
+// gather from shared memory.  A work item is 16 x 8 x 1 outputs with the 18 x 10 x 3 input halo box (540 voxel rows,
+// one 69 KB TMA).  The weights are split bf16(w) | bf16(w - bf16(w)) (~fp32 products, the output feeds the loss
+// directly) and stacked into ONE N = 64 operand: columns 0..31 hold the hi partials, 32..63 the lo partials, so the
+// input rows are read once for both (6 KB of operand reads per UMMA instead of 2 x 5 KB).
+// Persistent CTA, one per SM: the weights stay resident, the halo boxes are double-buffered (TMA of item i+1 under the
+// MMAs of item i), and the accumulators form a ring of eight 64-column TMEM slots handed over per M-tile, so the
+// epilogue warps (TMEM -> P in shared memory -> gather -> bias/ReLU/dropout -> fp32 store) overlap the MMAs of the
+// following tiles.  L2->SMEM traffic: 27 x 16 KB -> 69 KB per 128 outputs.
+// 6 warps: TMA producer, MMA issuer, 4 epilogue warps.
 // =================================================================================================
-static constexpr int kHW = 16, kHH = 8;                        // outputs per CTA (w, h); d = 1
+static constexpr int kHW = 16, kHH = 8;                        // outputs per item (w, h); d = 1
 static constexpr int kHBW = kHW + 2, kHBH = kHH + 2, kHBD = 3; // input halo box
 static constexpr int kHRows = kHBW * kHBH * kHBD;              // 540
 static constexpr int kHMTiles = (kHRows + 127) / 128;          // 5
-static constexpr int kPStride = 29;                            // floats per P row (odd: conflict-free gather)
+static constexpr int kPStride = 27;                            // floats per P row (odd: conflict-free)
+static constexpr int kHABuf = ((kHRows * 128 + 1023) / 1024) * 1024;        // 69,632: stride between the two boxes
+static constexpr int kHARegion = kHABuf + kHMTiles * kTileBytes;           // the last M-tile reads 100 rows past a box
+static constexpr int kHBBytes = 64 * 128;                                   // [hi 32 taps | lo 32 taps] x 64 channels
+static constexpr int kHPBytes = ((kHRows * kPStride * 4 + 127) / 128) * 128;
+static constexpr int kHSlots = 8;
+static constexpr int kTo1Smem = kHARegion + kHBBytes + kHPBytes + 1024 + 256;
 
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 1)
 conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int N, int D,
-                      int H, int W, int tiles_w, int tiles_h, const ToOneEpilogue ep) {
-  constexpr int A_BYTES = kHMTiles * kTileBytes;   // 80 KB (rows 540..639 are never written nor used)
-  constexpr int B_BYTES = 32 * 128;                // one 32-tap x 64-channel slab
+                      int H, int W, int tiles_w, int tiles_h, long long items, const ToOneEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + 2 * B_BYTES);
-  uint64_t* tmem_full_bar = full_bar + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* P = reinterpret_cast<float*>(smem);       // [640][kPStride] aliases the A buffer after the MMAs
+  uint8_t* smem_b = smem + kHARegion;
+  float* P = reinterpret_cast<float*>(smem_b + kHBBytes);          // [540][kPStride]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(P) + kHPBytes);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* slot_full = a_empty + 2;
+  uint64_t* slot_empty = slot_full + kHSlots;
+  uint64_t* b_full = slot_empty + kHSlots;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long id = blockIdx.x;
-  const int tw = (int)(id % tiles_w); id /= tiles_w;
-  const int th = (int)(id % tiles_h); id /= tiles_h;
-  const int d0 = (int)(id % D);
-  const int n = (int)(id / D);
-  const int w0 = tw * kHW, h0 = th * kHH;
 
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    mbar_init(full_bar, 1);
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kHSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 256);
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  auto decode = [&](long long id, int& w0, int& h0, int& d0, int& n) {
+    const int tw = (int)(id % tiles_w); id /= tiles_w;
+    const int th = (int)(id % tiles_h); id /= tiles_h;
+    d0 = (int)(id % D);
+    n = (int)(id / D);
+    w0 = tw * kHW; h0 = th * kHH;
+  };
+
   if (warp_id == 0) {
+    // ===== TMA producer: weights once, then one halo box per item =====
     if (lane == 0) {
-      mbar_expect_tx(full_bar, (uint32_t)kHRows * 128u + 2u * B_BYTES);
-      tma_load_5d(smem, &tmA, full_bar, 0, w0 - 1, h0 - 1, d0 - 1, n);
-      tma_load_3d(smem_b, &tmB, full_bar, 0, 0, 0);
-      tma_load_3d(smem_b + B_BYTES, &tmB, full_bar, 0, 0, 1);
+      mbar_expect_tx(b_full, kHBBytes);
+      tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
+      tma_load_3d(smem_b + 32 * 128, &tmB, b_full, 0, 0, 1);
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        const int s = it & 1;
+        mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&a_full[s], (uint32_t)kHRows * 128u);
+        tma_load_5d(smem + s * kHABuf, &tmA, &a_full[s], 0, w0 - 1, h0 - 1, d0 - 1, n);
+      }
     }
   } else if (warp_id == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
-    mbar_wait(full_bar, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem_b);
-#pragma unroll 1
-      for (int m = 0; m < kHMTiles; ++m)
-#pragma unroll
-        for (int part = 0; part < 2; ++part)     // hi then lo weight slab into the same accumulator
+    // ===== MMA issuer: 5 M-tiles x 4 K steps of UMMA 128 x 64 x 16 per item, one TMEM slot per M-tile =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    mbar_wait(b_full, 0);
+    const uint32_t b_addr = smem_u32(smem_b);
+    uint32_t it = 0, sl = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const uint32_t s = it & 1;
+      mbar_wait(&a_full[s], (it >> 1) & 1u);
+      const uint32_t a_addr = smem_u32(smem + s * kHABuf);
+      for (int m = 0; m < kHMTiles; ++m, ++sl) {
+        const uint32_t slot = sl % kHSlots;
+        mbar_wait(&slot_empty[slot], ((sl / kHSlots) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + (uint32_t)(m * 32), make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
-                      make_smem_desc(b_addr + part * B_BYTES + k * 32, 16, 1024), idesc, (part | k) != 0 ? 1u : 0u);
-      umma_commit(tmem_full_bar);
+            umma_bf16(tmem_base + slot * 64u, make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
+                      make_smem_desc(b_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+          umma_commit(&slot_full[slot]);
+          if (m == kHMTiles - 1) umma_commit(&a_empty[s]);
+        }
+        __syncwarp();
+      }
     }
-    __syncwarp();
   } else {
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    // ===== epilogue (warps 2..5 <-> TMEM lane quadrants 2,3,0,1) =====
     const int q = warp_id & 3;
-#pragma unroll 1
-    for (int m = 0; m < kHMTiles; ++m) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 32), v);
-      tmem_ld_wait();
-      float* dst = P + (size_t)(m * 128 + q * 32 + lane) * kPStride;
-#pragma unroll
-      for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v[t]);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int t128 = (warp_id - 2) * 32 + lane;          // one output voxel per epilogue thread
     const int ow = t128 % kHW, oh = t128 / kHW;
-    const int w = w0 + ow, h = h0 + oh;
-    if (w < W && h < H) {
-      float acc = 0.f;
+    const float bias = ep.bias ? ep.bias[0] : 0.f;
+    const float inv_keep = 1.f / (1.f - ep.p);
+    uint32_t sl = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      int w0, h0, d0, n;
+      decode(item, w0, h0, d0, n);
+#pragma unroll 1
+      for (int m = 0; m < kHMTiles; ++m, ++sl) {
+        const uint32_t slot = sl % kHSlots;
+        mbar_wait(&slot_full[slot], (sl / kHSlots) & 1u);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+        const int prow = m * 128 + q * 32 + lane;
+        if (prow < kHRows) {
+          float* dst = P + (size_t)prow * kPStride;
 #pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        const int row = ((t / 9) * kHBH + oh + (t / 3) % 3) * kHBW + ow + t % 3;
-        acc += P[row * kPStride + t];
+          for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+        }
       }
-      const long long vox = (((long long)n * D + d0) * H + h) * W + w;
-      float r = acc + (ep.bias ? ep.bias[0] : 0.f);
-      if (ep.act == 1) {
-        r = fmaxf(r, 0.f);
-        const float inv_keep = 1.f / (1.f - ep.p);
-        if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
-        else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int w = w0 + ow, h = h0 + oh;
+      if (w < W && h < H) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+          const int row = ((t / 9) * kHBH + oh + (t / 3) % 3) * kHBW + ow + t % 3;
+          acc += P[row * kPStride + t];
+        }
+        const long long vox = (((long long)n * D + d0) * H + h) * W + w;
+        float r = acc + bias;
+        if (ep.act == 1) {
+          r = fmaxf(r, 0.f);
+          if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
+          else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+        }
+        ep.y[vox] = r;
       }
-      ep.y[vox] = r;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // P is free for the next item
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_id == 1) tmem_dealloc(tmem_base, 256);
+  if (warp_id == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // fp32 [64][27] -> bf16 [2][32][64]: slab 0 = bf16(w) per tap row (rows 27..31 zero), slab 1 = bf16(w - bf16(w))
@@ -1853,17 +1903,16 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
     ToOneEpilogue ep;
     ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = make_seed_ref(seed); ep.p = p; ep.act = act;
     const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
-    const long long ctas = (long long)tiles_w * tiles_h * D * N;
-    SIVAE_CHECK(ctas < (1ll << 31), "conv3_to1: too many tiles");
-    constexpr int smem = kHMTiles * kTileBytes + 2 * 32 * 128 + 1024 + 256;
+    const long long items = (long long)tiles_w * tiles_h * D * N;
     static bool attr_set = false;
     if (!attr_set) {
-      if (check_cuda(cudaFuncSetAttribute(conv3_to1_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+      if (check_cuda(cudaFuncSetAttribute(conv3_to1_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTo1Smem),
                      "cudaFuncSetAttribute(conv3_to1_halo)"))
         return -1;
       attr_set = true;
     }
-    conv3_to1_halo_kernel<<<(unsigned)ctas, 192, smem, st>>>(tmA, tmB, N, D, H, W, tiles_w, tiles_h, ep);
+    const unsigned ctas = (unsigned)(items < (long long)num_sms() ? items : (long long)num_sms());
+    conv3_to1_halo_kernel<<<ctas, 192, kTo1Smem, st>>>(tmA, tmB, N, D, H, W, tiles_w, tiles_h, items, ep);
     SIVAE_LAUNCH_OK("conv3_to1_halo_kernel");
     return 0;
   }
