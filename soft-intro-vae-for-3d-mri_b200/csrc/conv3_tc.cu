@@ -1477,137 +1477,202 @@ __global__ void pack_to1_halo_weights_kernel(const float* __restrict__ w, int fl
 // 1 -> 64 channels, 3x3x3 (encoder stem Conv3d(1,64,3), models/models.py:92; input gradient of the decoder tail):
 // y[v][c] = bias[c] + sum_tap w[c][tap] * x1[v + delta(tap)] as a tensor-core GEMM whose A operand (the im2col of
 // the one-channel fp32 input) is BUILT IN SHARED MEMORY by the CTA's threads: M = 128 voxels (16 x 8 x 1), N = 64,
-// K = 128 = [x_hi(32) | x_lo(32) | x_hi(32) | 0] against B = [w_hi | w_hi | w_lo | 0]  (bf16 split of both operands:
-// x_hi*w_hi + x_lo*w_hi + x_hi*w_lo recovers ~16 mantissa bits of the fp32 product).  Epilogue as conv3_igemm.
+// K = 96 = [x_hi(32) | x_lo(32) | x_hi(32)] against B = [w_hi | w_hi | w_lo]  (bf16 split of both operands:
+// x_hi*w_hi + x_lo*w_hi + x_hi*w_lo recovers ~16 mantissa bits of the fp32 product).
 // HBM-bound on the 128 B/voxel output write instead of FMA-bound (1728 FMA/voxel on CUDA cores).
+// Persistent CTA, one per SM, three concurrent roles over double-buffered A tiles / TMEM stages / output staging:
+//   warps 0-3  builders : prefetch the next item's fp32 halo into registers, stage it, build one A row per thread
+//   warp  4    MMA      : weights loaded once (TMA), 6 UMMA 128x64x16 per item
+//   warps 5-8  epilogue : TMEM -> +bias -> bf16 -> swizzled smem -> TMA store
 // =================================================================================================
-__global__ void __launch_bounds__(160)
+static constexpr int kC1ABytes = 2 * kTileBytes;          // two 64-wide K blocks of the 128-row A tile
+static constexpr int kC1BBytes = 2 * 64 * 128;            // [2 K blocks][64 channels][64]
+static constexpr int kC1Halo = (kHRows + 3) & ~3;         // floats per staged halo
+static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + 2 * kTileBytes + 2 * kC1Halo * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(288, 1)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
-                    int tiles_w, int tiles_h) {
-  constexpr int A_BYTES = 2 * kTileBytes;          // two 64-wide K blocks of the 128-row A tile
-  constexpr int B_BYTES = 2 * 64 * 128;            // [2 K blocks][64 channels][64]
+                    int tiles_w, int tiles_h, long long items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + A_BYTES;
-  float* xs = reinterpret_cast<float*>(smem_b + B_BYTES);          // halo (kHRows floats)
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(xs + ((kHRows + 3) & ~3));
-  uint64_t* tmem_full_bar = b_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* smem_b = smem + 2 * kC1ABytes;
+  uint8_t* smem_o = smem_b + kC1BBytes;
+  float* xs = reinterpret_cast<float*>(smem_o + 2 * kTileBytes);   // [2][kC1Halo]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(xs + 2 * kC1Halo);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_full = acc_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
 
-  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warps 0-3: builders + epilogue, warp 4: TMA + MMA
-  long long id = blockIdx.x;
-  const int tw = (int)(id % tiles_w); id /= tiles_w;
-  const int th = (int)(id % tiles_h); id /= tiles_h;
-  const int d0 = (int)(id % D);
-  const long long n = id / D;
-  const int w0 = tw * kHW, h0 = th * kHH;
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp_id == 4) {
     if (lane == 0) {
       prefetch_tmap(&tmB);
       prefetch_tmap(&tmC);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&a_full[s], 128);     // every builder thread arrives after fencing its row
+        mbar_init(&a_empty[s], 1);
+        mbar_init(&acc_full[s], 1);
+        mbar_init(&acc_empty[s], 4);
+      }
       mbar_init(b_full, 1);
-      mbar_init(tmem_full_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 64);
+    tmem_alloc(tmem_ptr_smem, 128);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  auto decode = [&](long long id, int& w0, int& h0, int& d0, long long& n) {
+    const int tw = (int)(id % tiles_w); id /= tiles_w;
+    const int th = (int)(id % tiles_h); id /= tiles_h;
+    d0 = (int)(id % D);
+    n = id / D;
+    w0 = tw * kHW; h0 = th * kHH;
+  };
+
   if (warp_id == 4) {
+    // ===== MMA issuer =====
     if (lane == 0) {
-      mbar_expect_tx(b_full, B_BYTES);
+      mbar_expect_tx(b_full, kC1BBytes);
       tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
       tma_load_3d(smem_b + 64 * 128, &tmB, b_full, 0, 0, 1);
     }
     __syncwarp();
-    asm volatile("bar.sync 2, 160;" ::: "memory");        // A tile built (builders fenced to the async proxy)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
     mbar_wait(b_full, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem_b);
+    const uint32_t b_addr = smem_u32(smem_b);
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const uint32_t s = it & 1, ph = (it >> 1) & 1u;
+      mbar_wait(&acc_empty[s], ph ^ 1u);
+      mbar_wait(&a_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * kC1ABytes);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, make_smem_desc(a_addr + kb * kTileBytes + k * 32, 16, 1024),
-                    make_smem_desc(b_addr + kb * 64 * 128 + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
-      umma_commit(tmem_full_bar);
+        for (int kk = 0; kk < 6; ++kk) {   // K block 0: 4 steps [x_hi | x_lo], K block 1: 2 steps [x_hi]
+          const int kb = kk >> 2, k = kk & 3;
+          umma_bf16(tmem_base + s * 64u, make_smem_desc(a_addr + kb * kTileBytes + k * 32, 16, 1024),
+                    make_smem_desc(b_addr + kb * 64 * 128 + k * 32, 16, 1024), idesc, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&acc_full[s]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  } else {
-    // ---- stage the fp32 halo, then build this thread's A row (one output voxel) ----
-    for (int i = threadIdx.x; i < kHRows; i += 128) {
-      const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
-      const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
-      float v = 0.f;
-      if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-        v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
-      xs[i] = v;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+  } else if (warp_id < 4) {
+    // ===== builders: one A row (output voxel) per thread =====
     const int row = threadIdx.x;                          // 0..127
     const int ow = row % kHW, oh = row / kHW;
-    uint32_t hi[16], lo[16];                              // 32 bf16 each: taps 0..26, then zeros
+    constexpr int kPer = (kHRows + 127) / 128;            // halo floats per thread (5)
+    float pre[kPer];
+    auto fetch = [&](long long item) {
+      int w0, h0, d0; long long n;
+      decode(item, w0, h0, d0, n);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a = 0.f, b = 0.f;
-      if (2 * j < 27) a = xs[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
-      if (2 * j + 1 < 27) b = xs[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
-      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-      hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-      lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
-    }
-    uint8_t* r0 = smem + row * 128;                       // K block 0: [x_hi | x_lo]
-    uint8_t* r1 = smem + kTileBytes + row * 128;          // K block 1: [x_hi | 0]
+      for (int j = 0; j < kPer; ++j) {
+        const int i = row + j * 128;
+        const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
+        const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+        float v = 0.f;
+        if (i < kHRows && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+          v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+        pre[j] = v;
+      }
+    };
+    if ((long long)blockIdx.x < items) fetch(blockIdx.x);
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const uint32_t s = it & 1, ph = (it >> 1) & 1u;
+      float* xh = xs + s * kC1Halo;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-      const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-      *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = vh;
-      *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = vl;
-      *reinterpret_cast<uint4*>(r1 + ((c ^ (row & 7)) << 4)) = vh;
-      *reinterpret_cast<uint4*>(r1 + (((4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-    }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 2, 160;" ::: "memory");
-    // ---- epilogue ----
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    uint8_t* out_stage = smem;                            // A tile is dead once the MMAs have completed
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp_id * 32) << 16) + (uint32_t)(j * 32), v);
-      tmem_ld_wait();
+      for (int j = 0; j < kPer; ++j)
+        if (row + j * 128 < kHRows) xh[row + j * 128] = pre[j];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (item + gridDim.x < items) fetch(item + gridDim.x);     // next item's halo: in flight while this row is built
+      uint32_t hi[16], lo[16];                              // 32 bf16 each: taps 0..26, then zeros
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = 0.f, b = 0.f;
+        if (2 * j < 27) a = xh[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
+        if (2 * j + 1 < 27) b = xh[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+      }
+      mbar_wait(&a_empty[s], ph ^ 1u);                      // the MMAs that read this A buffer two items ago are done
+      uint8_t* r0 = smem + s * kC1ABytes + row * 128;       // K block 0: [x_hi | x_lo]
+      uint8_t* r1 = r0 + kTileBytes;                        // K block 1: [x_hi | (never read)]
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float f[8];
+        const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = vh;
+        *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = vl;
+        *reinterpret_cast<uint4*>(r1 + ((c ^ (row & 7)) << 4)) = vh;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
+    }
+  } else {
+    // ===== epilogue (warps 5..8 <-> TMEM lane quadrants 1,2,3,0) =====
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (warp_id == 5 && lane == 0);
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      int w0, h0, d0; long long n;
+      decode(item, w0, h0, d0, n);
+      const uint32_t s = it & 1;
+      uint8_t* tile = smem_o + s * kTileBytes;
+      mbar_wait(&acc_full[s], (it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64u;
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32u, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[s]);
+      // the store issued two items ago read this staging tile: it must have drained before it is overwritten
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]) + (bias ? __ldg(bias + j * 32 + c * 8 + e) : 0.f);
+      for (int c = 0; c < 4; ++c) {
+        float f[8], g8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[e] = __uint_as_float(v0[c * 8 + e]) + (bias ? __ldg(bias + c * 8 + e) : 0.f);
+          g8[e] = __uint_as_float(v1[c * 8 + e]) + (bias ? __ldg(bias + 32 + c * 8 + e) : 0.f);
+        }
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
         pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(out_stage + row * 128 + (((j * 4 + c) ^ (row & 7)) << 4)) = pk;
+        *reinterpret_cast<uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = pk;
+        pk.x = pack_bf16x2(g8[0], g8[1]); pk.y = pack_bf16x2(g8[2], g8[3]);
+        pk.z = pack_bf16x2(g8[4], g8[5]); pk.w = pack_bf16x2(g8[6], g8[7]);
+        *reinterpret_cast<uint4*>(tile + row * 128 + (((4 + c) ^ (row & 7)) << 4)) = pk;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_5d(&tmC, tile, 0, w0, h0, d0, (int)n);
+        tma_store_commit();
       }
     }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 0) {
-      tma_store_5d(&tmC, out_stage, 0, w0, h0, d0, (int)n);
-      tma_store_commit();
-      tma_store_wait_read_all();
-    }
+    if (issuer) tma_store_wait_read_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_id == 4) tmem_dealloc(tmem_base, 64);
+  if (warp_id == 4) tmem_dealloc(tmem_base, 128);
 }
 
 // fp32 [64][27] -> bf16 [2][64][64]: K block 0 = [w_hi(32) | w_hi(32)], K block 1 = [w_lo(32) | 0]  (tap-flipped if `flip`)
@@ -1643,17 +1708,17 @@ int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, in
   }
   if (make_act_tmap(&tmC, y, N, D, H, W, 64, kHW, kHH, 1)) return -1;
   const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
-  const long long ctas = (long long)tiles_w * tiles_h * D * N;
-  SIVAE_CHECK(ctas < (1ll << 31), "c1_to_c64: too many tiles");
-  constexpr int smem = 2 * kTileBytes + 2 * 64 * 128 + ((kHRows + 3) & ~3) * 4 + 1024 + 256;
+  const long long items = (long long)tiles_w * tiles_h * D * N;
   static bool attr_set = false;
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
                    "cudaFuncSetAttribute(c1_to_c64_tc)"))
       return -1;
     attr_set = true;
   }
-  c1_to_c64_tc_kernel<<<(unsigned)ctas, 160, smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h);
+  const long long cap = num_sms();   // one persistent CTA per SM (117 KB of shared memory, 288 threads x 161 registers)
+  const unsigned ctas = (unsigned)(items < cap ? items : cap);
+  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, items);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
   return 0;
 }
@@ -1747,19 +1812,32 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
     const int row = threadIdx.x;                          // voxel row of the tile
     const int ow = row % kHW, oh = row / kHW;
     float s1 = 0.f;
-    for (long long it = 0; it < my_tiles; ++it) {
-      const int s = (int)(it % kWg1Stages);
+    constexpr int kPer = (kHRows + 127) / 128;            // halo floats per thread (5)
+    float pre[kPer];
+    // the fp32 halo of the NEXT tile is fetched into registers while the current A tile is built, so the global-load
+    // latency is off the per-tile critical path
+    auto fetch = [&](long long id) {
       int w0, h0, d0; long long n;
-      decode(first + it * step, w0, h0, d0, n);
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous iteration's halo reads are done
-      for (int i = threadIdx.x; i < kHRows; i += 128) {
+      decode(id, w0, h0, d0, n);
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = row + j * 128;
         const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
         const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
         float v = 0.f;
-        if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+        if (i < kHRows && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
           v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
-        xs[i] = v;
+        pre[j] = v;
       }
+    };
+    if (my_tiles > 0) fetch(first);
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % kWg1Stages);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous iteration's halo reads are done
+#pragma unroll
+      for (int j = 0; j < kPer; ++j)
+        if (row + j * 128 < kHRows) xs[row + j * 128] = pre[j];
+      if (it + 1 < my_tiles) fetch(first + (it + 1) * step);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       uint32_t hi[16], lo[16];
 #pragma unroll
