@@ -1301,41 +1301,54 @@ int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wup
 }
 
 // =================================================================================================
-// C = 64 -> 1 channel, 3x3x3: "all taps as GEMM columns", persistent.
-// P[v_in][tap] = sum_c x[v_in][c] * w[c][tap] is one tiny GEMM per input voxel (N = 27 taps), so the input tile is
-// fetched ONCE instead of once per tap; the convolution is then out[v] = sum_tap P[v + delta(tap)][tap], a 27-term
-// gather from shared memory.  A work item is 16 x 8 x 1 outputs with the 18 x 10 x 3 input halo box (540 voxel rows,
-// one 69 KB TMA).  The weights are split bf16(w) | bf16(w - bf16(w)) (~fp32 products, the output feeds the loss
-// directly) and stacked into ONE N = 64 operand: columns 0..31 hold the hi partials, 32..63 the lo partials, so the
-// input rows are read once for both (6 KB of operand reads per UMMA instead of 2 x 5 KB).
-// Persistent CTA, one per SM: the weights stay resident, the halo boxes are double-buffered (TMA of item i+1 under the
-// MMAs of item i), and the accumulators form a ring of eight 64-column TMEM slots handed over per M-tile, so the
-// epilogue warps (TMEM -> P in shared memory -> gather -> bias/ReLU/dropout -> fp32 store) overlap the MMAs of the
-// following tiles.  L2->SMEM traffic: 27 x 16 KB -> 69 KB per 128 outputs.
-// 6 warps: TMA producer, MMA issuer, 4 epilogue warps.
+// C = 64 -> 1 channel, 3x3x3: "all taps as GEMM columns", persistent and streaming along depth.
+// P[v_in][tap] = sum_c x[v_in][c] * w[c][tap] is one tiny GEMM per INPUT voxel (N = 27 taps), so an input row is
+// multiplied ONCE for all the outputs it feeds; the convolution is then out[v] = sum_tap P[v + delta(tap)][tap], a
+// 27-term gather from shared memory.  The weights are split bf16(w) | bf16(w - bf16(w)) (~fp32 products: the output
+// feeds the loss directly) and stacked into ONE N = 64 operand (columns 0..31 hi partials, 32..63 lo partials).
+//
+// A work item is a 16(w) x 8(h) patch over a CHUNK of output planes.  The CTA walks the chunk's input planes
+// d_start-1 .. d_end: each plane's 18 x 10 halo (180 voxel rows, one 23 KB TMA) is loaded once, turned into P once
+// (2 M-tiles x 4 UMMA 128x64x16) and its P rows serve the three output planes around it; the gather for output plane d
+// runs as soon as P of planes d-1, d, d+1 sit in the 4-deep P ring.  Per 128 outputs: 23 KB of TMA, 8 UMMAs and
+// 180 x 27 floats of P traffic -- the first version of this kernel (one 18 x 10 x 3 box per output plane) moved 3x that
+// and was bound by shared-memory bandwidth (ncu: every pipe < 30 % busy, profiles/r01c).
+// Persistent CTA, one per SM: resident weights, 4-deep input ring, ring of eight 64-column TMEM slots handed over per
+// M-tile, 4-deep P ring.  6 warps: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> P -> gather -> bias / ReLU /
+// dropout -> fp32 store).
 // =================================================================================================
-static constexpr int kHW = 16, kHH = 8;                        // outputs per item (w, h); d = 1
-static constexpr int kHBW = kHW + 2, kHBH = kHH + 2, kHBD = 3; // input halo box
-static constexpr int kHRows = kHBW * kHBH * kHBD;              // 540
-static constexpr int kHMTiles = (kHRows + 127) / 128;          // 5
+static constexpr int kHW = 16, kHH = 8;                        // outputs per patch (w, h)
+static constexpr int kHBW = kHW + 2, kHBH = kHH + 2, kHBD = 3; // input halo (kHBD only used by the c1 kernels' 3-plane halo)
+static constexpr int kHRows = kHBW * kHBH * kHBD;              // 540 (3-plane halo of the c1 kernels)
+static constexpr int kSPRows = kHBW * kHBH;                    // 180 voxel rows per input plane
 static constexpr int kPStride = 27;                            // floats per P row (odd: conflict-free)
-static constexpr int kHABuf = ((kHRows * 128 + 1023) / 1024) * 1024;        // 69,632: stride between the two boxes
-static constexpr int kHARegion = kHABuf + kHMTiles * kTileBytes;           // the last M-tile reads 100 rows past a box
+static constexpr int kSASlot = ((kSPRows * 128 + 1023) / 1024) * 1024;     // 23,552: stride of the input ring
+static constexpr int kSASlots = 4;
+static constexpr int kSARegion = (kSASlots - 1) * kSASlot + 2 * kTileBytes;  // the 2nd M-tile reads 76 rows past a plane
 static constexpr int kHBBytes = 64 * 128;                                   // [hi 32 taps | lo 32 taps] x 64 channels
-static constexpr int kHPBytes = ((kHRows * kPStride * 4 + 127) / 128) * 128;
+static constexpr int kSPSlots = 4;
+static constexpr int kSPSlotFloats = kSPRows * kPStride;                    // 4,860
+static constexpr int kSPBytes = kSPSlots * kSPSlotFloats * 4;               // 77,760
 static constexpr int kHSlots = 8;
-static constexpr int kTo1Smem = kHARegion + kHBBytes + kHPBytes + 1024 + 256;
+static constexpr int kTo1Smem = kSARegion + kHBBytes + kSPBytes + 1024 + 256;
+
+struct To1Geom {
+  int N, D, H, W;
+  int tiles_w, tiles_h;
+  int chunks, dc;        // depth chunks per volume, planes per chunk
+  int items;             // tiles_w * tiles_h * chunks * N
+};
 
 __global__ void __launch_bounds__(192, 1)
-conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int N, int D,
-                      int H, int W, int tiles_w, int tiles_h, long long items, const ToOneEpilogue ep) {
+conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const To1Geom g,
+                      const ToOneEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + kHARegion;
-  float* P = reinterpret_cast<float*>(smem_b + kHBBytes);          // [540][kPStride]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(P) + kHPBytes);
-  uint64_t* a_empty = a_full + 2;
-  uint64_t* slot_full = a_empty + 2;
+  uint8_t* smem_b = smem + kSARegion;
+  float* P = reinterpret_cast<float*>(smem_b + kHBBytes);          // [kSPSlots][180][kPStride]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(P) + kSPBytes);
+  uint64_t* a_empty = a_full + kSASlots;
+  uint64_t* slot_full = a_empty + kSASlots;
   uint64_t* slot_empty = slot_full + kHSlots;
   uint64_t* b_full = slot_empty + kHSlots;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
@@ -1345,7 +1358,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kSASlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kHSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -1356,105 +1369,131 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  auto decode = [&](long long id, int& w0, int& h0, int& d0, int& n) {
-    const int tw = (int)(id % tiles_w); id /= tiles_w;
-    const int th = (int)(id % tiles_h); id /= tiles_h;
-    d0 = (int)(id % D);
-    n = (int)(id / D);
+  // item -> patch origin, sample, output planes [d_lo, d_hi)
+  auto decode = [&](int id, int& w0, int& h0, int& d_lo, int& d_hi, int& n) {
+    const int tw = id % g.tiles_w; id /= g.tiles_w;
+    const int th = id % g.tiles_h; id /= g.tiles_h;
+    const int ch = id % g.chunks;
+    n = id / g.chunks;
     w0 = tw * kHW; h0 = th * kHH;
+    d_lo = ch * g.dc;
+    d_hi = min(g.D, d_lo + g.dc);
   };
 
   if (warp_id == 0) {
-    // ===== TMA producer: weights once, then one halo box per item =====
+    // ===== TMA producer: weights once, then one input plane at a time =====
     if (lane == 0) {
       mbar_expect_tx(b_full, kHBBytes);
       tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
       tma_load_3d(smem_b + 32 * 128, &tmB, b_full, 0, 0, 1);
       uint32_t it = 0;
-      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        int w0, h0, d0, n;
-        decode(item, w0, h0, d0, n);
-        const int s = it & 1;
-        mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&a_full[s], (uint32_t)kHRows * 128u);
-        tma_load_5d(smem + s * kHABuf, &tmA, &a_full[s], 0, w0 - 1, h0 - 1, d0 - 1, n);
+      for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        int w0, h0, d_lo, d_hi, n;
+        decode(item, w0, h0, d_lo, d_hi, n);
+        for (int z = d_lo - 1; z <= d_hi; ++z, ++it) {
+          const int s = it % kSASlots;
+          mbar_wait(&a_empty[s], ((it / kSASlots) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[s], (uint32_t)kSPRows * 128u);
+          tma_load_5d(smem + s * kSASlot, &tmA, &a_full[s], 0, w0 - 1, h0 - 1, z, n);
+        }
       }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer: 5 M-tiles x 4 K steps of UMMA 128 x 64 x 16 per item, one TMEM slot per M-tile =====
+    // ===== MMA issuer: per input plane 2 M-tiles x 4 K steps of UMMA 128 x 64 x 16, one TMEM slot per M-tile =====
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
     mbar_wait(b_full, 0);
     const uint32_t b_addr = smem_u32(smem_b);
     uint32_t it = 0, sl = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-      const uint32_t s = it & 1;
-      mbar_wait(&a_full[s], (it >> 1) & 1u);
-      const uint32_t a_addr = smem_u32(smem + s * kHABuf);
-      for (int m = 0; m < kHMTiles; ++m, ++sl) {
-        const uint32_t slot = sl % kHSlots;
-        mbar_wait(&slot_empty[slot], ((sl / kHSlots) & 1u) ^ 1u);
-        tc_fence_after();
-        if (elect_one()) {
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+      int w0, h0, d_lo, d_hi, n;
+      decode(item, w0, h0, d_lo, d_hi, n);
+      for (int z = d_lo - 1; z <= d_hi; ++z, ++it) {
+        const uint32_t s = it % kSASlots;
+        mbar_wait(&a_full[s], (it / kSASlots) & 1u);
+        const uint32_t a_addr = smem_u32(smem + s * kSASlot);
+        for (int m = 0; m < 2; ++m, ++sl) {
+          const uint32_t slot = sl % kHSlots;
+          mbar_wait(&slot_empty[slot], ((sl / kHSlots) & 1u) ^ 1u);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + slot * 64u, make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
-                      make_smem_desc(b_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
-          umma_commit(&slot_full[slot]);
-          if (m == kHMTiles - 1) umma_commit(&a_empty[s]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + slot * 64u, make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
+                        make_smem_desc(b_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&slot_full[slot]);
+            if (m == 1) umma_commit(&a_empty[s]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ===== epilogue (warps 2..5 <-> TMEM lane quadrants 2,3,0,1) =====
     const int q = warp_id & 3;
-    const int t128 = (warp_id - 2) * 32 + lane;          // one output voxel per epilogue thread
+    const int t128 = (warp_id - 2) * 32 + lane;          // one output voxel of the patch per epilogue thread
     const int ow = t128 % kHW, oh = t128 / kHW;
     const float bias = ep.bias ? ep.bias[0] : 0.f;
     const float inv_keep = 1.f / (1.f - ep.p);
     uint32_t sl = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      int w0, h0, d0, n;
-      decode(item, w0, h0, d0, n);
-#pragma unroll 1
-      for (int m = 0; m < kHMTiles; ++m, ++sl) {
-        const uint32_t slot = sl % kHSlots;
-        mbar_wait(&slot_full[slot], (sl / kHSlots) & 1u);
-        tc_fence_after();
-        uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32u, v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_empty[slot]);
-        const int prow = m * 128 + q * 32 + lane;
-        if (prow < kHRows) {
-          float* dst = P + (size_t)prow * kPStride;
-#pragma unroll
-          for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+      int w0, h0, d_lo, d_hi, n;
+      decode(item, w0, h0, d_lo, d_hi, n);
       const int w = w0 + ow, h = h0 + oh;
-      if (w < W && h < H) {
-        float acc = 0.f;
+      const bool inside = (w < g.W && h < g.H);
+      const int planes = d_hi - d_lo + 2;
+      for (int zi = 0; zi < planes; ++zi) {
+        float* Pz = P + (zi & (kSPSlots - 1)) * kSPSlotFloats;
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m, ++sl) {
+          const uint32_t slot = sl % kHSlots;
+          const int prow = m * 128 + q * 32 + lane;
+          mbar_wait(&slot_full[slot], (sl / kHSlots) & 1u);
+          tc_fence_after();
+          if (m * 128 + q * 32 < kSPRows) {           // warp-uniform: this quadrant holds rows of the plane
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32u, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[slot]);
+            if (prow < kSPRows) {
+              float* dst = Pz + prow * kPStride;
 #pragma unroll
-        for (int t = 0; t < 27; ++t) {
-          const int row = ((t / 9) * kHBH + oh + (t / 3) % 3) * kHBW + ow + t % 3;
-          acc += P[row * kPStride + t];
+              for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+            }
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[slot]);
+          }
         }
-        const long long vox = (((long long)n * D + d0) * H + h) * W + w;
-        float r = acc + bias;
-        if (ep.act == 1) {
-          r = fmaxf(r, 0.f);
-          if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
-          else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // P of input plane zi is complete
+        if (zi >= 2 && inside) {
+          // output plane d = d_lo + zi - 2 gathers tap kd from input plane (zi - 2 + kd)
+          float acc = 0.f;
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const float* Pk = P + ((zi - 2 + kd) & (kSPSlots - 1)) * kSPSlotFloats;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const int row = (oh + t9 / 3) * kHBW + ow + t9 % 3;
+              acc += Pk[row * kPStride + kd * 9 + t9];
+            }
+          }
+          const int d = d_lo + zi - 2;
+          const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
+          float r = acc + bias;
+          if (ep.act == 1) {
+            r = fmaxf(r, 0.f);
+            if (ep.mask != nullptr) r = ep.mask[vox] ? r * inv_keep : 0.f;
+            else if (ep.p > 0.f) r = philox_keep(resolve_seed(ep.seed), (unsigned long long)vox, ep.p) ? r * inv_keep : 0.f;
+          }
+          ep.y[vox] = r;
         }
-        ep.y[vox] = r;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // P is free for the next item
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the P ring is free for the next item
     }
   }
   tc_fence_before();
@@ -1493,7 +1532,7 @@ static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + 2 * kTileBytes + 2 * 
 __global__ void __launch_bounds__(288, 1)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
-                    int tiles_w, int tiles_h, long long items) {
+                    int tiles_w, int tiles_h, int items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + 2 * kC1ABytes;
@@ -1529,10 +1568,10 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  auto decode = [&](long long id, int& w0, int& h0, int& d0, long long& n) {
-    const int tw = (int)(id % tiles_w); id /= tiles_w;
-    const int th = (int)(id % tiles_h); id /= tiles_h;
-    d0 = (int)(id % D);
+  auto decode = [&](int id, int& w0, int& h0, int& d0, long long& n) {   // 32-bit: items < 2^31 (host check)
+    const int tw = id % tiles_w; id /= tiles_w;
+    const int th = id % tiles_h; id /= tiles_h;
+    d0 = id % D;
     n = id / D;
     w0 = tw * kHW; h0 = th * kHH;
   };
@@ -1549,7 +1588,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     mbar_wait(b_full, 0);
     const uint32_t b_addr = smem_u32(smem_b);
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t s = it & 1, ph = (it >> 1) & 1u;
       mbar_wait(&acc_empty[s], ph ^ 1u);
       mbar_wait(&a_full[s], ph);
@@ -1573,7 +1612,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     const int ow = row % kHW, oh = row / kHW;
     constexpr int kPer = (kHRows + 127) / 128;            // halo floats per thread (5)
     float pre[kPer];
-    auto fetch = [&](long long item) {
+    auto fetch = [&](int item) {
       int w0, h0, d0; long long n;
       decode(item, w0, h0, d0, n);
 #pragma unroll
@@ -1587,25 +1626,24 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         pre[j] = v;
       }
     };
-    if ((long long)blockIdx.x < items) fetch(blockIdx.x);
+    if ((int)blockIdx.x < items) fetch(blockIdx.x);
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t s = it & 1, ph = (it >> 1) & 1u;
       float* xh = xs + s * kC1Halo;
 #pragma unroll
       for (int j = 0; j < kPer; ++j)
         if (row + j * 128 < kHRows) xh[row + j * 128] = pre[j];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (item + gridDim.x < items) fetch(item + gridDim.x);     // next item's halo: in flight while this row is built
+      if (item + (int)gridDim.x < items) fetch(item + gridDim.x);     // next item's halo: in flight while this row is built
       uint32_t hi[16], lo[16];                              // 32 bf16 each: taps 0..26, then zeros
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float a = 0.f, b = 0.f;
         if (2 * j < 27) a = xh[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
         if (2 * j + 1 < 27) b = xh[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
-        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+        hi[j] = pack_bf16x2(a, b);                          // one packed conversion; bf16 -> fp32 is a 16-bit shift
+        lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xffff0000u));
       }
       mbar_wait(&a_empty[s], ph ^ 1u);                      // the MMAs that read this A buffer two items ago are done
       uint8_t* r0 = smem + s * kC1ABytes + row * 128;       // K block 0: [x_hi | x_lo]
@@ -1626,8 +1664,11 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     const int q = warp_id & 3;
     const int row = q * 32 + lane;
     const bool issuer = (warp_id == 5 && lane == 0);
+    float bia[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) bia[e] = bias ? __ldg(bias + e) : 0.f;
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       int w0, h0, d0; long long n;
       decode(item, w0, h0, d0, n);
       const uint32_t s = it & 1;
@@ -1650,8 +1691,8 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         float f[8], g8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(v0[c * 8 + e]) + (bias ? __ldg(bias + c * 8 + e) : 0.f);
-          g8[e] = __uint_as_float(v1[c * 8 + e]) + (bias ? __ldg(bias + 32 + c * 8 + e) : 0.f);
+          f[e] = __uint_as_float(v0[c * 8 + e]) + bia[c * 8 + e];
+          g8[e] = __uint_as_float(v1[c * 8 + e]) + bia[32 + c * 8 + e];
         }
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
@@ -1709,6 +1750,7 @@ int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, in
   if (make_act_tmap(&tmC, y, N, D, H, W, 64, kHW, kHH, 1)) return -1;
   const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
   const long long items = (long long)tiles_w * tiles_h * D * N;
+  SIVAE_CHECK(items < (1ll << 31), "c1_to_c64: too many tiles");
   static bool attr_set = false;
   if (!attr_set) {
     if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
@@ -1718,7 +1760,7 @@ int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, in
   }
   const long long cap = num_sms();   // one persistent CTA per SM (117 KB of shared memory, 288 threads x 161 registers)
   const unsigned ctas = (unsigned)(items < cap ? items : cap);
-  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, items);
+  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
   return 0;
 }
@@ -1846,9 +1888,8 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
         if (2 * j < 27) a = xs[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
         if (2 * j + 1 < 27) b = xs[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
         if (2 * j + 1 == 27) b = 1.0f;                     // row 27 of D accumulates sum_v xc[v][c]
-        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        hi[j] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
-        lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+        hi[j] = pack_bf16x2(a, b);
+        lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xffff0000u));
       }
       s1 += xs[(1 * kHBH + oh + 1) * kHBW + ow + 1];       // centre tap; zero outside the volume
       mbar_wait(&empty[s], (uint32_t)((it / kWg1Stages) & 1) ^ 1u);
@@ -1971,7 +2012,7 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
     pack_to1_halo_weights_kernel<<<16, 256, 0, st>>>(w, flip, (__nv_bfloat16*)ws);
     SIVAE_LAUNCH_OK("pack_to1_halo_weights_kernel");
     CUtensorMap tmA, tmB;
-    if (make_act_tmap(&tmA, x, N, D, H, W, 64, kHBW, kHBH, kHBD)) return -1;
+    if (make_act_tmap(&tmA, x, N, D, H, W, 64, kHBW, kHBH, 1)) return -1;
     {
       uint64_t dims[3] = {64, 32, 2};
       uint64_t strides[2] = {128, 32 * 128};
@@ -1980,8 +2021,18 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
     }
     ToOneEpilogue ep;
     ep.y = y; ep.bias = bias; ep.mask = mask; ep.seed = make_seed_ref(seed); ep.p = p; ep.act = act;
-    const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
-    const long long items = (long long)tiles_w * tiles_h * D * N;
+    To1Geom tg;
+    tg.N = N; tg.D = D; tg.H = H; tg.W = W;
+    tg.tiles_w = cdiv(W, kHW); tg.tiles_h = cdiv(H, kHH);
+    // depth chunks: ~20 planes each (2 extra input planes per chunk = 10 % overhead), more chunks when the patches
+    // alone cannot fill the SMs
+    const long long patches = (long long)tg.tiles_w * tg.tiles_h * N;
+    int chunks = cdiv(D, 20);
+    while (patches * chunks < 2ll * num_sms() && chunks < D) ++chunks;
+    tg.dc = cdiv(D, chunks);
+    tg.chunks = cdiv(D, tg.dc);
+    SIVAE_CHECK(patches * tg.chunks < (1ll << 31), "conv3_to1: too many tiles");
+    tg.items = (int)(patches * tg.chunks);
     static bool attr_set = false;
     if (!attr_set) {
       if (check_cuda(cudaFuncSetAttribute(conv3_to1_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTo1Smem),
@@ -1989,8 +2040,8 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
         return -1;
       attr_set = true;
     }
-    const unsigned ctas = (unsigned)(items < (long long)num_sms() ? items : (long long)num_sms());
-    conv3_to1_halo_kernel<<<ctas, 192, kTo1Smem, st>>>(tmA, tmB, N, D, H, W, tiles_w, tiles_h, items, ep);
+    const unsigned ctas = (unsigned)(tg.items < num_sms() ? tg.items : num_sms());
+    conv3_to1_halo_kernel<<<ctas, 192, kTo1Smem, st>>>(tmA, tmB, tg, ep);
     SIVAE_LAUNCH_OK("conv3_to1_halo_kernel");
     return 0;
   }
