@@ -162,8 +162,12 @@ def run_ours(args):
     # between the replays (parallel.FlatGradReducer; graph.GraphedTrainStep).  --no-graph: eager step, and for
     # N > 1 the bucketed reducer that overlaps NCCL with backward (parallel.GradReducer).
     use_graph = not args.no_graph
-    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
-    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
+    if args.torch_adam:
+        opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=use_graph)
+        opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=use_graph)
+    else:   # fused multi-tensor Adam + bf16 weight re-pack (one C-ABI call per phase)
+        opt_e = sivae_b200.FusedAdam(net.encoder.parameters(), lr=2e-4)
+        opt_d = sivae_b200.FusedAdam(net.decoder.parameters(), lr=2e-4)
     Reducer = P.FlatGradReducer if use_graph else P.GradReducer
     red_e = Reducer(net.encoder.parameters()) if world > 1 else None
     red_d = Reducer(net.decoder.parameters()) if world > 1 else None
@@ -330,6 +334,7 @@ def main():
     ap.add_argument("--batch", type=int, default=LOCAL_BATCH, help="local batch per GPU (headline: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel/per-shape timing table here")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the fused optimiser")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

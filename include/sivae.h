@@ -221,6 +221,26 @@ int sivae_mse_persample_bwd(const float* x, const float* y, const float* g, floa
 int sivae_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst_bf16, int N, int C, long long vox, void* stream);
 int sivae_ndhwc_bf16_to_ncdhw_f32(const void* src_bf16, float* dst, int N, int C, long long vox, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step fused with the weight re-pack (SURVEY.md section 8f NEXT-2).
+ * Replaces optimizer_e.step() / optimizer_d.step() (utils/my_trainer.py:288,:324; torch.optim.Adam constructed at
+ * :183-184 with lr 2e-4 and default betas / eps) and the pack_conv3_weights call per updated 3x3x3 weight.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sivae_adam_tensor {
+  float* param;            /* fp32 parameter, updated in place */
+  const float* grad;       /* fp32 gradient */
+  float* exp_avg;          /* Adam first moment */
+  float* exp_avg_sq;       /* Adam second moment */
+  long long numel;
+  void* pack_fwd;          /* optional: bf16 wf[27][Cout][Cin] of a Conv3d(k=3) weight [Cout][Cin][27], refreshed */
+  void* pack_dgrad;        /* optional: bf16 wd[27][Cin][Cout] (flipped + transposed) */
+  int cout, cin;           /* only read when pack_fwd != NULL */
+} sivae_adam_tensor;
+/* `tensors` is a HOST array (descriptors travel as kernel arguments); `lr` and `step` are DEVICE scalars: the update
+ * uses t = *step + 1 for the bias corrections and *step is incremented once at the end of the call. */
+int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
+                    float eps, long long* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,4 +276,24 @@ def to_ncdhw_f32(x):
     return _ncdhw(x).contiguous()
 
 
+def adam_step(tensors, lr, beta1, beta2, eps, step):
+    """torch/optim/adam.py _single_tensor_adam (no weight decay / amsgrad / maximize), which is what the reference's
+    torch.optim.Adam(lr=2e-4) runs (utils/my_trainer.py:183-184,:288,:324); refreshes the given bf16 packs."""
+    t = int(step.item()) + 1
+    lr_v = float(lr.item())
+    bc1 = 1.0 - beta1 ** t
+    bc2_sqrt = (1.0 - beta2 ** t) ** 0.5
+    for p, g, m, v, packs in tensors:
+        m.lerp_(g, 1.0 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.data.addcdiv_(m, denom, value=-(lr_v / bc1))   # .data: like the kernel, no version-counter bump
+        if packs is not None:
+            wf, wd = pack_conv3_weights(p.detach())
+            packs[0].copy_(wf)
+            if packs[1] is not None:
+                packs[1].copy_(wd)
+    step += 1
+
+
 ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F",)]

@@ -101,6 +101,7 @@ int kl_persample_bwd(const float*, const float*, const float*, float*, float*, i
 size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
+int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
 
 }  // namespace sivae
 
@@ -247,6 +248,10 @@ int sivae_mse_persample_fwd(const float* x, const float* y, float* r, int B, lon
 int sivae_mse_persample_bwd(const float* x, const float* y, const float* g, float* dx, float* dy, int B, long long n,
                             void* stream) {
   return mse_persample_bwd(x, y, g, dx, dy, B, n, ST(stream));
+}
+int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
+                    float eps, long long* step, void* stream) {
+  return adam_step(tensors, ntensors, lr, beta1, beta2, eps, step, ST(stream));
 }
 int sivae_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, long long vox, void* stream) {
   return ncdhw_f32_to_ndhwc_bf16(src, dst, N, C, vox, ST(stream));

@@ -117,6 +117,24 @@ def _packed(weight: torch.Tensor, up: bool = False):
     return packs
 
 
+def current_packs(weight: torch.Tensor, up: bool = False):
+    """The cached packs of ``weight`` if they are current, else None (used by optim.FusedAdam, which refreshes the
+    plain 27-tap packs inside its update kernel)."""
+    hit = _pack_cache.get((id(weight), up))
+    if hit is not None:
+        ref, ptr, ver, packs = hit
+        if ref() is weight and ptr == weight.data_ptr() and ver == weight._version:
+            return packs
+    return None
+
+
+def drop_packs(weight: torch.Tensor, up: Optional[bool] = None):
+    """Forget cached packs of ``weight`` (both kinds, or only the plain / upsample-folded one): an update that bypasses
+    torch's version counter (FusedAdam) must call this for every pack it did not refresh itself."""
+    for kind in ((False, True) if up is None else (up,)):
+        _pack_cache.pop((id(weight), kind), None)
+
+
 class _ConvBnAct(torch.autograd.Function):
     """``pre_up``: a nearest Upsample(2) sits in front of the convolution (UpsampleBuildingkBlock, models.py:58-59);
     it is folded into the convolution (8 output parities x 8 pre-summed taps) instead of being materialised."""

@@ -41,9 +41,11 @@ class GraphedTrainStep:
     def __init__(self, model, optimizer_e, optimizer_d, real_example: torch.Tensor, noise_example: torch.Tensor,
                  hp: Optional[T.StepHyper] = None, warmup: int = 3, reducer_e=None, reducer_d=None):
         for opt in (optimizer_e, optimizer_d):
+            if getattr(opt, "graph_safe", False):      # optim.FusedAdam: lr / step counter live on the device
+                continue
             for g in opt.param_groups:
                 if not g.get("capturable", False):
-                    raise ValueError("GraphedTrainStep needs optimisers constructed with capturable=True")
+                    raise ValueError("GraphedTrainStep needs optim.FusedAdam or torch optimisers with capturable=True")
         self.model, self.opt_e, self.opt_d, self.hp = model, optimizer_e, optimizer_d, hp or T.StepHyper()
         self.red_e, self.red_d = reducer_e, reducer_d
         self.split = reducer_e is not None or reducer_d is not None
@@ -90,6 +92,9 @@ class GraphedTrainStep:
         The returned dict holds the captured loss tensors: values are overwritten by the next call."""
         self.real.copy_(real_batch, non_blocking=True)
         self.noise.copy_(noise_batch, non_blocking=True)
+        for opt in (self.opt_e, self.opt_d):
+            if hasattr(opt, "sync_lr"):
+                opt.sync_lr()          # LR-scheduler changes reach the device scalar the captured step reads
         if not self.split:
             self.graph.replay()
         else:

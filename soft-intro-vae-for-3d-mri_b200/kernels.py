@@ -65,6 +65,7 @@ _SIGNATURES = {
     "sivae_mse_workspace_bytes": (_sz, [_i, _ll]),
     "sivae_mse_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _sz, _vp]),
     "sivae_mse_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
+    "sivae_adam_step": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _vp]),
     "sivae_ncdhw_f32_to_ndhwc_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "sivae_ndhwc_bf16_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
 }
@@ -368,6 +369,41 @@ def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int
                                 n, d, h, w, c, slope, resample, _p(mask), p, seed, _p(ws), ws.numel(), _stream(y)),
            "sivae_bn_act_bwd")
     return dconv, dres, (aff[0] if need_affine else None), (aff[1] if need_affine else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused multi-tensor Adam step + weight re-pack (SURVEY section 8f NEXT-2)
+# ----------------------------------------------------------------------------------------------
+class _AdamTensor(ctypes.Structure):
+    """mirror of ``sivae_adam_tensor`` (include/sivae.h)"""
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("numel", _ll),
+                ("pack_fwd", _vp), ("pack_dgrad", _vp), ("cout", _i), ("cin", _i)]
+
+
+def adam_step(tensors, lr: torch.Tensor, beta1: float, beta2: float, eps: float, step: torch.Tensor):
+    """One Adam update of every (param, grad, exp_avg, exp_avg_sq, packs) in ``tensors`` -- ``packs`` is None or the
+    (wf, wd) bf16 packs of a Conv3d(k=3) weight, refreshed in the same pass.  ``lr`` (fp32) and ``step`` (int64) are
+    one-element device tensors; ``step`` is incremented once."""
+    if not tensors:
+        return
+    _req(lr, torch.float32, "lr")
+    _req(step, torch.int64, "step")
+    arr = (_AdamTensor * len(tensors))()
+    for i, (p, g, m, v, packs) in enumerate(tensors):
+        for t, nm in ((p, "param"), (g, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+            _req(t, torch.float32, nm)
+        assert g.shape == p.shape and m.shape == p.shape and v.shape == p.shape
+        arr[i].param, arr[i].grad, arr[i].exp_avg, arr[i].exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+        arr[i].numel = p.numel()
+        if packs is not None:
+            wf, wd = packs
+            assert p.dim() == 5 and tuple(p.shape[2:]) == (3, 3, 3)
+            _req(wf, torch.bfloat16, "wf")
+            arr[i].pack_fwd = wf.data_ptr()
+            arr[i].pack_dgrad = wd.data_ptr() if wd is not None else None
+            arr[i].cout, arr[i].cin = p.shape[0], p.shape[1]
+    _check(_L().sivae_adam_step(ctypes.cast(arr, ctypes.c_void_p), len(tensors), _p(lr), beta1, beta2, eps, _p(step),
+                                _stream(lr)), "sivae_adam_step")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(rank), GLOO_SOCKET_IFNAME="lo")
     import sivae_b200
     from sivae_b200 import parallel as P
     r, w, _ = P.init_distributed("gloo")
@@ -69,11 +69,11 @@ def _worker(rank, world, port, q):
         out[step] = got.clone()
     scal = P.all_reduce_mean_scalars({"a": torch.tensor(float(rank)), "b": torch.tensor(2.0)})
     assert float(scal["a"]) == pytest.approx((world - 1) / 2) and float(scal["b"]) == 2.0
-    q.put((rank, out[2]))
+    q.put((rank, out[2].tolist()))        # plain lists: a tensor would travel as a shared-memory fd that dies with the child
     dist.destroy_process_group()
 
 
-def _run_world(worker, world=2, attempts=2):
+def _run_world(worker, world=2, attempts=3):
     """Spawn ``world`` gloo ranks; retry once on a rendezvous failure (the probed free port can be taken by
     another process between the probe and the bind)."""
     ctx = mp.get_context("spawn")
@@ -102,14 +102,14 @@ def _run_world(worker, world=2, attempts=2):
 
 def test_grad_reducer_world2_gloo():
     res = _run_world(_worker)
-    assert torch.equal(res[0], res[1])
+    assert res[0] == res[1]
 
 
 def _flat_worker(rank, world, port, q):
     """FlatGradReducer (the reducer of the multi-rank CUDA-graph path): gradients live as views of one flat
     buffer, one all-reduce per phase; an unused parameter keeps grad None; replicas stay bit-identical."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(rank), GLOO_SOCKET_IFNAME="lo")
     import sivae_b200
     from sivae_b200 import parallel as P
     from sivae_b200 import trainer as T
@@ -136,10 +136,10 @@ def _flat_worker(rank, world, port, q):
         assert all(p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
                    for p in enc.parameters())
         opt.step()
-    q.put((rank, torch.cat([p.detach().flatten() for p in enc.parameters()])))
+    q.put((rank, torch.cat([p.detach().flatten() for p in enc.parameters()]).tolist()))
     dist.destroy_process_group()
 
 
 def test_flat_grad_reducer_world2_gloo():
     res = _run_world(_flat_worker)
-    assert torch.equal(res[0], res[1])
+    assert res[0] == res[1]

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== all gpu tests"; timeout 1200 python -m pytest tests -q -m gpu --tb=short -x > gpurun_out/t_all.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/t_all.log
+echo "== bench fused adam"; timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --kernel-table gpurun_out/kernel_table.txt > gpurun_out/bench.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench.log | cut -c1-300
+echo "== bench torch adam"; timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --torch-adam > gpurun_out/bench_torch_adam.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_torch_adam.log | cut -c1-300
