@@ -68,6 +68,17 @@ int sivae_conv3_igemm(const void* x_bf16, const void* wpack_bf16, void* y_bf16,
 
 /* dw[co][ci][tap] = sum_{n,d,h,w} dy[n,d,h,w,co] * x[n,d+kd-1,h+kh-1,w+kw-1,ci]   (fp32, torch layout)
  * Split-K tcgen05 GEMM over voxels + deterministic second-stage reduction. */
+/* Conv3d(k=3,p=1,bias=False) followed by the train-mode statistics of BatchNorm3d on its output (models/models.py:17-18,
+ * :21-22, :55-56): y as sivae_conv3_igemm, then mean / invstd / scale = gamma*invstd / shift = beta - mean*scale and the
+ * running-stat update exactly as sivae_bn_train_coeffs.  When the persistent convolution kernel takes the shape the
+ * per-channel sums come out of its epilogue (no extra pass over y); otherwise the separate statistics pass runs.
+ * workspace: sivae_bn_workspace_bytes(Cout). */
+int sivae_conv3_igemm_bn(const void* x_bf16, const void* wpack_bf16, void* y_bf16,
+                         int N, int D, int H, int W, int Cin, int Cout,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var,
+                         long long* num_batches_tracked, float momentum, float eps,
+                         float* mean, float* invstd, float* scale, float* shift,
+                         void* workspace, size_t workspace_bytes, void* stream);
 size_t sivae_conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
 int sivae_conv3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw,
                       void* workspace, size_t workspace_bytes,

@@ -61,6 +61,11 @@ def conv3_igemm(x, wpack):
     return _ndhwc(y, x.dtype)
 
 
+def conv3_igemm_bn(x, wpack, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps):
+    y = conv3_igemm(x, wpack)
+    return (y,) + tuple(bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps))
+
+
 def conv3_wgrad(x, dy):
     xi, g = _ncdhw(x), _ncdhw(dy)
     co, ci = g.shape[1], xi.shape[1]

@@ -102,6 +102,8 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+int conv3_igemm_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
+                   float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 
 }  // namespace sivae
 
@@ -145,6 +147,13 @@ int sivae_pack_conv3_weights(const float* w, int Cout, int Cin, void* wf, void* 
 int sivae_conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
                       void* stream) {
   return conv3_igemm(x, wpack, y, N, D, H, W, Cin, Cout, ST(stream));
+}
+int sivae_conv3_igemm_bn(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                         const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                         float eps, float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                         void* stream) {
+  return conv3_igemm_bn(x, wpack, y, N, D, H, W, Cin, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale,
+                        shift, ws, ws_bytes, ST(stream));
 }
 size_t sivae_conv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
   return conv3_wgrad_workspace_bytes(N, D, H, W, Cin, Cout);

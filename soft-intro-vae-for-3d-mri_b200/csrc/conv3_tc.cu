@@ -452,7 +452,7 @@ conv3_kw64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // pass (kh,kw)=(0,0)) is issued separately with accumulate = 0.
 //   work item  = 8(w) x 16(h) patch x 4 planes;   9 (kh,kw) passes x 6 input tiles of 16 KB, 9 x 24 KB of weights.
 //   L2 -> SMEM = (54*16 + 9*24) KB / 4 tiles = 270 KB per 128 outputs (tap-by-tap kernel: 648 KB).
-// Persistent, one CTA per SM; A ring 6 x 16 KB, B ring 3 x 24 KB, two TMEM stages of 256 columns (the epilogue of
+// Persistent, one CTA per SM; A ring 8 x 16 KB, B ring 2 x 24 KB, two TMEM stages of 256 columns (the epilogue of
 // item i overlaps the MMAs of item i+1), two output staging tiles for the TMA stores.
 // 7 warps: A producer, MMA issuer, B producer, 4 epilogue warps.
 // =================================================================================================
@@ -462,14 +462,14 @@ struct KdGeom {
   long long items;
 };
 static constexpr int kKdP = 4;                       // output planes per work item
-static constexpr int kKdAStages = 6;
-static constexpr int kKdBStages = 3;
+static constexpr int kKdAStages = 8;
+static constexpr int kKdBStages = 2;
 static constexpr int kKdBBytes = 3 * 64 * 128;       // [kd=0 | kd=1 | kd=2] slabs of one (kh, kw)
 static constexpr int kKdSmem = kKdAStages * kTileBytes + kKdBStages * kKdBBytes + 2 * kTileBytes + 1024 + 256;
 
 __global__ void __launch_bounds__(224, 1)
 conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const KdGeom g) {
+                 const __grid_constant__ CUtensorMap tmC, const KdGeom g, float* __restrict__ stats_partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + kKdAStages * kTileBytes;
@@ -595,6 +595,9 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp_id & 3;
     const int row = q * 32 + lane;
     const bool issuer = (warp_id == 3 && lane == 0);
+    // fused BatchNorm statistics (stats_partial != NULL): every epilogue warp sums, per channel pair of its lane, the
+    // bf16-rounded values of the 32 rows it staged -- i.e. statistics of the tensor exactly as stored
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     uint32_t acc_it = 0, st_it = 0;
     for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
       int w0, h0, d0, n;
@@ -639,7 +642,28 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (d0 + i < g.D) tma_store_5d(&tmC, tile, 0, w0, h0, d0 + i, n);
           tma_store_commit();   // a (possibly empty) group per tile keeps the wait_group arithmetic uniform
         }
+        if (stats_partial != nullptr && d0 + i < g.D) {
+          // lane l owns channels 2l, 2l+1: one conflict-free 4-byte read per row of this warp's 32 staged rows
+          const bool full = (w0 + kKwW <= g.W) && (h0 + kKwH <= g.H);
+          const uint32_t chunk = (uint32_t)lane >> 2, within = ((uint32_t)lane & 3u) * 4u;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int rr = q * 32 + r;
+            if (full || ((w0 + (rr & 7) < g.W) && (h0 + (rr >> 3) < g.H))) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + rr * 128 + ((chunk ^ (uint32_t)(rr & 7)) << 4) + within);
+              const float2 f = unpack_bf16x2(u);
+              s1a += f.x; s1b += f.y;
+              s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+            }
+          }
+        }
       }
+    }
+    if (stats_partial != nullptr) {
+      // partial[(blk * 2 + {0: sum, 1: sum of squares}) * 64 + c], blk = CTA * 4 + epilogue warp (bn finalize layout)
+      float* dst = stats_partial + (size_t)(blockIdx.x * 4 + (warp_id - 3)) * 2 * 64;
+      *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(s1a, s1b);
+      *reinterpret_cast<float2*>(dst + 64 + 2 * lane) = make_float2(s2a, s2b);
     }
     if (issuer) tma_store_wait_read_all();
   }
@@ -1126,8 +1150,12 @@ static int make_weight_tmap(CUtensorMap* tm, const void* wpack, int taps, int ro
   return make_tmap_bf16(tm, wpack, 3, dims, strides, box);
 }
 
-int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
-                cudaStream_t st) {
+// stats / stats_blocks: when both are non-NULL and the persistent kd-fused kernel takes the shape, the kernel also
+// writes per-block BatchNorm partial sums of its output to `stats` and *stats_blocks = number of partial blocks;
+// otherwise *stats_blocks = 0 and the caller runs the separate statistics pass.
+static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                            float* stats, int* stats_blocks, cudaStream_t st) {
+  if (stats_blocks) *stats_blocks = 0;
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64, "conv3_igemm: Cin=%d must be a multiple of 64", Cin);
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
@@ -1154,8 +1182,10 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
         attr_set = true;
       }
       const unsigned ctas = (unsigned)(kg.items < (long long)num_sms() ? kg.items : (long long)num_sms());
-      conv3_kd3_kernel<<<ctas, 224, kKdSmem, st>>>(tA, tB, tC, kg);
+      const bool fuse_stats = stats != nullptr && stats_blocks != nullptr;
+      conv3_kd3_kernel<<<ctas, 224, kKdSmem, st>>>(tA, tB, tC, kg, fuse_stats ? stats : nullptr);
       SIVAE_LAUNCH_OK("conv3_kd3_kernel");
+      if (fuse_stats) *stats_blocks = (int)ctas * 4;
       return 0;
     }
   }
@@ -1209,6 +1239,40 @@ int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, 
   const ToOneEpilogue ep{};
   if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
   return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
+}
+
+int conv3_igemm(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                cudaStream_t st) {
+  return conv3_igemm_impl(x, wpack, y, N, D, H, W, Cin, Cout, nullptr, nullptr, st);
+}
+
+// pointwise.cu
+int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, const float* beta, float* rm, float* rv,
+                    long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+int bn_coeffs_from_partials(const float* partial, int nblocks, long long nvox, int C, const float* gamma,
+                            const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                            float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
+size_t bn_workspace_bytes(int C);
+
+// Convolution + train-mode BatchNorm coefficients of its output in one call (models/models.py:17-18, :21-22: Conv3d
+// followed by BatchNorm3d): the statistics come out of the convolution's epilogue when the persistent kernel runs,
+// from the separate bn_stats pass otherwise.
+int conv3_igemm_bn(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                   const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                   float eps, float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  SIVAE_CHECK(ws && ws_bytes >= bn_workspace_bytes(Cout), "conv3_igemm_bn: workspace too small");
+  int blocks = 0;
+  const bool allow = getenv("SIVAE_NO_FUSED_STATS") == nullptr;
+  int rc = conv3_igemm_impl(x, wpack, y, N, D, H, W, Cin, Cout, allow ? (float*)ws : nullptr, allow ? &blocks : nullptr, st);
+  if (rc) return rc;
+  const long long nvox = (long long)N * D * H * W;
+  if (blocks > 0)
+    return bn_coeffs_from_partials((const float*)ws, blocks, nvox, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean,
+                                   invstd, scale, shift, st);
+  return bn_train_coeffs(y, nvox, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift, ws, ws_bytes,
+                         st);
 }
 
 // y_hi[n, 2d+pd, 2h+ph, 2w+pw, co] = conv3(upsample2(x_lo), w):  8 parity-specific 2x2x2 convolutions on the low-res grid.

@@ -760,6 +760,16 @@ int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, co
   return 0;
 }
 
+int bn_coeffs_from_partials(const float* partial, int nblocks, long long nvox, int C, const float* gamma,
+                            const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                            float* mean, float* invstd, float* scale, float* shift, cudaStream_t st) {
+  SIVAE_CHECK(channels_ok(C) && nblocks > 0 && nblocks <= kBnMaxBlocks && nvox > 0, "bn_coeffs_from_partials: bad arguments");
+  bn_stats_finalize_kernel<<<cdiv(C, 8), kFinThreads, 0, st>>>(partial, nblocks, C, nvox, gamma, beta, rm, rv, nbt,
+                                                                momentum, eps, mean, invstd, scale, shift);
+  SIVAE_LAUNCH_OK("bn_stats_finalize_kernel");
+  return 0;
+}
+
 static int check_resample(const char* who, int D, int H, int W, int resample) {
   SIVAE_CHECK(resample >= 0 && resample <= 2, "%s: bad resample mode %d", who, resample);
   if (resample == SIVAE_RESAMPLE_AVGPOOL2)

@@ -142,8 +142,13 @@ class _ConvBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int, pre_up: bool):
         wf, wd = _packed(weight, pre_up)
-        y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
-        mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
+        if bn.training and not pre_up:
+            # convolution + batch statistics in one C-ABI call (the sums come out of the conv epilogue)
+            y, mean, invstd, scale, shift = K.conv3_igemm_bn(x, wf, gamma, beta, bn.running_mean, bn.running_var,
+                                                             bn.num_batches_tracked, bn.momentum, bn.eps)
+        else:
+            y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
+            mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
         out = K.bn_act_fwd(y, scale, shift, res, slope, resample)
         # x is only needed for the weight gradient: frozen-parameter passes (dgrad-only) do not keep it
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)

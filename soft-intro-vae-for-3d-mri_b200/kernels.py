@@ -35,6 +35,8 @@ _SIGNATURES = {
     "sivae_advance_seed_counter": (_i, [_vp]),
     "sivae_pack_conv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "sivae_conv3_igemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_conv3_igemm_bn": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp,
+                                  _vp, _vp, _sz, _vp]),
     "sivae_conv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_conv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_pack_upconv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -229,6 +231,30 @@ def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
            lambda: _check(_L().sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
                           "sivae_conv3_igemm"))
     return y
+
+
+def conv3_igemm_bn(x: torch.Tensor, wpack: torch.Tensor, gamma, beta, running_mean, running_var, num_batches_tracked,
+                   momentum: float, eps: float):
+    """y = conv3(x), plus the train-mode BatchNorm coefficients of y: -> (y, mean, invstd, scale, shift).  The channel
+    sums come from the convolution's epilogue when the persistent kernel runs (no extra pass over y)."""
+    _req(x, torch.bfloat16, "x")
+    _req(wpack, torch.bfloat16, "wpack")
+    n, d, h, w, ci = x.shape
+    taps, co, ci2 = wpack.shape
+    assert taps == 27 and ci2 == ci
+    lib = _L()
+    y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
+    ws = _workspace(x.device, lib.sivae_bn_workspace_bytes(co), "bn")
+    coef = torch.empty(4, co, dtype=torch.float32, device=x.device)
+    if num_batches_tracked is not None:
+        _req(num_batches_tracked, torch.int64, "num_batches_tracked")
+    flops = 2.0 * 27 * ci * co * n * d * h * w
+    _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(lib.sivae_conv3_igemm_bn(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _p(gamma), _p(beta),
+                                                   _p(running_mean), _p(running_var), _p(num_batches_tracked), momentum,
+                                                   eps, _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]), _p(ws),
+                                                   ws.numel(), _stream(x)), "sivae_conv3_igemm_bn"))
+    return y, coef[0], coef[1], coef[2], coef[3]
 
 
 def conv3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:

@@ -203,3 +203,40 @@ def test_upconv_wgrad(shape):
     assert torch.isfinite(got).all()
     err, scale = float((got - ref).abs().max()), float(ref.abs().max())
     assert err <= 2e-3 * scale + 1e-5, f"upconv wgrad {shape}: max err {err:.4e} vs scale {scale:.4e}"
+
+
+# ---------------------------------------------------------------- convolution + fused BatchNorm statistics
+@pytest.mark.parametrize("shape", [(1, 8, 16, 16, 64, 64), (2, 6, 30, 44, 64, 64), (1, 7, 16, 40, 64, 64),
+                                   (3, 12, 32, 24, 64, 64), (1, 5, 7, 9, 128, 64), (1, 10, 12, 10, 256, 256)])
+@pytest.mark.parametrize("mode", ["auto", "kd_force"])
+def test_conv_bn_fused_stats(shape, mode):
+    """sivae_conv3_igemm_bn = sivae_conv3_igemm + sivae_bn_train_coeffs: with the persistent kd-fused kernel
+    (forced here also for ragged shapes: partial tiles must be masked out of the sums) the statistics come from the
+    convolution epilogue; they must equal the separate pass over the stored tensor."""
+    import os
+    old = os.environ.pop("SIVAE_CONV_KD", None)
+    if mode == "kd_force":
+        os.environ["SIVAE_CONV_KD"] = "force"
+    try:
+        n, d, h, w, ci, co = shape
+        x, wt = _mk(*shape)
+        wf, _ = K.pack_conv3_weights(wt)
+        gamma, beta = torch.rand(co, device=DEV) + 0.5, torch.randn(co, device=DEV)
+        rm1, rv1, nbt1 = torch.zeros(co, device=DEV), torch.ones(co, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+        rm2, rv2, nbt2 = rm1.clone(), rv1.clone(), nbt1.clone()
+        y, mean, invstd, scale, shift = K.conv3_igemm_bn(x, wf, gamma, beta, rm1, rv1, nbt1, 0.1, 1e-5)
+        y_ref = K.conv3_igemm(x, wf)
+        ref = K.bn_train_coeffs(y_ref, gamma, beta, rm2, rv2, nbt2, 0.1, 1e-5)
+        assert torch.equal(y, y_ref)
+        for a, b, name in zip((mean, invstd, scale, shift), ref, ("mean", "invstd", "scale", "shift")):
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (name, float((a - b).abs().max()))
+        assert torch.allclose(rm1, rm2, rtol=2e-5, atol=2e-6) and torch.allclose(rv1, rv2, rtol=2e-5, atol=2e-6)
+        assert int(nbt1) == 1 and int(nbt2) == 1
+        # and against the definition
+        yf = y.float().reshape(-1, co)
+        assert torch.allclose(mean, yf.mean(0), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(invstd, (yf.var(0, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+    finally:
+        os.environ.pop("SIVAE_CONV_KD", None)
+        if old is not None:
+            os.environ["SIVAE_CONV_KD"] = old
