@@ -33,6 +33,12 @@ VOL = (80, 96, 80)
 LOCAL_BATCH = 8
 GFLOP_PER_VOLUME_STEP = 7270.4       # 32 network passes x 227.2 GFLOP (SURVEY.md section 8d / BASELINE.md section 2)
 METRIC = "train volumes/sec (Soft-IntroVAE z=1200, 80x96x80)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on its top shape
+# (conv3_kd3_kernel, 64->64 @ 8x80x96x80; algorithmic 2 x 629.1 MB), from the ncu --set full capture summarised in
+# profiles/r01c_ncu_hot_kernels.md
+TRAFFIC_TOP_SHAPE_BYTES = 629615000 + 592356352
+TRAFFIC_NOTE = ("per launch of the top shape (64->64 @ 8x80x96x80), ncu --set full capture in "
+                "profiles/r01c_ncu_hot_kernels.md; algorithmic bytes 1.258e9")
 
 
 def _peaks():
@@ -153,7 +159,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     K.device_check()
     B = args.batch
-    D, H, W = VOL
+    D, H, W = args.vol
     torch.manual_seed(77)                                   # identical init on every rank
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
@@ -277,14 +283,19 @@ def run_ours(args):
     vols = world * B * args.steps
     value = vols / (ms / 1e3)
     e2e = vols / (ms_e2e / 1e3)
+    vol_scale = (D * H * W) / float(VOL[0] * VOL[1] * VOL[2])     # FLOPs scale with the voxel count (fully convolutional)
+    gflop_step = GFLOP_PER_VOLUME_STEP * vol_scale
     peak_tf, peak_gbs, peak_src = _peaks()
     dom = ksum.get("conv3_igemm", dict(launches=0, ms=0.0, work=0.0, by_shape={}))
     achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
     top_shape = max(dom["by_shape"].items(), key=lambda kv: kv[1]["ms"]) if dom["by_shape"] else None
     wg = ksum.get("conv3_wgrad", dict(launches=0, ms=0.0, work=0.0))
-    roofline = {"bound": "tensor", "kernel": "conv3_igemm_kernel (tcgen05 implicit-GEMM fprop/dgrad)",
+    roofline = {"bound": "tensor",
+                "kernel": "3x3x3 conv fprop/dgrad on tcgen05 (conv3_kd3_kernel + conv3_igemm_kernel, all layer shapes)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained",
+                "traffic": TRAFFIC_TOP_SHAPE_BYTES if tuple(args.vol) == VOL and B == LOCAL_BATCH else None,
+                "traffic_note": TRAFFIC_NOTE,
                 "launches": dom["launches"],
                 "share_of_step": dom["ms"] / (ms / args.steps if graphed is not None else ms) if ms else None,
                 "top_shape": ({"NDHWCiCo": list(top_shape[0]),
@@ -295,15 +306,16 @@ def run_ours(args):
                           "launches": wg["launches"]},
                 "timing": ("CUDA events around every launch of the kernel in one eager step of the same run"
                            if graphed is not None else "CUDA events around every launch inside the timed region"),
-                "whole_step_tflops": value / world * GFLOP_PER_VOLUME_STEP / 1e3}
+                "whole_step_tflops": value / world * gflop_step / 1e3}
     line = {"metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "z-1200main.py Soft-IntroVAE(64,[[64,1,2],[128,1,2],[256,2,2]]) z=1200, 80x96x80, "
+            "config": {"workload": "z-1200main.py Soft-IntroVAE(64,[[64,1,2],[128,1,2],[256,2,2]]) "
+                                   f"latent {D // 8}x{H // 8}x{W // 8} (z={D * H * W // 512}), {D}x{H}x{W}, "
                                    "one E+D train step incl. 2 Adam steps",
                        "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
-                       "gflop_per_volume_step": GFLOP_PER_VOLUME_STEP, "cuda_graph": graphed is not None,
+                       "gflop_per_volume_step": gflop_step, "cuda_graph": graphed is not None,
                        "cuda_graph_note": graph_note},
             "clocks": clocks, "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
@@ -332,6 +344,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=LOCAL_BATCH, help="local batch per GPU (headline: 8)")
+    ap.add_argument("--vol", type=int, nargs=3, default=list(VOL), metavar=("D", "H", "W"),
+                    help="volume extents (headline 80 96 80; 160 192 160 = the ~5M-voxel L-shape, use --batch 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel/per-shape timing table here")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the fused optimiser")

@@ -174,6 +174,16 @@ size_t sivae_c1_to_c64_workspace_bytes(void);
 int sivae_c1_to_c64(const float* x1, const float* w, const float* bias, void* y_bf16,
                     int N, int D, int H, int W, int flip, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Encoder stem Conv3d(1,64,3,bias) + train-mode BatchNorm3d coefficients of its output (models/models.py:92-93) in one
+ * call: y as sivae_c1_to_c64, coefficients / running stats as sivae_bn_train_coeffs, the channel sums taken in the
+ * convolution epilogue.  workspaces: sivae_c1_to_c64_workspace_bytes() and sivae_bn_workspace_bytes(64). */
+int sivae_c1_to_c64_bn(const float* x1, const float* w, const float* bias, void* y_bf16,
+                       int N, int D, int H, int W, int flip,
+                       const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float momentum, float eps,
+                       float* mean, float* invstd, float* scale, float* shift,
+                       void* pack_workspace, size_t pack_workspace_bytes,
+                       void* bn_workspace, size_t bn_workspace_bytes, void* stream);
 /* y[v] = act( bias[0] + sum_{t,c} w[c][t] * x[v + delta(t)][c] )     x bf16 NDHWC, y fp32 [N][D][H][W]
  *   act = 0: identity; act = 1: ReLU followed by dropout (mask / Philox(seed) / p as above).        */
 int sivae_cn_to_c1(const void* x_bf16, const float* w, const float* bias, float* y,

@@ -220,6 +220,11 @@ def c1_to_cn(x1, w, bias, flip=False, out=None):
     return y.contiguous().to(ACT_DTYPE)
 
 
+def c1_to_cn_bn(x1, w, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps):
+    y = c1_to_cn(x1, w, bias)
+    return (y,) + tuple(bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps))
+
+
 def cn_to_c1(x, w, bias, flip=False, act=0, mask=None, p=0.0, seed=0):
     w5, k = _w5(w, flip)
     y = F.conv3d(_ncdhw(x), w5.unsqueeze(0), bias, 1, k // 2)[:, 0]             # [N,D,H,W]

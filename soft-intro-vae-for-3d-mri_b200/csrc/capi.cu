@@ -102,6 +102,9 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+int c1_to_c64_bn(const float*, const float*, const float*, void*, int, int, int, int, int, const float*, const float*,
+                 float*, float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, void*, size_t,
+                 cudaStream_t);
 int conv3_igemm_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
                    float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 
@@ -257,6 +260,13 @@ int sivae_mse_persample_fwd(const float* x, const float* y, float* r, int B, lon
 int sivae_mse_persample_bwd(const float* x, const float* y, const float* g, float* dx, float* dy, int B, long long n,
                             void* stream) {
   return mse_persample_bwd(x, y, g, dx, dy, B, n, ST(stream));
+}
+int sivae_c1_to_c64_bn(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
+                       const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                       float eps, float* mean, float* invstd, float* scale, float* shift, void* ws_pack,
+                       size_t ws_pack_bytes, void* ws_bn, size_t ws_bn_bytes, void* stream) {
+  return c1_to_c64_bn(x1, w, bias, y, N, D, H, W, flip, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift,
+                      ws_pack, ws_pack_bytes, ws_bn, ws_bn_bytes, ST(stream));
 }
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream) {

@@ -1596,7 +1596,7 @@ static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + 2 * kTileBytes + 2 * 
 __global__ void __launch_bounds__(288, 1)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
-                    int tiles_w, int tiles_h, int items) {
+                    int tiles_w, int tiles_h, int items, float* __restrict__ stats_partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + 2 * kC1ABytes;
@@ -1731,6 +1731,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     float bia[64];
 #pragma unroll
     for (int e = 0; e < 64; ++e) bia[e] = bias ? __ldg(bias + e) : 0.f;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       int w0, h0, d0; long long n;
@@ -1772,6 +1773,27 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         tma_store_5d(&tmC, tile, 0, w0, h0, d0, (int)n);
         tma_store_commit();
       }
+      if (stats_partial != nullptr) {
+        // fused BatchNorm statistics of the stored (bf16-rounded) values: lane l owns channels 2l, 2l+1 and sums the
+        // 32 rows its warp staged (conflict-free 4-byte reads); rows outside the volume are masked
+        const bool full = (w0 + kHW <= W) && (h0 + kHH <= H);
+        const uint32_t chunk = (uint32_t)lane >> 2, within = ((uint32_t)lane & 3u) * 4u;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int rr = q * 32 + r;
+          if (full || ((w0 + rr % kHW < W) && (h0 + rr / kHW < H))) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + rr * 128 + ((chunk ^ (uint32_t)(rr & 7)) << 4) + within);
+            const float2 f = unpack_bf16x2(u);
+            s1a += f.x; s1b += f.y;
+            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+          }
+        }
+      }
+    }
+    if (stats_partial != nullptr) {
+      float* dst = stats_partial + (size_t)(blockIdx.x * 4 + (warp_id - 5)) * 2 * 64;
+      *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(s1a, s1b);
+      *reinterpret_cast<float2*>(dst + 64 + 2 * lane) = make_float2(s2a, s2b);
     }
     if (issuer) tma_store_wait_read_all();
   }
@@ -1798,8 +1820,8 @@ __global__ void pack_c1_to_c64_weights_kernel(const float* __restrict__ w, int f
 
 size_t c1_to_c64_workspace_bytes() { return (size_t)2 * 64 * 64 * sizeof(__nv_bfloat16); }
 
-int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
-                 void* ws, size_t ws_bytes, cudaStream_t st) {
+static int c1_to_c64_tc_impl(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W,
+                            int flip, void* ws, size_t ws_bytes, float* stats, int* stats_blocks, cudaStream_t st) {
   SIVAE_CHECK(ws && ws_bytes >= c1_to_c64_workspace_bytes(), "c1_to_c64: workspace too small");
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "c1_to_c64: empty tensor");
   pack_c1_to_c64_weights_kernel<<<32, 256, 0, st>>>(w, flip, (__nv_bfloat16*)ws);
@@ -1824,9 +1846,34 @@ int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, in
   }
   const long long cap = num_sms();   // one persistent CTA per SM (117 KB of shared memory, 288 threads x 161 registers)
   const unsigned ctas = (unsigned)(items < cap ? items : cap);
-  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items);
+  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
+  if (stats != nullptr && stats_blocks != nullptr) *stats_blocks = (int)ctas * 4;
   return 0;
+}
+
+int c1_to_c64_tc(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  return c1_to_c64_tc_impl(x1, w, bias, y, N, D, H, W, flip, ws, ws_bytes, nullptr, nullptr, st);
+}
+
+int bn_coeffs_from_partials(const float* partial, int nblocks, long long nvox, int C, const float* gamma,
+                            const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                            float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
+size_t bn_workspace_bytes(int C);
+
+// Encoder stem Conv3d(1,64,3,bias) + the train-mode statistics of the BatchNorm3d behind it (models/models.py:92-93):
+// the channel sums come out of the convolution's epilogue.
+int c1_to_c64_bn(const float* x1, const float* w, const float* bias, void* y, int N, int D, int H, int W, int flip,
+                 const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                 float* mean, float* invstd, float* scale, float* shift, void* ws_pack, size_t ws_pack_bytes,
+                 void* ws_bn, size_t ws_bn_bytes, cudaStream_t st) {
+  SIVAE_CHECK(ws_bn && ws_bn_bytes >= bn_workspace_bytes(64), "c1_to_c64_bn: BN workspace too small");
+  int blocks = 0;
+  int rc = c1_to_c64_tc_impl(x1, w, bias, y, N, D, H, W, flip, ws_pack, ws_pack_bytes, (float*)ws_bn, &blocks, st);
+  if (rc) return rc;
+  return bn_coeffs_from_partials((const float*)ws_bn, blocks, (long long)N * D * H * W, 64, gamma, beta, rm, rv, nbt,
+                                 momentum, eps, mean, invstd, scale, shift, st);
 }
 
 // =================================================================================================

@@ -264,13 +264,34 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
       const unsigned dd = t2 % Do;
       const long long n = t2 / Do;
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (res == nullptr && mask == nullptr && p == 0.f) {
+        // common case (BuildingBlock, models/models.py:18-20): all eight 16-byte loads in flight before the first use
+        // (one dependent load at a time ran this pass at 2.4 TB/s)
+        uint4 raw[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const long long vi = ((n * D + (2 * dd + (q >> 2))) * H + (2 * ho + ((q >> 1) & 1))) * W + (2 * wo + (q & 1));
-        float a[8];
-        act_chunk(y, res, sc, sh, vi * C + chunk * 8, slope, mask, p, seed, a);
+        for (int q = 0; q < 8; ++q) {
+          const long long vi = ((n * D + (2 * dd + (q >> 2))) * H + (2 * ho + ((q >> 1) & 1))) * W + (2 * wo + (q & 1));
+          raw[q] = *reinterpret_cast<const uint4*>(y + vi * C + chunk * 8);
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += a[k];
+        for (int q = 0; q < 8; ++q) {
+          float f[8];
+          unpack8(raw[q], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float t = fmaf(f[k], sc[k], sh[k]);
+            acc[k] += t > 0.f ? t : slope * t;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const long long vi = ((n * D + (2 * dd + (q >> 2))) * H + (2 * ho + ((q >> 1) & 1))) * W + (2 * wo + (q & 1));
+          float a[8];
+          act_chunk(y, res, sc, sh, vi * C + chunk * 8, slope, mask, p, seed, a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += a[k];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] *= 0.125f;

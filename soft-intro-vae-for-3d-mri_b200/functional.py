@@ -183,8 +183,12 @@ class _StemBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1, weight, bias, gamma, beta, bn: BnState, slope: float, p: float):
-        y = K.c1_to_cn(x1, weight, bias)
-        mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
+        if bn.training:
+            y, mean, invstd, scale, shift = K.c1_to_cn_bn(x1, weight, bias, gamma, beta, bn.running_mean, bn.running_var,
+                                                          bn.num_batches_tracked, bn.momentum, bn.eps)
+        else:
+            y = K.c1_to_cn(x1, weight, bias)
+            mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
         mask, seed = (None, 0)
         p_eff = p if bn.training else 0.0
         if p_eff > 0.0:

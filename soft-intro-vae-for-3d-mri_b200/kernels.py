@@ -54,6 +54,8 @@ _SIGNATURES = {
     "sivae_c1_to_cn": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_c1_to_c64_workspace_bytes": (_sz, []),
     "sivae_c1_to_c64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sivae_c1_to_c64_bn": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp,
+                                _vp, _sz, _vp, _sz, _vp]),
     "sivae_cn_to_c1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp]),
     "sivae_wgrad_c1_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_wgrad_c1": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -456,6 +458,31 @@ def c1_to_cn(x1, w, bias, flip: bool = False, out: Optional[torch.Tensor] = None
     _check(_L().sivae_c1_to_cn(_p(x1), _p(w), _p(bias), _p(out), n, d, h, ww, c, t, int(flip), int(acc), _stream(x1)),
            "sivae_c1_to_cn")
     return out
+
+
+def c1_to_cn_bn(x1, w, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float, eps: float):
+    """Stem convolution + train-mode BatchNorm coefficients of its output: -> (y, mean, invstd, scale, shift).
+    Conv3d(1,64,3) runs as one fused call (channel sums from the convolution epilogue); other widths / 1x1 kernels
+    run the convolution and the statistics pass separately."""
+    c, t = w.shape
+    if not (t == 27 and c == 64):
+        y = c1_to_cn(x1, w, bias)
+        return (y,) + tuple(bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps))
+    _req(x1, torch.float32, "x1")
+    _req(w, torch.float32, "w")
+    n, d, h, ww = x1.shape
+    lib = _L()
+    y = torch.empty(n, d, h, ww, c, dtype=torch.bfloat16, device=x1.device)
+    ws = _workspace(x1.device, lib.sivae_c1_to_c64_workspace_bytes(), "c1c64")
+    wsb = _workspace(x1.device, lib.sivae_bn_workspace_bytes(c), "bn")
+    coef = torch.empty(4, c, dtype=torch.float32, device=x1.device)
+    if num_batches_tracked is not None:
+        _req(num_batches_tracked, torch.int64, "num_batches_tracked")
+    _check(lib.sivae_c1_to_c64_bn(_p(x1), _p(w), _p(bias), _p(y), n, d, h, ww, 0, _p(gamma), _p(beta), _p(running_mean),
+                                  _p(running_var), _p(num_batches_tracked), momentum, eps, _p(coef[0]), _p(coef[1]),
+                                  _p(coef[2]), _p(coef[3]), _p(ws), ws.numel(), _p(wsb), wsb.numel(), _stream(x1)),
+           "sivae_c1_to_c64_bn")
+    return y, coef[0], coef[1], coef[2], coef[3]
 
 
 def cn_to_c1(x, w, bias, flip: bool = False, act: int = 0, mask=None, p: float = 0.0, seed: int = 0):

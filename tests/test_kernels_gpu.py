@@ -143,6 +143,28 @@ def test_c1_to_cn(C, T, flip):
     assert_bf16_close(acc, ref2, "c1_to_cn accumulate", rel=2 ** -6)
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 6, 9), (1, 16, 16, 32), (3, 7, 20, 40), (8, 20, 24, 16)])
+@pytest.mark.parametrize("C,T", [(64, 27), (128, 27), (256, 1)])
+def test_c1_to_cn_bn_fused_stats(shape, C, T):
+    """Stem convolution + BatchNorm coefficients in one call: Conv3d(1,64,3) takes the channel sums in the convolution
+    epilogue (ragged tiles masked), other widths run the two passes; both must match conv followed by the stats pass."""
+    x1 = torch.randn(*shape, device=DEV)
+    w = torch.randn(C, T, device=DEV) * 0.3
+    b = torch.randn(C, device=DEV)
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    rm1, rv1, n1 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+    rm2, rv2, n2 = rm1.clone(), rv1.clone(), n1.clone()
+    y, *coef = K.c1_to_cn_bn(x1, w, b, gamma, beta, rm1, rv1, n1, 0.1, 1e-5)
+    y_ref = K.c1_to_cn(x1, w, b)
+    ref = K.bn_train_coeffs(y_ref, gamma, beta, rm2, rv2, n2, 0.1, 1e-5)
+    assert torch.equal(y, y_ref)
+    for a, r, name in zip(coef, ref, ("mean", "invstd", "scale", "shift")):
+        assert_f32_close(a, r, name, 3e-5)
+    assert_f32_close(rm1, rm2, "running_mean", 3e-5)
+    assert_f32_close(rv1, rv2, "running_var", 3e-5)
+    assert int(n1) == 1
+
+
 @pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (128, 1), (256, 1)])
 @pytest.mark.parametrize("flip,act", [(False, 0), (True, 0), (False, 1)])
 def test_cn_to_c1(C, T, flip, act):
