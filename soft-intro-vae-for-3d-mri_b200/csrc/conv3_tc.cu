@@ -203,7 +203,7 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
       tmem_ld_wait();
-      uint8_t* tile = out_stage + (j >> 1) * kTileBytes + row * 128;
+      const uint32_t tile = smem_u32(out_stage + (j >> 1) * kTileBytes + row * 128);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 pk;
@@ -212,7 +212,7 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
         pk.z = pack_bf16x2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
         pk.w = pack_bf16x2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
         const int chunk = (j & 1) * 4 + c;
-        *reinterpret_cast<uint4*>(tile + ((chunk ^ (row & 7)) << 4)) = pk;
+        sts128(tile + ((uint32_t)(chunk ^ (row & 7)) << 4), pk);
       }
     }
     fence_proxy_async_smem();
@@ -621,7 +621,7 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
-        uint8_t* dst = tile + row * 128;
+        const uint32_t dst = smem_u32(tile) + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 pk;
@@ -629,12 +629,12 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           pk.y = pack_bf16x2(__uint_as_float(v0[c * 8 + 2]), __uint_as_float(v0[c * 8 + 3]));
           pk.z = pack_bf16x2(__uint_as_float(v0[c * 8 + 4]), __uint_as_float(v0[c * 8 + 5]));
           pk.w = pack_bf16x2(__uint_as_float(v0[c * 8 + 6]), __uint_as_float(v0[c * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = pk;
+          sts128(dst + ((uint32_t)(c ^ (row & 7)) << 4), pk);
           pk.x = pack_bf16x2(__uint_as_float(v1[c * 8 + 0]), __uint_as_float(v1[c * 8 + 1]));
           pk.y = pack_bf16x2(__uint_as_float(v1[c * 8 + 2]), __uint_as_float(v1[c * 8 + 3]));
           pk.z = pack_bf16x2(__uint_as_float(v1[c * 8 + 4]), __uint_as_float(v1[c * 8 + 5]));
           pk.w = pack_bf16x2(__uint_as_float(v1[c * 8 + 6]), __uint_as_float(v1[c * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + (((4 + c) ^ (row & 7)) << 4)) = pk;
+          sts128(dst + ((uint32_t)((4 + c) ^ (row & 7)) << 4), pk);
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -642,21 +642,8 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (d0 + i < g.D) tma_store_5d(&tmC, tile, 0, w0, h0, d0 + i, n);
           tma_store_commit();   // a (possibly empty) group per tile keeps the wait_group arithmetic uniform
         }
-        if (stats_partial != nullptr && d0 + i < g.D) {
-          // lane l owns channels 2l, 2l+1: one conflict-free 4-byte read per row of this warp's 32 staged rows
-          const bool full = (w0 + kKwW <= g.W) && (h0 + kKwH <= g.H);
-          const uint32_t chunk = (uint32_t)lane >> 2, within = ((uint32_t)lane & 3u) * 4u;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int rr = q * 32 + r;
-            if (full || ((w0 + (rr & 7) < g.W) && (h0 + (rr >> 3) < g.H))) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + rr * 128 + ((chunk ^ (uint32_t)(rr & 7)) << 4) + within);
-              const float2 f = unpack_bf16x2(u);
-              s1a += f.x; s1b += f.y;
-              s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
-            }
-          }
-        }
+        if (stats_partial != nullptr && d0 + i < g.D)
+          tile_channel_sums<kKwW>(smem_u32(tile), q, lane, g.W - w0, g.H - h0, s1a, s1b, s2a, s2b);
       }
     }
     if (stats_partial != nullptr) {
@@ -1498,6 +1485,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int ow = t128 % kHW, oh = t128 / kHW;
     const float bias = ep.bias ? ep.bias[0] : 0.f;
     const float inv_keep = 1.f / (1.f - ep.p);
+    const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: STS / LDS below
     uint32_t sl = 0;
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
       int w0, h0, d_lo, d_hi, n;
@@ -1506,7 +1494,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool inside = (w < g.W && h < g.H);
       const int planes = d_hi - d_lo + 2;
       for (int zi = 0; zi < planes; ++zi) {
-        float* Pz = P + (zi & (kSPSlots - 1)) * kSPSlotFloats;
+        const uint32_t Pz = p_addr + (uint32_t)(zi & (kSPSlots - 1)) * (kSPSlotFloats * 4u);
 #pragma unroll 1
         for (int m = 0; m < 2; ++m, ++sl) {
           const uint32_t slot = sl % kHSlots;
@@ -1523,9 +1511,9 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&slot_empty[slot]);
             if (prow < kSPRows) {
-              float* dst = Pz + prow * kPStride;
+              const uint32_t dst = Pz + (uint32_t)(prow * kPStride) * 4u;
 #pragma unroll
-              for (int t = 0; t < 27; ++t) dst[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+              for (int t = 0; t < 27; ++t) sts_f32(dst + t * 4u, __uint_as_float(v0[t]) + __uint_as_float(v1[t]));
             }
           } else {
             tc_fence_before();
@@ -1539,11 +1527,11 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           float acc = 0.f;
 #pragma unroll
           for (int kd = 0; kd < 3; ++kd) {
-            const float* Pk = P + ((zi - 2 + kd) & (kSPSlots - 1)) * kSPSlotFloats;
+            const uint32_t Pk = p_addr + (uint32_t)((zi - 2 + kd) & (kSPSlots - 1)) * (kSPSlotFloats * 4u);
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
               const int row = (oh + t9 / 3) * kHBW + ow + t9 % 3;
-              acc += Pk[row * kPStride + kd * 9 + t9];
+              acc += lds_f32(Pk + (uint32_t)(row * kPStride + kd * 9 + t9) * 4u);
             }
           }
           const int d = d_lo + zi - 2;
@@ -1694,31 +1682,32 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     uint32_t it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t s = it & 1, ph = (it >> 1) & 1u;
-      float* xh = xs + s * kC1Halo;
+      const uint32_t xh = smem_u32(xs + s * kC1Halo);       // shared-window address: LDS / STS below
 #pragma unroll
       for (int j = 0; j < kPer; ++j)
-        if (row + j * 128 < kHRows) xh[row + j * 128] = pre[j];
+        if (row + j * 128 < kHRows) sts_f32(xh + (uint32_t)(row + j * 128) * 4u, pre[j]);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (item + (int)gridDim.x < items) fetch(item + gridDim.x);     // next item's halo: in flight while this row is built
       uint32_t hi[16], lo[16];                              // 32 bf16 each: taps 0..26, then zeros
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float a = 0.f, b = 0.f;
-        if (2 * j < 27) a = xh[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
-        if (2 * j + 1 < 27) b = xh[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
+        if (2 * j < 27) a = lds_f32(xh + (uint32_t)((((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3) * 4u);
+        if (2 * j + 1 < 27)
+          b = lds_f32(xh + (uint32_t)((((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3) * 4u);
         hi[j] = pack_bf16x2(a, b);                          // one packed conversion; bf16 -> fp32 is a 16-bit shift
         lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xffff0000u));
       }
       mbar_wait(&a_empty[s], ph ^ 1u);                      // the MMAs that read this A buffer two items ago are done
-      uint8_t* r0 = smem + s * kC1ABytes + row * 128;       // K block 0: [x_hi | x_lo]
-      uint8_t* r1 = r0 + kTileBytes;                        // K block 1: [x_hi | (never read)]
+      const uint32_t r0 = smem_u32(smem + s * kC1ABytes + row * 128);   // K block 0: [x_hi | x_lo]
+      const uint32_t r1 = r0 + kTileBytes;                              // K block 1: [x_hi | (never read)]
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
         const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-        *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = vh;
-        *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = vl;
-        *reinterpret_cast<uint4*>(r1 + ((c ^ (row & 7)) << 4)) = vh;
+        sts128(r0 + ((uint32_t)(c ^ (row & 7)) << 4), vh);
+        sts128(r0 + ((uint32_t)((4 + c) ^ (row & 7)) << 4), vl);
+        sts128(r1 + ((uint32_t)(c ^ (row & 7)) << 4), vh);
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
@@ -1751,6 +1740,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
       // the store issued two items ago read this staging tile: it must have drained before it is overwritten
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       asm volatile("bar.sync 2, 128;" ::: "memory");
+      const uint32_t tile_row = smem_u32(tile) + (uint32_t)row * 128u;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float f[8], g8[8];
@@ -1762,10 +1752,10 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
         pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = pk;
+        sts128(tile_row + ((uint32_t)(c ^ (row & 7)) << 4), pk);
         pk.x = pack_bf16x2(g8[0], g8[1]); pk.y = pack_bf16x2(g8[2], g8[3]);
         pk.z = pack_bf16x2(g8[4], g8[5]); pk.w = pack_bf16x2(g8[6], g8[7]);
-        *reinterpret_cast<uint4*>(tile + row * 128 + (((4 + c) ^ (row & 7)) << 4)) = pk;
+        sts128(tile_row + ((uint32_t)((4 + c) ^ (row & 7)) << 4), pk);
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -1773,22 +1763,8 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         tma_store_5d(&tmC, tile, 0, w0, h0, d0, (int)n);
         tma_store_commit();
       }
-      if (stats_partial != nullptr) {
-        // fused BatchNorm statistics of the stored (bf16-rounded) values: lane l owns channels 2l, 2l+1 and sums the
-        // 32 rows its warp staged (conflict-free 4-byte reads); rows outside the volume are masked
-        const bool full = (w0 + kHW <= W) && (h0 + kHH <= H);
-        const uint32_t chunk = (uint32_t)lane >> 2, within = ((uint32_t)lane & 3u) * 4u;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int rr = q * 32 + r;
-          if (full || ((w0 + rr % kHW < W) && (h0 + rr / kHW < H))) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + rr * 128 + ((chunk ^ (uint32_t)(rr & 7)) << 4) + within);
-            const float2 f = unpack_bf16x2(u);
-            s1a += f.x; s1b += f.y;
-            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
-          }
-        }
-      }
+      if (stats_partial != nullptr)   // fused BatchNorm statistics of the stored (bf16-rounded) values
+        tile_channel_sums<kHW>(smem_u32(tile), q, lane, W - w0, H - h0, s1a, s1b, s2a, s2b);
     }
     if (stats_partial != nullptr) {
       float* dst = stats_partial + (size_t)(blockIdx.x * 4 + (warp_id - 5)) * 2 * 64;
@@ -1965,6 +1941,7 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
     const int row = threadIdx.x;                          // voxel row of the tile
     const int ow = row % kHW, oh = row / kHW;
     float s1 = 0.f;
+    const uint32_t xs_addr = smem_u32(xs);                // shared-window address of the halo: LDS / STS below
     constexpr int kPer = (kHRows + 127) / 128;            // halo floats per thread (5)
     float pre[kPer];
     // the fp32 halo of the NEXT tile is fetched into registers while the current A tile is built, so the global-load
@@ -1989,26 +1966,27 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
       asm volatile("bar.sync 1, 128;" ::: "memory");      // previous iteration's halo reads are done
 #pragma unroll
       for (int j = 0; j < kPer; ++j)
-        if (row + j * 128 < kHRows) xs[row + j * 128] = pre[j];
+        if (row + j * 128 < kHRows) sts_f32(xs_addr + (uint32_t)(row + j * 128) * 4u, pre[j]);
       if (it + 1 < my_tiles) fetch(first + (it + 1) * step);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float a = 0.f, b = 0.f;
-        if (2 * j < 27) a = xs[(((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3];
-        if (2 * j + 1 < 27) b = xs[(((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3];
+        if (2 * j < 27) a = lds_f32(xs_addr + (uint32_t)((((2 * j) / 9) * kHBH + oh + ((2 * j) / 3) % 3) * kHBW + ow + (2 * j) % 3) * 4u);
+        if (2 * j + 1 < 27)
+          b = lds_f32(xs_addr + (uint32_t)((((2 * j + 1) / 9) * kHBH + oh + ((2 * j + 1) / 3) % 3) * kHBW + ow + (2 * j + 1) % 3) * 4u);
         if (2 * j + 1 == 27) b = 1.0f;                     // row 27 of D accumulates sum_v xc[v][c]
         hi[j] = pack_bf16x2(a, b);
         lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xffff0000u));
       }
-      s1 += xs[(1 * kHBH + oh + 1) * kHBW + ow + 1];       // centre tap; zero outside the volume
+      s1 += lds_f32(xs_addr + (uint32_t)((1 * kHBH + oh + 1) * kHBW + ow + 1) * 4u);   // centre tap; zero outside the volume
       mbar_wait(&empty[s], (uint32_t)((it / kWg1Stages) & 1) ^ 1u);
-      uint8_t* r0 = smem_a + s * A_STAGE + row * 128;
+      const uint32_t r0 = smem_u32(smem_a + s * A_STAGE + row * 128);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<uint4*>(r0 + ((c ^ (row & 7)) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-        *reinterpret_cast<uint4*>(r0 + (((4 + c) ^ (row & 7)) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        sts128(r0 + ((uint32_t)(c ^ (row & 7)) << 4), make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]));
+        sts128(r0 + ((uint32_t)((4 + c) ^ (row & 7)) << 4), make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);

@@ -88,6 +88,30 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- explicit shared-memory accesses ---------------------------------------------------------------
+// The kernels carve their dynamic shared memory from a 1024-byte-aligned pointer computed with integer arithmetic,
+// which makes the compiler lose the address space and emit generic LD.E / ST.E.  Hot loops therefore use 32-bit
+// shared-window addresses (smem_u32) and these wrappers (LDS / STS).
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -247,6 +271,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+
+// BatchNorm statistics of one staged output tile (128 rows x 64 bf16 channels, SWIZZLE_128B): the calling warp sums
+// rows [32*q, 32*q + 32) for the channel pair (2*lane, 2*lane + 1) -- conflict-free 4-byte LDS, all loads of a batch in
+// flight before use.  rows_w = patch width (rows are (h, w) with w fastest); rows outside [0,wlim) x [0,hlim) skipped.
+template <int ROWS_W>
+__device__ __forceinline__ void tile_channel_sums(uint32_t tile_addr, int q, int lane, int wlim, int hlim, float& s1a,
+                                                  float& s1b, float& s2a, float& s2b) {
+  const uint32_t chunk = (uint32_t)lane >> 2, within = ((uint32_t)lane & 3u) * 4u;
+  const uint32_t base = tile_addr + (uint32_t)q * 32u * 128u + within;
+  const bool full = (wlim >= ROWS_W) && (hlim >= 128 / ROWS_W);
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 16) {
+    uint32_t u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = lds32(base + (uint32_t)(r0 + r) * 128u + ((chunk ^ (uint32_t)((r0 + r) & 7)) << 4));
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int rr = r0 + r;                                   // row within the warp's quarter (32*q is a multiple of ROWS_W)
+      const float m = (full || (rr % ROWS_W < wlim && (q * 32 + rr) / ROWS_W < hlim)) ? 1.f : 0.f;
+      const float2 f = unpack_bf16x2(u[r]);
+      const float fx = f.x * m, fy = f.y * m;
+      s1a += fx; s1b += fy;
+      s2a = fmaf(fx, fx, s2a); s2b = fmaf(fy, fy, s2b);
+    }
+  }
 }
 
 // Philox4x32-10 (Salmon et al.): counter-based, so forward and backward regenerate the same dropout mask.
