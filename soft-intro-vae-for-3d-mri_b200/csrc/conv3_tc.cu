@@ -1216,7 +1216,11 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   fill_geom(g, N, D, H, W, Cin, kTapsPlain);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
   SIVAE_CHECK(tiles < (1ll << 31), "conv3_igemm: too many tiles");
-  const int block_n = (Cout % 128 == 0) ? 128 : 64;
+  // N = 256 tiles (opt-in, SIVAE_N256=1) for the 256-channel layers at the latent resolution (80 voxel tiles): one wave of
+  // 80 CTAs instead of 160 CTAs on 148 SMs.  Measured SLOWER (71 vs 64 us per conv + statistics): the doubly loaded SMs
+  // of the N = 128 grid overlap their two CTAs well, while 68 idle SMs cost more than the saved A re-reads.
+  const int block_n = (Cout % 256 == 0 && tiles <= num_sms() && getenv("SIVAE_N256") != nullptr) ? 256
+                      : (Cout % 128 == 0) ? 128 : 64;
   TmapPack tmA, tmC;
   CUtensorMap tmB;
   if (make_act_tmap(&tmA.m[0], x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
@@ -1224,6 +1228,7 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   for (int i = 1; i < 8; ++i) { tmA.m[i] = tmA.m[0]; tmC.m[i] = tmC.m[0]; }
   if (make_weight_tmap(&tmB, wpack, 27, Cout, Cin, block_n)) return -1;
   const ToOneEpilogue ep{};
+  if (block_n == 256) return launch_igemm<256, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 256, ep, st);
   if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
   return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
 }
@@ -1579,9 +1584,9 @@ __global__ void pack_to1_halo_weights_kernel(const float* __restrict__ w, int fl
 static constexpr int kC1ABytes = 2 * kTileBytes;          // two 64-wide K blocks of the 128-row A tile
 static constexpr int kC1BBytes = 2 * 64 * 128;            // [2 K blocks][64 channels][64]
 static constexpr int kC1Halo = (kHRows + 3) & ~3;         // floats per staged halo
-static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + 2 * kTileBytes + 2 * kC1Halo * 4 + 1024 + 256;
+static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + kTileBytes + 2 * kC1Halo * 4 + 64 * 4 + 1024 + 256;
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(288, 2)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
                     int tiles_w, int tiles_h, int items, float* __restrict__ stats_partial) {
@@ -1589,8 +1594,9 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + 2 * kC1ABytes;
   uint8_t* smem_o = smem_b + kC1BBytes;
-  float* xs = reinterpret_cast<float*>(smem_o + 2 * kTileBytes);   // [2][kC1Halo]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(xs + 2 * kC1Halo);
+  float* xs = reinterpret_cast<float*>(smem_o + kTileBytes);       // [2][kC1Halo]
+  float* bias_s = xs + 2 * kC1Halo;                                // [64]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint64_t* a_empty = a_full + 2;
   uint64_t* acc_full = a_empty + 2;
   uint64_t* acc_empty = acc_full + 2;
@@ -1615,6 +1621,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     __syncwarp();
     tmem_alloc(tmem_ptr_smem, 128);
   }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1717,16 +1724,14 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     const int q = warp_id & 3;
     const int row = q * 32 + lane;
     const bool issuer = (warp_id == 5 && lane == 0);
-    float bia[64];
-#pragma unroll
-    for (int e = 0; e < 64; ++e) bia[e] = bias ? __ldg(bias + e) : 0.f;
+    const uint32_t bias_addr = smem_u32(bias_s);
     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       int w0, h0, d0; long long n;
       decode(item, w0, h0, d0, n);
       const uint32_t s = it & 1;
-      uint8_t* tile = smem_o + s * kTileBytes;
+      uint8_t* tile = smem_o;                               // single staging tile (two CTAs share an SM)
       mbar_wait(&acc_full[s], (it >> 1) & 1u);
       tc_fence_after();
       uint32_t v0[32], v1[32];
@@ -1737,8 +1742,8 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[s]);
-      // the store issued two items ago read this staging tile: it must have drained before it is overwritten
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      // the previous item's store must have read the staging tile before it is overwritten
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 2, 128;" ::: "memory");
       const uint32_t tile_row = smem_u32(tile) + (uint32_t)row * 128u;
 #pragma unroll
@@ -1746,8 +1751,8 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
         float f[8], g8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(v0[c * 8 + e]) + bia[c * 8 + e];
-          g8[e] = __uint_as_float(v1[c * 8 + e]) + bia[32 + c * 8 + e];
+          f[e] = __uint_as_float(v0[c * 8 + e]) + lds_f32(bias_addr + (uint32_t)(c * 8 + e) * 4u);          // broadcast reads
+          g8[e] = __uint_as_float(v1[c * 8 + e]) + lds_f32(bias_addr + (uint32_t)(32 + c * 8 + e) * 4u);
         }
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
@@ -1820,7 +1825,9 @@ static int c1_to_c64_tc_impl(const float* x1, const float* w, const float* bias,
       return -1;
     attr_set = true;
   }
-  const long long cap = num_sms();   // one persistent CTA per SM (117 KB of shared memory, 288 threads x 161 registers)
+  // two persistent CTAs per SM (102 KB of shared memory, 288 threads x <= 112 registers, 128 TMEM columns each): every
+  // role is a single warp per scheduler, so a second CTA is what hides the LDS / ALU latencies of the builders
+  const long long cap = 2ll * num_sms();
   const unsigned ctas = (unsigned)(items < cap ? items : cap);
   c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
