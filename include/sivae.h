@@ -262,6 +262,17 @@ typedef struct sivae_adam_tensor {
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Latent retrieval (SURVEY.md section 8f NEXT-4): top-k similarity search over encoder latents, the content-based
+ * image retrieval the reference states as its goal (README.md:4-11; latent extraction loop: logistic1.ipynb cell 7).
+ * q [nq][dim], db [nd][dim] fp32 row-major; metric 0 = cosine similarity, 1 = negative squared L2 distance (larger is
+ * more similar for both); out_scores / out_index [nq][k], best first, ties broken by the lower database index;
+ * 1 <= k <= 32.  workspace: sivae_similarity_workspace_bytes(nq, nd).
+ * ---------------------------------------------------------------------------------------------- */
+size_t sivae_similarity_workspace_bytes(int nq, int nd);
+int sivae_similarity_topk(const float* q, const float* db, int nq, int nd, int dim, int metric, int k,
+                          float* out_scores, int* out_index, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,6 +286,16 @@ def to_ncdhw_f32(x):
     return _ncdhw(x).contiguous()
 
 
+def similarity_topk(queries, database, k, metric="cosine"):
+    """Top-k similarity (cosine, or negative squared L2), best first, ties -> lower database index."""
+    q, d = queries.double(), database.double()
+    dot = q @ d.t()
+    qn, dn = (q * q).sum(1, keepdim=True), (d * d).sum(1, keepdim=True).t()
+    s = dot / (qn * dn).clamp_min(1e-30).sqrt() if metric == "cosine" else -(qn + dn - 2 * dot)
+    order = torch.argsort(s, dim=1, descending=True, stable=True)[:, :k]
+    return torch.gather(s, 1, order).float(), order.to(torch.int32)
+
+
 def adam_step(tensors, lr, beta1, beta2, eps, step):
     """torch/optim/adam.py _single_tensor_adam (no weight decay / amsgrad / maximize), which is what the reference's
     torch.optim.Adam(lr=2e-4) runs (utils/my_trainer.py:183-184,:288,:324); refreshes the given bf16 packs."""

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "sivae_mse_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _sz, _vp]),
     "sivae_mse_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "sivae_adam_step": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _vp]),
+    "sivae_similarity_workspace_bytes": (_sz, [_i, _i]),
+    "sivae_similarity_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sivae_ncdhw_f32_to_ndhwc_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "sivae_ndhwc_bf16_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
 }
@@ -432,6 +434,28 @@ def adam_step(tensors, lr: torch.Tensor, beta1: float, beta2: float, eps: float,
             arr[i].cout, arr[i].cin = p.shape[0], p.shape[1]
     _check(_L().sivae_adam_step(ctypes.cast(arr, ctypes.c_void_p), len(tensors), _p(lr), beta1, beta2, eps, _p(step),
                                 _stream(lr)), "sivae_adam_step")
+
+
+# ----------------------------------------------------------------------------------------------
+# latent retrieval (SURVEY section 8f NEXT-4)
+# ----------------------------------------------------------------------------------------------
+def similarity_topk(queries: torch.Tensor, database: torch.Tensor, k: int, metric: str = "cosine"):
+    """-> (scores [nq,k] fp32, index [nq,k] int32), best first.  metric "cosine" or "l2" (score = -squared distance)."""
+    _req(queries, torch.float32, "queries")
+    _req(database, torch.float32, "database")
+    nq, dim = queries.shape
+    nd, dim2 = database.shape
+    assert dim == dim2
+    if metric not in ("cosine", "l2"):
+        raise ValueError("metric must be 'cosine' or 'l2'")
+    lib = _L()
+    ws = _workspace(queries.device, lib.sivae_similarity_workspace_bytes(nq, nd), "sim")
+    scores = torch.empty(nq, k, dtype=torch.float32, device=queries.device)
+    index = torch.empty(nq, k, dtype=torch.int32, device=queries.device)
+    _check(lib.sivae_similarity_topk(_p(queries), _p(database), nq, nd, dim, 0 if metric == "cosine" else 1, k,
+                                     _p(scores), _p(index), _p(ws), ws.numel(), _stream(queries)),
+           "sivae_similarity_topk")
+    return scores, index
 
 
 # ----------------------------------------------------------------------------------------------
