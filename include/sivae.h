@@ -96,6 +96,15 @@ int sivae_conv3_wgrad(const void* x_bf16, const void* dy_bf16, float* dw,
 int sivae_pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup_bf16, void* wupT_bf16, void* stream);
 int sivae_upconv3_fprop(const void* x_lo_bf16, const void* wup_bf16, void* y_hi_bf16,
                         int N, int D, int H, int W, int Cin, int Cout, void* stream);
+/* fprop + train-mode BatchNorm3d coefficients of the high-res output (models/models.py:58-60), as sivae_conv3_igemm_bn:
+ * statistics from the convolution epilogue when the persistent kernel takes the shape.  workspace:
+ * sivae_bn_workspace_bytes(Cout). */
+int sivae_upconv3_fprop_bn(const void* x_lo_bf16, const void* wup_bf16, void* y_hi_bf16,
+                           int N, int D, int H, int W, int Cin, int Cout,
+                           const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           long long* num_batches_tracked, float momentum, float eps,
+                           float* mean, float* invstd, float* scale, float* shift,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int sivae_upconv3_dgrad(const void* dy_hi_bf16, const void* wupT_bf16, void* dx_lo_bf16,
                         int N, int D, int H, int W, int Cin, int Cout, void* stream);
 size_t sivae_upconv3_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);

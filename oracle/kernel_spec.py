@@ -114,6 +114,11 @@ def upconv3_fprop(x_lo, wup):
     return _upconv3_fprop_f32(x_lo, wup).to(x_lo.dtype)
 
 
+def upconv3_fprop_bn(x_lo, wup, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps):
+    y = upconv3_fprop(x_lo, wup)
+    return (y,) + tuple(bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps))
+
+
 def upconv3_dgrad(dy_hi, wupT):
     n, d2, h2, w2, co = dy_hi.shape
     ci = wupT.shape[1]

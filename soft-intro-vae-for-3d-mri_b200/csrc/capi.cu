@@ -102,6 +102,8 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+int upconv3_fprop_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
+                     float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 size_t similarity_workspace_bytes(int, int);
 int similarity_topk(const float*, const float*, int, int, int, int, int, float*, int*, void*, size_t, cudaStream_t);
 int c1_to_c64_bn(const float*, const float*, const float*, void*, int, int, int, int, int, const float*, const float*,
@@ -274,6 +276,13 @@ size_t sivae_similarity_workspace_bytes(int nq, int nd) { return similarity_work
 int sivae_similarity_topk(const float* q, const float* db, int nq, int nd, int dim, int metric, int k, float* out_scores,
                           int* out_index, void* ws, size_t ws_bytes, void* stream) {
   return similarity_topk(q, db, nq, nd, dim, metric, k, out_scores, out_index, ws, ws_bytes, ST(stream));
+}
+int sivae_upconv3_fprop_bn(const void* x, const void* wup, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                           const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                           float eps, float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                           void* stream) {
+  return upconv3_fprop_bn(x, wup, y, N, D, H, W, Cin, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale,
+                          shift, ws, ws_bytes, ST(stream));
 }
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream) {

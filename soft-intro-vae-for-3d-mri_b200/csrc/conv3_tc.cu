@@ -660,6 +660,255 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // =================================================================================================
+// Upsample(2) + Conv3d fprop, Cout = 64: persistent kernel with shared-tile tap stacking.
+//
+// In the folded form (see kTapsUpFprop) output parity (pd,ph,pw) at low-res voxel v is an 8-tap convolution over the
+// low-res inputs v + (ad-1+pd, ah-1+ph, aw-1+pw).  The tap-by-tap kernel treats the 8 parities x 8 taps as 64 separate
+// (A tile, weight slab) pairs.  But a low-res tile shifted by (oh, ow) in the plane is shared by every (ph,ah) / (pw,aw)
+// combination with ah-1+ph = oh and aw-1+pw = ow -- 4 units for (0,0), 2 for the edge shifts, 1 for the corners -- and
+// all of them land on the same voxel rows = the same TMEM lanes.  A work item is therefore
+//     8(w) x 16(h) low-res patch  x  one low-res plane d  x  one depth parity pd
+// with the four (ph,pw) parity accumulators side by side in TMEM (column block pw*2 + ph); per depth tap ad it walks the
+// 9 in-plane shifts of input plane d + ad - 1 + pd and issues
+//     (0,0): two UMMAs N = 128 (all four parities)     (0,-1) / (0,+1): ONE UMMA N = 128 (the two ph of one pw)
+//     (-1,0) / (+1,0): two UMMAs N = 64 (column blocks not adjacent)       corners: one UMMA N = 64
+// = 12 A reads instead of 16 per input plane, and 18 TMA tile loads per item instead of 32.  (The (0,0) tile is issued as
+// two N = 128 steps: a 32 KB weight slot would leave too few ring slots to hide the L2 latency of the weight stream.)
+// The (0,0) steps of ad = 0 come first and overwrite all four accumulators (accumulate = 0).  The weight slabs of a step
+// are TMA-loaded back to back into one 16 KB ring slot so the stacked operand is contiguous.
+// Persistent, one CTA per SM: A ring 5 x 16 KB, B ring 7 x 16 KB, two TMEM stages x 256 columns, two staging tiles;
+// the four parity tiles are stored through the strided parity-sub-lattice tensor maps; BatchNorm statistics fused as in
+// conv3_kd3_kernel.  7 warps: A producer, MMA issuer, B producer, 4 epilogue warps.
+// =================================================================================================
+struct UpGeom {
+  int N, D, H, W;                  // low-res lattice
+  int tiles_w, tiles_h;
+  int cin_blocks;
+  long long items;                 // tiles_w * tiles_h * D * 2 * N
+};
+static constexpr int kUpAStages = 5, kUpBStages = 7;
+static constexpr int kUpBSlot = 2 * 64 * 128;       // up to two stacked 64 x 64 slabs
+static constexpr int kUpSmem = kUpAStages * kTileBytes + kUpBStages * kUpBSlot + 2 * kTileBytes + 1024 + 256;
+static constexpr int kUpSteps = 10;
+
+// schedule of one depth tap: in-plane shift (oh, ow), its 1..2 units (ph, pw) (accumulator column block = pw * 2 + ph),
+// stacked (one UMMA N = 128) or separate (two UMMAs N = 64), and whether the step loads a new A tile / is the last
+// user of the current one.  The (0,0) tile feeds all four parities: two N = 128 steps on the same A tile (a 32 KB weight
+// slot would leave too few slots to hide the L2 latency of the weight stream).
+struct UpStep { int8_t oh, ow, n, stacked, new_a, rel_a; int8_t ph[2], pw[2]; };
+__device__ __constant__ UpStep kUpStepTab[kUpSteps] = {
+    {0, 0, 2, 1, 1, 0, {0, 1}, {0, 0}},
+    {0, 0, 2, 1, 0, 1, {0, 1}, {1, 1}},
+    {0, -1, 2, 1, 1, 1, {0, 1}, {0, 0}},
+    {0, 1, 2, 1, 1, 1, {0, 1}, {1, 1}},
+    {-1, 0, 2, 0, 1, 1, {0, 0}, {0, 1}},
+    {1, 0, 2, 0, 1, 1, {1, 1}, {0, 1}},
+    {-1, -1, 1, 1, 1, 1, {0, 0}, {0, 0}},
+    {-1, 1, 1, 1, 1, 1, {0, 0}, {1, 0}},
+    {1, -1, 1, 1, 1, 1, {1, 0}, {0, 0}},
+    {1, 1, 1, 1, 1, 1, {1, 0}, {1, 0}},
+};
+
+__global__ void __launch_bounds__(224, 1)
+upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ TmapPack tmC, const UpGeom g, float* __restrict__ stats_partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + kUpAStages * kTileBytes;
+  uint8_t* smem_o = smem_b + kUpBStages * kUpBSlot;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_o + 2 * kTileBytes);
+  uint64_t* a_empty = a_full + kUpAStages;
+  uint64_t* b_full = a_empty + kUpAStages;
+  uint64_t* b_empty = b_full + kUpBStages;
+  uint64_t* acc_full = b_empty + kUpBStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int p = 0; p < 8; ++p) prefetch_tmap(&tmC.m[p]);
+    for (int s = 0; s < kUpAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kUpBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](long long item, int& w0, int& h0, int& d, int& pd, int& n) {
+    pd = (int)(item & 1); item >>= 1;
+    const int tw = (int)(item % g.tiles_w); item /= g.tiles_w;
+    const int th = (int)(item % g.tiles_h); item /= g.tiles_h;
+    d = (int)(item % g.D);
+    n = (int)(item / g.D);
+    w0 = tw * kKwW; h0 = th * kKwH;
+  };
+
+  if (warp_id == 0) {
+    // ===== A producer: per depth tap the 9 shifted low-res tiles (x cin_blocks K blocks) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        int w0, h0, d, pd, n;
+        decode(item, w0, h0, d, pd, n);
+        for (int cb = 0; cb < g.cin_blocks; ++cb)      // K block outermost: every (tile, K block) is one A stage
+          for (int ad = 0; ad < 2; ++ad)
+            for (int t = 0; t < kUpSteps; ++t) {
+              const UpStep sh = kUpStepTab[t];
+              if (!sh.new_a) continue;
+              const int s = it % kUpAStages;
+              mbar_wait(&a_empty[s], ((it / kUpAStages) & 1u) ^ 1u);
+              mbar_expect_tx(&a_full[s], kTileBytes);
+              tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], cb * 64, w0 + sh.ow, h0 + sh.oh, d + ad - 1 + pd, n);
+              ++it;
+            }
+      }
+    }
+  } else if (warp_id == 2) {
+    // ===== B producer: the 1..4 weight slabs of a shifted tile, stacked in unit order =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int pd = (int)(item & 1);
+        for (int cb = 0; cb < g.cin_blocks; ++cb)
+          for (int ad = 0; ad < 2; ++ad)
+            for (int t = 0; t < kUpSteps; ++t, ++it) {
+              const UpStep sh = kUpStepTab[t];
+              const int s = it % kUpBStages;
+              mbar_wait(&b_empty[s], ((it / kUpBStages) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[s], (uint32_t)sh.n * (64u * 128u));
+              for (int u = 0; u < sh.n; ++u) {
+                const int ph = sh.ph[u], pw = sh.pw[u];
+                const int ah = sh.oh + 1 - ph, aw = sh.ow + 1 - pw;
+                const int slab = (pd * 4 + ph * 2 + pw) * 8 + ad * 4 + ah * 2 + aw;
+                tma_load_3d(smem_b + s * kUpBSlot + u * (64 * 128), &tmB, &b_full[s], cb * 64, 0, slab);
+              }
+            }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===== MMA issuer =====
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256u;
+      uint32_t sa = 0;
+      for (int cb = 0; cb < g.cin_blocks; ++cb)
+        for (int ad = 0; ad < 2; ++ad)
+          for (int t = 0; t < kUpSteps; ++t, ++b_it) {
+            const UpStep sh = kUpStepTab[t];
+            if (sh.new_a) {
+              sa = a_it % kUpAStages;
+              mbar_wait(&a_full[sa], (a_it / kUpAStages) & 1u);
+              ++a_it;
+            }
+            const uint32_t sb = b_it % kUpBStages;
+            mbar_wait(&b_full[sb], (b_it / kUpBStages) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_addr = smem_u32(smem + sa * kTileBytes);
+              const uint32_t b_addr = smem_u32(smem_b + sb * kUpBSlot);
+              // steps 0 and 1 of the first (K block, depth tap) cover all four parity accumulators: overwrite
+              const uint32_t first = (cb == 0 && ad == 0 && t < 2) ? 0u : 1u;
+              if (sh.stacked) {
+                const uint32_t col = (uint32_t)(sh.pw[0] * 2 + sh.ph[0]) * 64u;
+                const uint32_t idesc = make_idesc_bf16(128, 64 * sh.n, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
+                            make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
+              } else {
+                constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
+                for (int u = 0; u < sh.n; ++u) {
+                  const uint32_t col = (uint32_t)(sh.pw[u] * 2 + sh.ph[u]) * 64u;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
+                              make_smem_desc(b_addr + u * (64 * 128) + k * 32, 16, 1024), idesc64, 1u);
+                }
+              }
+              if (sh.rel_a) umma_commit(&a_empty[sa]);
+              umma_commit(&b_empty[sb]);
+              if (cb == g.cin_blocks - 1 && ad == 1 && t == kUpSteps - 1) umma_commit(&acc_full[as]);
+            }
+            __syncwarp();
+          }
+    }
+  } else {
+    // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2): four parity tiles per item =====
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (warp_id == 3 && lane == 0);
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    uint32_t acc_it = 0, st_it = 0;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+      int w0, h0, d, pd, n;
+      decode(item, w0, h0, d, pd, n);
+      const uint32_t as = acc_it & 1;
+      mbar_wait(&acc_full[as], (acc_it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j, ++st_it) {          // column block j = pw * 2 + ph
+        uint8_t* tile = smem_o + (st_it & 1) * kTileBytes;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256u + (uint32_t)(j * 64);
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
+        tmem_ld_wait();
+        if (j == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        const uint32_t dst = smem_u32(tile) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v0[c * 8 + 0]), __uint_as_float(v0[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v0[c * 8 + 2]), __uint_as_float(v0[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v0[c * 8 + 4]), __uint_as_float(v0[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v0[c * 8 + 6]), __uint_as_float(v0[c * 8 + 7]));
+          sts128(dst + ((uint32_t)(c ^ (row & 7)) << 4), pk);
+          pk.x = pack_bf16x2(__uint_as_float(v1[c * 8 + 0]), __uint_as_float(v1[c * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v1[c * 8 + 2]), __uint_as_float(v1[c * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v1[c * 8 + 4]), __uint_as_float(v1[c * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v1[c * 8 + 6]), __uint_as_float(v1[c * 8 + 7]));
+          sts128(dst + ((uint32_t)((4 + c) ^ (row & 7)) << 4), pk);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const int parity = pd * 4 + (j & 1) * 2 + (j >> 1);
+          tma_store_5d(&tmC.m[parity], tile, 0, w0, h0, d, n);
+          tma_store_commit();
+        }
+        if (stats_partial != nullptr)
+          tile_channel_sums<kKwW>(smem_u32(tile), q, lane, g.W - w0, g.H - h0, s1a, s1b, s2a, s2b);
+      }
+    }
+    if (stats_partial != nullptr) {
+      float* dst = stats_partial + (size_t)(blockIdx.x * 4 + (warp_id - 3)) * 2 * 64;
+      *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(s1a, s1b);
+      *reinterpret_cast<float2*>(dst + 64 + 2 * lane) = make_float2(s2a, s2b);
+    }
+    if (issuer) tma_store_wait_read_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
 // wgrad
 // =================================================================================================
 struct WgradGeom {
@@ -1269,11 +1518,45 @@ int conv3_igemm_bn(const void* x, const void* wpack, void* y, int N, int D, int 
 
 // y_hi[n, 2d+pd, 2h+ph, 2w+pw, co] = conv3(upsample2(x_lo), w):  8 parity-specific 2x2x2 convolutions on the low-res grid.
 // x_lo [N][D][H][W][Cin], wup bf16 [64 = parity*8+abc][Cout][Cin], y_hi [N][2D][2H][2W][Cout].
-int upconv3_fprop(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin, int Cout,
-                  cudaStream_t st) {
+static int upconv3_fprop_impl(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin,
+                             int Cout, float* stats, int* stats_blocks, cudaStream_t st) {
+  if (stats_blocks) *stats_blocks = 0;
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
               "upconv3_fprop: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "upconv3_fprop: empty tensor");
+  // Cout = 64: persistent kernel with shared-tile tap stacking when 8 x 16 patches tile the low-res plane well
+  // (SIVAE_UPCONV_FUSED=0 disables it, =force takes it for every Cout = 64 shape -- the parity tests use both)
+  if (Cout == 64) {
+    const char* e = getenv("SIVAE_UPCONV_FUSED");
+    const bool off = e != nullptr && e[0] == '0';
+    const bool force = e != nullptr && e[0] == 'f';
+    UpGeom ug;
+    ug.N = N; ug.D = D; ug.H = H; ug.W = W;
+    ug.tiles_w = cdiv(W, kKwW); ug.tiles_h = cdiv(H, kKwH);
+    ug.cin_blocks = Cin / 64;
+    ug.items = (long long)ug.tiles_w * ug.tiles_h * D * 2 * N;
+    const double eff = ((double)W * H) / ((double)ug.tiles_w * kKwW * ug.tiles_h * kKwH);
+    if (!off && (force || (eff >= 0.8 && ug.items >= 2 * num_sms()))) {
+      CUtensorMap tA, tB;
+      TmapPack tC;
+      if (make_act_tmap(&tA, x_lo, N, D, H, W, Cin, kKwW, kKwH, 1)) return -1;
+      for (int p = 0; p < 8; ++p)
+        if (make_parity_tmap(&tC.m[p], y_hi, N, D, H, W, Cout, p, kKwW, kKwH, 1)) return -1;
+      if (make_weight_tmap(&tB, wup, 64, Cout, Cin, 64)) return -1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(upconv3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem),
+                       "cudaFuncSetAttribute(upconv3_fused)")) return -1;
+        attr_set = true;
+      }
+      const unsigned ctas = (unsigned)(ug.items < (long long)num_sms() ? ug.items : (long long)num_sms());
+      const bool fuse_stats = stats != nullptr && stats_blocks != nullptr;
+      upconv3_fused_kernel<<<ctas, 224, kUpSmem, st>>>(tA, tB, tC, ug, fuse_stats ? stats : nullptr);
+      SIVAE_LAUNCH_OK("upconv3_fused_kernel");
+      if (fuse_stats) *stats_blocks = (int)ctas * 4;
+      return 0;
+    }
+  }
   ConvGeom g;
   fill_geom(g, N, D, H, W, Cin, kTapsUpFprop);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
@@ -1289,6 +1572,31 @@ int upconv3_fprop(const void* x_lo, const void* wup, void* y_hi, int N, int D, i
   const ToOneEpilogue ep{};
   if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
   return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
+}
+
+int upconv3_fprop(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin, int Cout,
+                  cudaStream_t st) {
+  return upconv3_fprop_impl(x_lo, wup, y_hi, N, D, H, W, Cin, Cout, nullptr, nullptr, st);
+}
+
+// Upsample(2) + Conv3d + train-mode BatchNorm3d coefficients of the (high-res) output in one call
+// (models/models.py:58-60); statistics from the convolution epilogue when the persistent kernel runs.
+int upconv3_fprop_bn(const void* x_lo, const void* wup, void* y_hi, int N, int D, int H, int W, int Cin, int Cout,
+                     const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                     float eps, float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  SIVAE_CHECK(ws && ws_bytes >= bn_workspace_bytes(Cout), "upconv3_fprop_bn: workspace too small");
+  int blocks = 0;
+  const bool allow = getenv("SIVAE_NO_FUSED_STATS") == nullptr;
+  int rc = upconv3_fprop_impl(x_lo, wup, y_hi, N, D, H, W, Cin, Cout, allow ? (float*)ws : nullptr,
+                              allow ? &blocks : nullptr, st);
+  if (rc) return rc;
+  const long long nvox = (long long)N * D * H * W * 8;
+  if (blocks > 0)
+    return bn_coeffs_from_partials((const float*)ws, blocks, nvox, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean,
+                                   invstd, scale, shift, st);
+  return bn_train_coeffs(y_hi, nvox, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift, ws,
+                         ws_bytes, st);
 }
 
 // dx_lo = upsample2^T(conv3^T(dy_hi)):  one 64-tap (8 parities x 8 taps) implicit GEMM gathering dy on its parity

@@ -142,10 +142,11 @@ class _ConvBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int, pre_up: bool):
         wf, wd = _packed(weight, pre_up)
-        if bn.training and not pre_up:
+        if bn.training:
             # convolution + batch statistics in one C-ABI call (the sums come out of the conv epilogue)
-            y, mean, invstd, scale, shift = K.conv3_igemm_bn(x, wf, gamma, beta, bn.running_mean, bn.running_var,
-                                                             bn.num_batches_tracked, bn.momentum, bn.eps)
+            conv_bn = K.upconv3_fprop_bn if pre_up else K.conv3_igemm_bn
+            y, mean, invstd, scale, shift = conv_bn(x, wf, gamma, beta, bn.running_mean, bn.running_var,
+                                                    bn.num_batches_tracked, bn.momentum, bn.eps)
         else:
             y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
             mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)

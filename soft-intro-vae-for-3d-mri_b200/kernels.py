@@ -41,6 +41,8 @@ _SIGNATURES = {
     "sivae_conv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_pack_upconv3_weights": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "sivae_upconv3_fprop": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sivae_upconv3_fprop_bn": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp,
+                                    _vp, _vp, _sz, _vp]),
     "sivae_upconv3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sivae_upconv3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "sivae_upconv3_wgrad": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
@@ -303,6 +305,29 @@ def upconv3_fprop(x_lo: torch.Tensor, wup: torch.Tensor) -> torch.Tensor:
            lambda: _check(_L().sivae_upconv3_fprop(_p(x_lo), _p(wup), _p(y), n, d, h, w, ci, co, _stream(x_lo)),
                           "sivae_upconv3_fprop"))
     return y
+
+
+def upconv3_fprop_bn(x_lo: torch.Tensor, wup: torch.Tensor, gamma, beta, running_mean, running_var,
+                     num_batches_tracked, momentum: float, eps: float):
+    """upconv3_fprop + train-mode BatchNorm coefficients of the output: -> (y_hi, mean, invstd, scale, shift)."""
+    _req(x_lo, torch.bfloat16, "x_lo")
+    _req(wup, torch.bfloat16, "wup")
+    n, d, h, w, ci = x_lo.shape
+    co = wup.shape[1]
+    assert wup.shape == (64, co, ci)
+    lib = _L()
+    y = torch.empty(n, 2 * d, 2 * h, 2 * w, co, dtype=torch.bfloat16, device=x_lo.device)
+    ws = _workspace(x_lo.device, lib.sivae_bn_workspace_bytes(co), "bn")
+    coef = torch.empty(4, co, dtype=torch.float32, device=x_lo.device)
+    if num_batches_tracked is not None:
+        _req(num_batches_tracked, torch.int64, "num_batches_tracked")
+    flops = 2.0 * 27 * ci * co * n * d * h * w * 8
+    _timed("upconv3_fprop", (flops, (n, d, h, w, ci, co)),
+           lambda: _check(lib.sivae_upconv3_fprop_bn(_p(x_lo), _p(wup), _p(y), n, d, h, w, ci, co, _p(gamma), _p(beta),
+                                                     _p(running_mean), _p(running_var), _p(num_batches_tracked),
+                                                     momentum, eps, _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]),
+                                                     _p(ws), ws.numel(), _stream(x_lo)), "sivae_upconv3_fprop_bn"))
+    return y, coef[0], coef[1], coef[2], coef[3]
 
 
 def upconv3_dgrad(dy_hi: torch.Tensor, wupT: torch.Tensor) -> torch.Tensor:

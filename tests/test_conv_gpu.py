@@ -170,8 +170,41 @@ def test_pack_upconv_weights():
     assert torch.equal(wupT, wup.transpose(1, 2).contiguous())
 
 
+@pytest.fixture(params=["auto", "force", "0"])
+def upmode(request):
+    """persistent shared-tile kernel: library's choice / forced for every Cout = 64 shape / tap-by-tap forced"""
+    import os
+    old = os.environ.pop("SIVAE_UPCONV_FUSED", None)
+    if request.param != "auto":
+        os.environ["SIVAE_UPCONV_FUSED"] = request.param
+    yield request.param
+    os.environ.pop("SIVAE_UPCONV_FUSED", None)
+    if old is not None:
+        os.environ["SIVAE_UPCONV_FUSED"] = old
+
+
+@pytest.mark.parametrize("shape", UP_SHAPES + [(2, 6, 16, 24, 64, 64), (1, 3, 32, 8, 128, 64), (3, 5, 20, 13, 64, 64)])
+def test_upconv_fprop_bn_fused_stats(shape, upmode):
+    """sivae_upconv3_fprop_bn = sivae_upconv3_fprop + sivae_bn_train_coeffs (statistics from the epilogue of the
+    persistent kernel when it runs; ragged low-res tiles masked)."""
+    n, d, h, w, ci, co = shape
+    x, wt = _mk(*shape)
+    wup, _ = K.pack_upconv3_weights(wt)
+    gamma, beta = torch.rand(co, device=DEV) + 0.5, torch.randn(co, device=DEV)
+    rm1, rv1, n1 = torch.zeros(co, device=DEV), torch.ones(co, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+    rm2, rv2, n2 = rm1.clone(), rv1.clone(), n1.clone()
+    y, *coef = K.upconv3_fprop_bn(x, wup, gamma, beta, rm1, rv1, n1, 0.1, 1e-5)
+    y_ref = K.upconv3_fprop(x, wup)
+    ref = K.bn_train_coeffs(y_ref, gamma, beta, rm2, rv2, n2, 0.1, 1e-5)
+    assert torch.equal(y, y_ref)
+    _check_bf16(y, S.upconv3_fprop(x, wup), f"upconv fprop (bn entry) vs folded spec {shape}")
+    for a, b, name in zip(coef, ref, ("mean", "invstd", "scale", "shift")):
+        assert torch.allclose(a, b, rtol=3e-5, atol=3e-6), (name, float((a - b).abs().max()))
+    assert torch.allclose(rm1, rm2, rtol=3e-5, atol=3e-6) and torch.allclose(rv1, rv2, rtol=3e-5, atol=3e-6)
+
+
 @pytest.mark.parametrize("shape", UP_SHAPES)
-def test_upconv_fprop(shape):
+def test_upconv_fprop(shape, upmode):
     n, d, h, w, ci, co = shape
     x, wt = _mk(*shape)
     wup, _ = K.pack_upconv3_weights(wt)
