@@ -541,6 +541,8 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp_id == 1) {
     // ===== MMA issuer =====
+    // The tile loop is fully unrolled so that column offsets, slab offsets and instruction descriptors are immediates:
+    // a single thread issues every UMMA, and its bookkeeping must stay well below the ~600 cycles a tile's MMAs take.
     uint32_t a_it = 0, b_it = 0, acc_it = 0;
     for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
       const uint32_t as = acc_it & 1;
@@ -550,35 +552,35 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int pass = 0; pass < 9; ++pass, ++b_it) {
         const uint32_t bs = b_it % kKdBStages;
         mbar_wait(&b_full[bs], (b_it / kKdBStages) & 1u);
-        const uint32_t b_base = smem_u32(smem_b + bs * kKdBBytes);
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kKdBBytes), 16, 1024);
+        const bool pass0 = (pass == 0);
+#pragma unroll
         for (int t = 0; t < kKdP + 2; ++t, ++a_it) {
           const uint32_t sa = a_it % kKdAStages;
           mbar_wait(&a_full[sa], (a_it / kKdAStages) & 1u);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_addr = smem_u32(smem + sa * kTileBytes);
-            // input plane t of the chunk feeds output plane i = t - kd through tap kd, 0 <= i < P
-            int kd_lo = t - (kKdP - 1); if (kd_lo < 0) kd_lo = 0;
+            const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kTileBytes), 16, 1024);
+            // input plane t of the chunk feeds output plane i = t - kd through tap kd, 0 <= i < P  (all compile time)
+            constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
+            const int kd_lo0 = t - (kKdP - 1) > 0 ? t - (kKdP - 1) : 0;
             const int kd_hi = t < 2 ? t : 2;
-            if (pass == 0 && kd_lo == 0) {
+            int kd_lo = kd_lo0;
+            if (pass0 && kd_lo0 == 0) {
               // first contribution to output plane i = t: overwrite
               const uint32_t col = (uint32_t)(64 * (kKdP - 1 - t));
-              constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
-                          make_smem_desc(b_base + k * 32, 16, 1024), idesc64, k != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem + col, adesc + 2 * k, bdesc + 2 * k, idesc64, k != 0 ? 1u : 0u);
               kd_lo = 1;
             }
             if (kd_lo <= kd_hi) {
               const int nun = kd_hi - kd_lo + 1;                                  // stacked taps: 1..3
               const uint32_t col = (uint32_t)(64 * (kKdP - 1 - (t - kd_lo)));    // highest output plane first
-              const uint32_t idesc = make_idesc_bf16(128, 64 * nun, 0, 0);
-              const uint32_t b_addr = b_base + (uint32_t)kd_lo * (64u * 128u);
+              const uint32_t idesc = nun == 3 ? make_idesc_bf16(128, 192, 0, 0)
+                                     : nun == 2 ? make_idesc_bf16(128, 128, 0, 0) : idesc64;
+              const uint64_t bd = bdesc + (uint64_t)(kd_lo * (64 * 128 / 16));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
-                          make_smem_desc(b_addr + k * 32, 16, 1024), idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem + col, adesc + 2 * k, bd + 2 * k, idesc, 1u);
             }
             umma_commit(&a_empty[sa]);
             if (t == kKdP + 1) {
@@ -696,18 +698,18 @@ static constexpr int kUpSteps = 10;
 // user of the current one.  The (0,0) tile feeds all four parities: two N = 128 steps on the same A tile (a 32 KB weight
 // slot would leave too few slots to hide the L2 latency of the weight stream).
 struct UpStep { int8_t oh, ow, n, stacked, new_a, rel_a; int8_t ph[2], pw[2]; };
-__device__ __constant__ UpStep kUpStepTab[kUpSteps] = {
-    {0, 0, 2, 1, 1, 0, {0, 1}, {0, 0}},
-    {0, 0, 2, 1, 0, 1, {0, 1}, {1, 1}},
-    {0, -1, 2, 1, 1, 1, {0, 1}, {0, 0}},
-    {0, 1, 2, 1, 1, 1, {0, 1}, {1, 1}},
-    {-1, 0, 2, 0, 1, 1, {0, 0}, {0, 1}},
-    {1, 0, 2, 0, 1, 1, {1, 1}, {0, 1}},
-    {-1, -1, 1, 1, 1, 1, {0, 0}, {0, 0}},
-    {-1, 1, 1, 1, 1, 1, {0, 0}, {1, 0}},
-    {1, -1, 1, 1, 1, 1, {1, 0}, {0, 0}},
-    {1, 1, 1, 1, 1, 1, {1, 0}, {1, 0}},
-};
+#define SIVAE_UP_STEPS                                                                                   \
+  {0, 0, 2, 1, 1, 0, {0, 1}, {0, 0}}, {0, 0, 2, 1, 0, 1, {0, 1}, {1, 1}}, {0, -1, 2, 1, 1, 1, {0, 1}, {0, 0}}, \
+  {0, 1, 2, 1, 1, 1, {0, 1}, {1, 1}}, {-1, 0, 2, 0, 1, 1, {0, 0}, {0, 1}}, {1, 0, 2, 0, 1, 1, {1, 1}, {0, 1}}, \
+  {-1, -1, 1, 1, 1, 1, {0, 0}, {0, 0}}, {-1, 1, 1, 1, 1, 1, {0, 0}, {1, 0}}, {1, -1, 1, 1, 1, 1, {1, 0}, {0, 0}}, \
+  {1, 1, 1, 1, 1, 1, {1, 0}, {1, 0}}
+// compile-time copy: the MMA issuer's step loop is fully unrolled so every field folds into an immediate (with run-time
+// table look-ups the single issuing thread, not the tensor pipe, set the pace: ~1000 cycles of bookkeeping per step)
+__host__ __device__ constexpr UpStep up_step_c(int t) {
+  constexpr UpStep tab[kUpSteps] = {SIVAE_UP_STEPS};
+  return tab[t];
+}
+__device__ __constant__ UpStep kUpStepTab[kUpSteps] = {SIVAE_UP_STEPS};
 
 __global__ void __launch_bounds__(224, 1)
 upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -802,10 +804,13 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t d_tmem = tmem_base + as * 256u;
       uint32_t sa = 0;
       for (int cb = 0; cb < g.cin_blocks; ++cb)
-        for (int ad = 0; ad < 2; ++ad)
+        for (int ad = 0; ad < 2; ++ad) {
+          const uint32_t first = (cb == 0 && ad == 0) ? 0u : 1u;   // steps 0, 1 of the first tap overwrite all 4 parities
+          const bool last = (cb == g.cin_blocks - 1 && ad == 1);
+#pragma unroll
           for (int t = 0; t < kUpSteps; ++t, ++b_it) {
-            const UpStep sh = kUpStepTab[t];
-            if (sh.new_a) {
+            constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc128 = make_idesc_bf16(128, 128, 0, 0);
+            if (up_step_c(t).new_a) {
               sa = a_it % kUpAStages;
               mbar_wait(&a_full[sa], (a_it / kUpAStages) & 1u);
               ++a_it;
@@ -814,33 +819,30 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&b_full[sb], (b_it / kUpBStages) & 1u);
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t a_addr = smem_u32(smem + sa * kTileBytes);
-              const uint32_t b_addr = smem_u32(smem_b + sb * kUpBSlot);
-              // steps 0 and 1 of the first (K block, depth tap) cover all four parity accumulators: overwrite
-              const uint32_t first = (cb == 0 && ad == 0 && t < 2) ? 0u : 1u;
-              if (sh.stacked) {
-                const uint32_t col = (uint32_t)(sh.pw[0] * 2 + sh.ph[0]) * 64u;
-                const uint32_t idesc = make_idesc_bf16(128, 64 * sh.n, 0, 0);
+              const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kTileBytes), 16, 1024);
+              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * kUpBSlot), 16, 1024);
+              if (up_step_c(t).stacked) {
+                const uint32_t col = (uint32_t)(up_step_c(t).pw[0] * 2 + up_step_c(t).ph[0]) * 64u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
-                            make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
+                for (int k = 0; k < 4; ++k)   // +32 bytes per K step = +2 in the descriptor's (address >> 4) field
+                  umma_bf16(d_tmem + col, adesc + 2 * k, bdesc + 2 * k, up_step_c(t).n == 2 ? idesc128 : idesc64,
+                            (k == 0 && t < 2) ? first : 1u);
               } else {
-                constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
-                for (int u = 0; u < sh.n; ++u) {
-                  const uint32_t col = (uint32_t)(sh.pw[u] * 2 + sh.ph[u]) * 64u;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const uint32_t col = (uint32_t)(up_step_c(t).pw[u] * 2 + up_step_c(t).ph[u]) * 64u;
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem + col, make_smem_desc(a_addr + k * 32, 16, 1024),
-                              make_smem_desc(b_addr + u * (64 * 128) + k * 32, 16, 1024), idesc64, 1u);
+                    umma_bf16(d_tmem + col, adesc + 2 * k, bdesc + (uint64_t)(u * (64 * 128 / 16) + 2 * k), idesc64, 1u);
                 }
               }
-              if (sh.rel_a) umma_commit(&a_empty[sa]);
+              if (up_step_c(t).rel_a) umma_commit(&a_empty[sa]);
               umma_commit(&b_empty[sb]);
-              if (cb == g.cin_blocks - 1 && ad == 1 && t == kUpSteps - 1) umma_commit(&acc_full[as]);
+              if (last && t == kUpSteps - 1) umma_commit(&acc_full[as]);
             }
             __syncwarp();
           }
+        }
     }
   } else {
     // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2): four parity tiles per item =====
