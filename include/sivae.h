@@ -282,6 +282,24 @@ size_t sivae_similarity_workspace_bytes(int nq, int nd);
 int sivae_similarity_topk(const float* q, const float* db, int nq, int nd, int dim, int metric, int k,
                           float* out_scores, int* out_index, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-GPU input pipeline (SURVEY.md section 8f NEXT-3).  x, y: fp32 [B][n] / [B][D][H][W] on the device.
+ * ---------------------------------------------------------------------------------------------- */
+/* stats[b] = {mean, population std, min, max} of volume b.  workspace: sivae_volume_stats_workspace_bytes(B). */
+size_t sivae_volume_stats_workspace_bytes(int B);
+int sivae_volume_stats(const float* x, int B, long long n, float* stats, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* BrainDataset._preprocess (utils/data_load.py:25-30): y = minmax(clip(x, 0, cut_range * std(x))) per volume
+ * (cut_range = 4 in the reference); also returns the raw-volume stats.  In place (y == x) is allowed. */
+int sivae_preprocess_clip_minmax(const float* x, float* y, int B, long long n, float cut_range, float* stats,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* Trilinear resampling through per-volume 3x4 matrices mats[b] mapping OUTPUT voxel (d,h,w,1) to INPUT voxel
+ * coordinates (tio.RandomAffine, aug-z-1200main.py:114; identity rows leave a volume unchanged).  Samples outside the
+ * volume take pad[b]; with pad == NULL the per-volume minimum stats[b][2] (torchio default_pad_value='minimum'), or 0
+ * when stats is NULL as well.  y must not alias x. */
+int sivae_affine_resample(const float* x, float* y, int B, int D, int H, int W, const float* mats, const float* pad,
+                          const float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

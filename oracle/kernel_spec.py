@@ -291,6 +291,44 @@ def to_ncdhw_f32(x):
     return _ncdhw(x).contiguous()
 
 
+def volume_stats(x):
+    v = x.reshape(x.shape[0], -1).double()
+    return torch.stack([v.mean(1), v.std(1, unbiased=False), v.min(1).values, v.max(1).values], 1).float()
+
+
+def preprocess_clip_minmax(x, cut_range=4.0, out=None):
+    """utils/data_load.py:25-30: np.clip(v, 0, 4*np.std(v)); (v - min) / (max - min), per volume."""
+    stats = volume_stats(x)
+    v = x.reshape(x.shape[0], -1)
+    c = torch.minimum(v.clamp_min(0.0), cut_range * stats[:, 1:2])
+    lo, hi = c.min(1, keepdim=True).values, c.max(1, keepdim=True).values
+    y = ((c - lo) / (hi - lo)).reshape(x.shape)
+    if out is not None:
+        out.copy_(y)
+        y = out
+    return y, stats
+
+
+def affine_resample(x, mats, pad=None, stats=None):
+    """Trilinear resampling through output->input voxel matrices, via F.grid_sample(align_corners=True); samples outside
+    the volume take the pad value (pad[b], else stats[b][2] = per-volume minimum, else 0)."""
+    b, d, h, w = x.shape
+    dev = x.device
+    dd, hh, ww = torch.meshgrid(torch.arange(d, device=dev), torch.arange(h, device=dev), torch.arange(w, device=dev),
+                                indexing="ij")
+    ones = torch.ones_like(dd)
+    out_idx = torch.stack([dd, hh, ww, ones], -1).double().reshape(-1, 4)            # [n,4]
+    m = mats.double().reshape(b, 3, 4)
+    src = torch.einsum("bij,nj->bni", m, out_idx)                                    # [b,n,3] = (d,h,w) input coords
+    size = torch.tensor([d, h, w], device=dev, dtype=torch.float64)
+    norm = 2.0 * src / (size - 1).clamp_min(1) - 1.0
+    grid = norm[..., [2, 1, 0]].reshape(b, d, h, w, 3).float()                       # grid_sample wants (x=w, y=h, z=d)
+    padv = pad if pad is not None else (stats[:, 2] if stats is not None else torch.zeros(b, device=dev))
+    padv = padv.reshape(b, 1, 1, 1, 1).float()
+    y = F.grid_sample(x[:, None] - padv, grid, mode="bilinear", padding_mode="zeros", align_corners=True) + padv
+    return y[:, 0]
+
+
 def similarity_topk(queries, database, k, metric="cosine"):
     """Top-k similarity (cosine, or negative squared L2), best first, ties -> lower database index."""
     q, d = queries.double(), database.double()

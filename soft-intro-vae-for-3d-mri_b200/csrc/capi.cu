@@ -102,6 +102,10 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+size_t volume_stats_workspace_bytes(int);
+int volume_stats(const float*, int, long long, float*, void*, size_t, cudaStream_t);
+int preprocess_clip_minmax(const float*, float*, int, long long, float, float*, void*, size_t, cudaStream_t);
+int affine_resample(const float*, float*, int, int, int, int, const float*, const float*, const float*, cudaStream_t);
 int upconv3_fprop_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
                      float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 size_t similarity_workspace_bytes(int, int);
@@ -283,6 +287,18 @@ int sivae_upconv3_fprop_bn(const void* x, const void* wup, void* y, int N, int D
                            void* stream) {
   return upconv3_fprop_bn(x, wup, y, N, D, H, W, Cin, Cout, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale,
                           shift, ws, ws_bytes, ST(stream));
+}
+size_t sivae_volume_stats_workspace_bytes(int B) { return volume_stats_workspace_bytes(B); }
+int sivae_volume_stats(const float* x, int B, long long n, float* stats, void* ws, size_t ws_bytes, void* stream) {
+  return volume_stats(x, B, n, stats, ws, ws_bytes, ST(stream));
+}
+int sivae_preprocess_clip_minmax(const float* x, float* y, int B, long long n, float cut_range, float* stats, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  return preprocess_clip_minmax(x, y, B, n, cut_range, stats, ws, ws_bytes, ST(stream));
+}
+int sivae_affine_resample(const float* x, float* y, int B, int D, int H, int W, const float* mats, const float* pad,
+                          const float* stats, void* stream) {
+  return affine_resample(x, y, B, D, H, W, mats, pad, stats, ST(stream));
 }
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream) {

@@ -163,12 +163,10 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + kTileBytes;
+        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024), bdesc = make_smem_desc(a_addr + kTileBytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 64-channel K block = 4 x UMMA_K(16)
-          umma_bf16(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)  // 64-channel K block = 4 x UMMA_K(16); +32 bytes = +2 in the (address >> 4) field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "sivae_mse_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _sz, _vp]),
     "sivae_mse_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "sivae_adam_step": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _vp]),
+    "sivae_volume_stats_workspace_bytes": (_sz, [_i]),
+    "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
+    "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
+    "sivae_affine_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sivae_similarity_workspace_bytes": (_sz, [_i, _i]),
     "sivae_similarity_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sivae_ncdhw_f32_to_ndhwc_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
@@ -459,6 +463,48 @@ def adam_step(tensors, lr: torch.Tensor, beta1: float, beta2: float, eps: float,
             arr[i].cout, arr[i].cin = p.shape[0], p.shape[1]
     _check(_L().sivae_adam_step(ctypes.cast(arr, ctypes.c_void_p), len(tensors), _p(lr), beta1, beta2, eps, _p(step),
                                 _stream(lr)), "sivae_adam_step")
+
+
+# ----------------------------------------------------------------------------------------------
+# on-GPU input pipeline (SURVEY section 8f NEXT-3)
+# ----------------------------------------------------------------------------------------------
+def volume_stats(x: torch.Tensor) -> torch.Tensor:
+    """x fp32 [B, ...] -> [B, 4] = (mean, population std, min, max) per volume."""
+    _req(x, torch.float32, "x")
+    b = x.shape[0]
+    n = x.numel() // b
+    lib = _L()
+    ws = _workspace(x.device, lib.sivae_volume_stats_workspace_bytes(b), "vstats")
+    stats = torch.empty(b, 4, dtype=torch.float32, device=x.device)
+    _check(lib.sivae_volume_stats(_p(x), b, n, _p(stats), _p(ws), ws.numel(), _stream(x)), "sivae_volume_stats")
+    return stats
+
+
+def preprocess_clip_minmax(x: torch.Tensor, cut_range: float = 4.0, out: Optional[torch.Tensor] = None):
+    """BrainDataset._preprocess per volume: minmax(clip(x, 0, cut_range*std)).  -> (y, raw stats [B,4])."""
+    _req(x, torch.float32, "x")
+    b = x.shape[0]
+    n = x.numel() // b
+    lib = _L()
+    ws = _workspace(x.device, lib.sivae_volume_stats_workspace_bytes(b), "vstats")
+    stats = torch.empty(b, 4, dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x) if out is None else out
+    _check(lib.sivae_preprocess_clip_minmax(_p(x), _p(y), b, n, float(cut_range), _p(stats), _p(ws), ws.numel(),
+                                            _stream(x)), "sivae_preprocess_clip_minmax")
+    return y, stats
+
+
+def affine_resample(x: torch.Tensor, mats: torch.Tensor, pad: Optional[torch.Tensor] = None,
+                    stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Trilinear resampling of x fp32 [B,D,H,W] through mats fp32 [B,12] (output voxel -> input voxel, rows d,h,w)."""
+    _req(x, torch.float32, "x")
+    _req(mats, torch.float32, "mats")
+    b, d, h, w = x.shape
+    assert mats.shape == (b, 12)
+    y = torch.empty_like(x)
+    _check(_L().sivae_affine_resample(_p(x), _p(y), b, d, h, w, _p(mats), _p(pad), _p(stats), _stream(x)),
+           "sivae_affine_resample")
+    return y
 
 
 # ----------------------------------------------------------------------------------------------
