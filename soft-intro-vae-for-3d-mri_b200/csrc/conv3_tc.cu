@@ -457,6 +457,7 @@ conv3_kw64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 struct KdGeom {
   int N, D, H, W;
   int tiles_w, tiles_h, tiles_d;   // 8 x 16 patches, chunks of 4 planes
+  int cin_blocks;                  // Cin / 64 (K blocks per tap)
   long long items;
 };
 static constexpr int kKdP = 4;                       // output planes per work item
@@ -514,12 +515,13 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         decode(item, w0, h0, d0, n);
         for (int pass = 0; pass < 9; ++pass) {
           const int kh = pass / 3, kw = pass - kh * 3;
-          for (int t = 0; t < kKdP + 2; ++t, ++it) {
-            const int s = it % kKdAStages;
-            mbar_wait(&a_empty[s], ((it / kKdAStages) & 1u) ^ 1u);
-            mbar_expect_tx(&a_full[s], kTileBytes);
-            tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], 0, w0 + kw - 1, h0 + kh - 1, d0 - 1 + t, n);
-          }
+          for (int cb = 0; cb < g.cin_blocks; ++cb)
+            for (int t = 0; t < kKdP + 2; ++t, ++it) {
+              const int s = it % kKdAStages;
+              mbar_wait(&a_empty[s], ((it / kKdAStages) & 1u) ^ 1u);
+              mbar_expect_tx(&a_full[s], kTileBytes);
+              tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], cb * 64, w0 + kw - 1, h0 + kh - 1, d0 - 1 + t, n);
+            }
         }
       }
     }
@@ -528,14 +530,15 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x)
-        for (int pass = 0; pass < 9; ++pass, ++it) {
-          const int s = it % kKdBStages;
-          mbar_wait(&b_empty[s], ((it / kKdBStages) & 1u) ^ 1u);
-          mbar_expect_tx(&b_full[s], kKdBBytes);
+        for (int pass = 0; pass < 9; ++pass)
+          for (int cb = 0; cb < g.cin_blocks; ++cb, ++it) {
+            const int s = it % kKdBStages;
+            mbar_wait(&b_empty[s], ((it / kKdBStages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], kKdBBytes);
 #pragma unroll
-          for (int kd = 0; kd < 3; ++kd)
-            tma_load_3d(smem_b + s * kKdBBytes + kd * (64 * 128), &tmB, &b_full[s], 0, 0, kd * 9 + pass);
-        }
+            for (int kd = 0; kd < 3; ++kd)
+              tma_load_3d(smem_b + s * kKdBBytes + kd * (64 * 128), &tmB, &b_full[s], cb * 64, 0, kd * 9 + pass);
+          }
     }
   } else if (warp_id == 1) {
     // ===== MMA issuer =====
@@ -547,11 +550,12 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * 256u;
-      for (int pass = 0; pass < 9; ++pass, ++b_it) {
+      for (int pc = 0; pc < 9 * g.cin_blocks; ++pc, ++b_it) {   // (pass, K block) pairs, K block fastest
         const uint32_t bs = b_it % kKdBStages;
         mbar_wait(&b_full[bs], (b_it / kKdBStages) & 1u);
         const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kKdBBytes), 16, 1024);
-        const bool pass0 = (pass == 0);
+        const bool pass0 = (pc == 0);                            // first tap, first K block: overwrite
+        const bool last = (pc == 9 * g.cin_blocks - 1);
 #pragma unroll
         for (int t = 0; t < kKdP + 2; ++t, ++a_it) {
           const uint32_t sa = a_it % kKdAStages;
@@ -583,7 +587,7 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_commit(&a_empty[sa]);
             if (t == kKdP + 1) {
               umma_commit(&b_empty[bs]);
-              if (pass == 8) umma_commit(&acc_full[as]);
+              if (last) umma_commit(&acc_full[as]);
             }
           }
           __syncwarp();
@@ -1395,22 +1399,23 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64, "conv3_igemm: Cin=%d must be a multiple of 64", Cin);
   SIVAE_CHECK(Cout % 64 == 0 && Cout >= 64, "conv3_igemm: Cout=%d must be a multiple of 64", Cout);
   SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm: empty tensor");
-  // Cin = Cout = 64: persistent kd-fused kernel when 8 x 16 x 4 chunks tile the volume well (SIVAE_CONV_KD=0 disables
-  // it, =force takes it for every 64 -> 64 shape -- the parity tests use both).
-  if (Cin == 64 && Cout == 64) {
+  // Cout = 64 (Cin = 64, 128, ...): persistent kd-fused kernel when 8 x 16 x 4 chunks tile the volume well
+  // (SIVAE_CONV_KD=0 disables it, =force takes it for every Cout = 64 shape -- the parity tests use both).
+  if (Cout == 64) {
     const char* kdenv = getenv("SIVAE_CONV_KD");
     const bool off = kdenv != nullptr && kdenv[0] == '0';
     const bool force = kdenv != nullptr && kdenv[0] == 'f';
     KdGeom kg;
     kg.N = N; kg.D = D; kg.H = H; kg.W = W;
     kg.tiles_w = cdiv(W, kKwW); kg.tiles_h = cdiv(H, kKwH); kg.tiles_d = cdiv(D, kKdP);
+    kg.cin_blocks = Cin / 64;
     kg.items = (long long)kg.tiles_w * kg.tiles_h * kg.tiles_d * N;
     const double eff = ((double)W * H * D) / ((double)kg.tiles_w * kKwW * kg.tiles_h * kKwH * kg.tiles_d * kKdP);
     if (!off && (force || (eff >= 0.8 && kg.items >= 2 * num_sms()))) {
       CUtensorMap tA, tB, tC;
-      if (make_act_tmap(&tA, x, N, D, H, W, 64, kKwW, kKwH, 1)) return -1;
+      if (make_act_tmap(&tA, x, N, D, H, W, Cin, kKwW, kKwH, 1)) return -1;
       if (make_act_tmap(&tC, y, N, D, H, W, 64, kKwW, kKwH, 1)) return -1;
-      if (make_weight_tmap(&tB, wpack, 27, 64, 64, 64)) return -1;
+      if (make_weight_tmap(&tB, wpack, 27, 64, Cin, 64)) return -1;
       static bool attr_set = false;
       if (!attr_set) {
         if (check_cuda(cudaFuncSetAttribute(conv3_kd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKdSmem),
@@ -2338,27 +2343,30 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
   if (warp_id == 5) tmem_dealloc(tmem_base, 64);
 }
 
+// one warp per output element: lanes stride over the per-CTA partials (fp64, fixed order -> deterministic)
 __global__ void wgrad_c1_tc_finalize_kernel(const float* __restrict__ partial, int nctas, int flip, float* dw,
                                             float* sum_c, float* sum_1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 27*64 (dw), then 64 (sum_c), then 1
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 0 .. 27*64 (dw), then 64 (sum_c), then 1
+  const int lane = threadIdx.x & 31;
   const int per = 64 * 64 + 4;
+  if (i > 27 * 64 + 64) return;
+  double a = 0.0;
   if (i < 27 * 64) {
     const int t = i / 64, c = i % 64;
     const int m = flip ? 26 - t : t;
-    double a = 0.0;
-    for (int b = 0; b < nctas; ++b)
+    for (int b = lane; b < nctas; b += 32)
       a += (double)partial[(long long)b * per + m * 64 + c] + (double)partial[(long long)b * per + (32 + m) * 64 + c];
-    dw[c * 27 + t] = (float)a;
   } else if (i < 27 * 64 + 64) {
-    const int c = i - 27 * 64;
-    double a = 0.0;
-    for (int b = 0; b < nctas; ++b) a += (double)partial[(long long)b * per + 27 * 64 + c];
-    if (sum_c) sum_c[c] = (float)a;
-  } else if (i == 27 * 64 + 64) {
-    double a = 0.0;
-    for (int b = 0; b < nctas; ++b) a += (double)partial[(long long)b * per + 64 * 64];
-    if (sum_1) sum_1[0] = (float)a;
+    for (int b = lane; b < nctas; b += 32) a += (double)partial[(long long)b * per + 27 * 64 + (i - 27 * 64)];
+  } else {
+    for (int b = lane; b < nctas; b += 32) a += (double)partial[(long long)b * per + 64 * 64];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane != 0) return;
+  if (i < 27 * 64) dw[(i % 64) * 27 + i / 64] = (float)a;
+  else if (i < 27 * 64 + 64) { if (sum_c) sum_c[i - 27 * 64] = (float)a; }
+  else if (sum_1) sum_1[0] = (float)a;
 }
 
 static constexpr int kWg1Ctas = 148 * 2;
@@ -2383,7 +2391,7 @@ int wgrad_c1_tc(const void* xc, const float* x1, float* dw, float* sum_c, float*
   }
   wgrad_c1_tc_kernel<<<ctas, 192, smem, st>>>(x1, tmXC, N, D, H, W, tiles_w, tiles_h, total, (float*)ws);
   SIVAE_LAUNCH_OK("wgrad_c1_tc_kernel");
-  wgrad_c1_tc_finalize_kernel<<<cdiv(27 * 64 + 64 + 1, 128), 128, 0, st>>>((const float*)ws, ctas, flip, dw, sum_c, sum_1);
+  wgrad_c1_tc_finalize_kernel<<<cdiv(27 * 64 + 64 + 1, 8), 256, 0, st>>>((const float*)ws, ctas, flip, dw, sum_c, sum_1);
   SIVAE_LAUNCH_OK("wgrad_c1_tc_finalize_kernel");
   return 0;
 }

@@ -351,13 +351,18 @@ __global__ void __launch_bounds__(256) wgrad_c1_27_kernel(const __nv_bfloat16* _
   for (int i = threadIdx.x; i < PER; i += blockDim.x) partial[(long long)blockIdx.x * PER + i] = red[i];
 }
 
+// one warp per output element: lanes stride over the per-block partials (fp64, fixed order -> deterministic)
 __global__ void wgrad_c1_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int T, float* dw,
                                          float* sum_c, float* sum_1) {
   const int per = T * C + C + 1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= per) return;
   double a = 0.0;
-  for (int b = 0; b < nblocks; ++b) a += (double)partial[(long long)b * per + i];
+  for (int b = lane; b < nblocks; b += 32) a += (double)partial[(long long)b * per + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane != 0) return;
   if (i < T * C) {
     const int t = i / C, c = i % C;
     dw[c * T + t] = (float)a;
@@ -556,7 +561,7 @@ int wgrad_c1(const void* xc, const float* x1, float* dw, float* sum_c, float* su
 #undef SIVAE_WG1
   SIVAE_LAUNCH_OK("wgrad_c1_kernel");
   const int per = T * C + C + 1;
-  wgrad_c1_finalize_kernel<<<cdiv(per, 128), 128, 0, st>>>(partial, blocks, C, T, dw, sum_c, sum_1);
+  wgrad_c1_finalize_kernel<<<cdiv(per, 8), 256, 0, st>>>(partial, blocks, C, T, dw, sum_c, sum_1);
   SIVAE_LAUNCH_OK("wgrad_c1_finalize_kernel");
   return 0;
 }

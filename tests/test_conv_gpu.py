@@ -17,6 +17,8 @@ SHAPES = [
     (1, 6, 8, 20, 256, 128),      # ragged W
     (1, 20, 24, 20, 64, 128),     # headline mid resolution
     (1, 5, 7, 9, 128, 64),        # every extent odd: overhanging boxes on all sides
+    (2, 8, 16, 24, 128, 64),      # kd-fused kernel with two K blocks per tap (E2a dgrad shape class)
+    (1, 6, 16, 8, 256, 64),       # ... four K blocks
     (1, 1, 1, 1, 64, 64),         # single voxel
     (1, 7, 16, 40, 64, 64),       # 8x16 patches of the persistent kw-slab kernel, odd depth (half-empty depth pair)
     (2, 4, 24, 32, 64, 128),      # ... two output-channel blocks, batch 2
@@ -80,8 +82,9 @@ def test_pack_weights_exact():
 
 @pytest.mark.parametrize("shape", SHAPES)
 def test_fprop(shape, kwmode):
-    if kwmode != "auto" and shape[4] != 64:
-        pytest.skip("kernel choice only exists for Cin = 64")
+    # kd-fused kernel: any Cin with Cout = 64; kw-slab kernel: Cin = 64
+    if (kwmode == "kw_force" and shape[4] != 64) or (kwmode in ("kd_force", "tapwise") and shape[5] != 64 and shape[4] != 64):
+        pytest.skip("no kernel choice for this channel combination")
     x, wt = _mk(*shape)
     wf, _ = K.pack_conv3_weights(wt)
     _check_bf16(K.conv3_igemm(x, wf), S.conv3_igemm(x, wf), f"fprop {shape}")
@@ -91,8 +94,9 @@ def test_fprop(shape, kwmode):
 def test_dgrad_is_conv_transpose(shape, kwmode):
     """dgrad = the same kernel on the flipped/transposed pack; checked against autograd of F.conv3d."""
     n, d, h, w, ci, co = shape
-    if kwmode != "auto" and co != 64:
-        pytest.skip("kernel choice only exists for (GEMM-K) channels = 64")
+    # the kernel sees GEMM-K = co, GEMM-N = ci
+    if (kwmode == "kw_force" and co != 64) or (kwmode in ("kd_force", "tapwise") and ci != 64 and co != 64):
+        pytest.skip("no kernel choice for this channel combination")
     x, wt = _mk(*shape)
     dy = torch.randn(n, d, h, w, co, device=DEV).to(torch.bfloat16)
     _, wd = K.pack_conv3_weights(wt)
