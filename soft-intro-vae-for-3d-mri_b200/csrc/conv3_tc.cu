@@ -762,16 +762,18 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int w0, h0, d, pd, n;
         decode(item, w0, h0, d, pd, n);
         for (int cb = 0; cb < g.cin_blocks; ++cb)      // K block outermost: every (tile, K block) is one A stage
-          for (int ad = 0; ad < 2; ++ad)
-            for (int t = 0; t < kUpSteps; ++t) {
-              const UpStep sh = kUpStepTab[t];
-              if (!sh.new_a) continue;
+          for (int ad = 0; ad < 2; ++ad) {
+#pragma unroll
+            for (int t = 0; t < kUpSteps; ++t) {         // unrolled: the schedule folds into immediates
+              if (!up_step_c(t).new_a) continue;
               const int s = it % kUpAStages;
               mbar_wait(&a_empty[s], ((it / kUpAStages) & 1u) ^ 1u);
               mbar_expect_tx(&a_full[s], kTileBytes);
-              tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], cb * 64, w0 + sh.ow, h0 + sh.oh, d + ad - 1 + pd, n);
+              tma_load_5d(smem + s * kTileBytes, &tmA, &a_full[s], cb * 64, w0 + up_step_c(t).ow, h0 + up_step_c(t).oh,
+                          d + ad - 1 + pd, n);
               ++it;
             }
+          }
       }
     }
   } else if (warp_id == 2) {
@@ -781,19 +783,22 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         const int pd = (int)(item & 1);
         for (int cb = 0; cb < g.cin_blocks; ++cb)
-          for (int ad = 0; ad < 2; ++ad)
-            for (int t = 0; t < kUpSteps; ++t, ++it) {
-              const UpStep sh = kUpStepTab[t];
+          for (int ad = 0; ad < 2; ++ad) {
+#pragma unroll
+            for (int t = 0; t < kUpSteps; ++t, ++it) {   // unrolled: slab indices become base + immediate
               const int s = it % kUpBStages;
               mbar_wait(&b_empty[s], ((it / kUpBStages) & 1u) ^ 1u);
-              mbar_expect_tx(&b_full[s], (uint32_t)sh.n * (64u * 128u));
-              for (int u = 0; u < sh.n; ++u) {
-                const int ph = sh.ph[u], pw = sh.pw[u];
-                const int ah = sh.oh + 1 - ph, aw = sh.ow + 1 - pw;
+              mbar_expect_tx(&b_full[s], (uint32_t)up_step_c(t).n * (64u * 128u));
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (u >= up_step_c(t).n) continue;
+                const int ph = up_step_c(t).ph[u], pw = up_step_c(t).pw[u];
+                const int ah = up_step_c(t).oh + 1 - ph, aw = up_step_c(t).ow + 1 - pw;
                 const int slab = (pd * 4 + ph * 2 + pw) * 8 + ad * 4 + ah * 2 + aw;
                 tma_load_3d(smem_b + s * kUpBSlot + u * (64 * 128), &tmB, &b_full[s], cb * 64, 0, slab);
               }
             }
+          }
       }
     }
   } else if (warp_id == 1) {
