@@ -128,37 +128,45 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
 
   if (warp_id == 0) {
     // ===== TMA producer =====
+    // Nested tap / K-block loops with incremental stage and phase counters: no per-iteration divisions in the single
+    // producing thread (its bookkeeping has to stay well below the ~400 cycles a K block's MMAs take).
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)g.rows * 128u + (uint32_t)B_BYTES;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      int s = 0;
+      uint32_t ph = 0;
+      auto issue = [&](const CUtensorMap* amap, int cb, int ow, int oh, int od, int wtap) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], tx_bytes);
-        const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
-        int od, oh, ow, wtap = tap;
-        const CUtensorMap* amap = &tmA.m[0];
-        if (g.mode == kTapsPlain) {
-          od = tap / 9 - 1; oh = (tap / 3) % 3 - 1; ow = tap % 3 - 1;
-        } else if (g.mode == kTapsUpFprop) {
-          od = (tap >> 2) - 1 + (parity >> 2); oh = ((tap >> 1) & 1) - 1 + ((parity >> 1) & 1); ow = (tap & 1) - 1 + (parity & 1);
-          wtap = parity * 8 + tap;
-        } else {
-          const int pp = tap >> 3, abc = tap & 7;
-          od = -((abc >> 2) - 1 + (pp >> 2)); oh = -(((abc >> 1) & 1) - 1 + ((pp >> 1) & 1)); ow = -((abc & 1) - 1 + (pp & 1));
-          amap = &tmA.m[pp];
-        }
         uint8_t* a_dst = smem + s * STAGE_BYTES;
         tma_load_5d(a_dst, amap, &full_bar[s], cb * 64, w0 + ow, h0 + oh, d0 + od, n);
         tma_load_3d(a_dst + kTileBytes, &tmB, &full_bar[s], cb * 64, nb * BLOCK_N, wtap);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      };
+      if (g.mode == kTapsPlain) {
+        int tap = 0;
+        for (int od = -1; od <= 1; ++od)
+          for (int oh = -1; oh <= 1; ++oh)
+            for (int ow = -1; ow <= 1; ++ow, ++tap)
+              for (int cb = 0; cb < g.cin_blocks; ++cb) issue(&tmA.m[0], cb, ow, oh, od, tap);
+      } else if (g.mode == kTapsUpFprop) {
+        const int pd = parity >> 2, php = (parity >> 1) & 1, pw = parity & 1;
+        for (int tap = 0; tap < 8; ++tap)
+          for (int cb = 0; cb < g.cin_blocks; ++cb)
+            issue(&tmA.m[0], cb, (tap & 1) - 1 + pw, ((tap >> 1) & 1) - 1 + php, (tap >> 2) - 1 + pd, parity * 8 + tap);
+      } else {
+        for (int pp = 0; pp < 8; ++pp)
+          for (int abc = 0; abc < 8; ++abc)
+            for (int cb = 0; cb < g.cin_blocks; ++cb)
+              issue(&tmA.m[pp], cb, -((abc & 1) - 1 + (pp & 1)), -(((abc >> 1) & 1) - 1 + ((pp >> 1) & 1)),
+                    -((abc >> 2) - 1 + (pp >> 2)), pp * 8 + abc);
       }
     }
   } else if (warp_id == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (elect_one()) {
@@ -171,6 +179,7 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA store =====
