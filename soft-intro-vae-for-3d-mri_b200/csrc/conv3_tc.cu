@@ -1012,9 +1012,20 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp_id == 0) {
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
+      // voxel-box coordinates advance incrementally (one 64-bit decode per CTA, none per box)
+      int w0, h0, d0, n;
+      decode_tile(g, kb0, w0, h0, d0, n);
       for (long long kb = kb0; kb < kb1; ++kb) {
-        int w0, h0, d0, n;
-        decode_tile(g, kb, w0, h0, d0, n);
+        if (kb != kb0) {
+          w0 += g.wt;
+          if (w0 >= g.tiles_w * g.wt) {
+            w0 = 0; h0 += g.ht;
+            if (h0 >= g.tiles_h * g.ht) {
+              h0 = 0; d0 += g.dt;
+              if (d0 >= g.tiles_d * g.dt) { d0 = 0; ++n; }
+            }
+          }
+        }
         {
           const int s = b_it % B_STAGES;
           mbar_wait(&b_empty[s], ((b_it / B_STAGES) & 1u) ^ 1u);
@@ -1060,11 +1071,11 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         mbar_wait(&a_full[as], (a_it / A_STAGES) & 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem_a + as * A_STAGE_BYTES);
-          for (int k = 0; k < k16s; ++k) {  // 16 voxel rows (2048 B) per UMMA
-            umma_bf16(tmem_base + (uint32_t)(lp * NT), make_smem_desc(a_addr + k * 2048, g.a_lbo, g.a_sbo),
-                      make_smem_desc(b_addr + k * 2048, g.b_lbo, g.b_sbo), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + as * A_STAGE_BYTES), g.a_lbo, g.a_sbo);
+          const uint64_t bdesc = make_smem_desc(b_addr, g.b_lbo, g.b_sbo);
+          for (int k = 0; k < k16s; ++k)  // 16 voxel rows (2048 B = +128 in the descriptor's address field) per UMMA
+            umma_bf16(tmem_base + (uint32_t)(lp * NT), adesc + 128 * k, bdesc + 128 * k, idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (lp == npairs - 1) {
             umma_commit(&b_empty[bs]);
@@ -1211,7 +1222,7 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_wait(&b_full[bs], (b_it / kWgKwBStages) & 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b_addr = smem_u32(smem_b + bs * kTileBytes);
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kTileBytes), kTileBytes, 1024);
           const bool first = (item == it0 && j == 0);
 #pragma unroll
           for (int acc = 0; acc < 5; ++acc) {
@@ -1219,11 +1230,11 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             const int kd = acc < 3 ? acc : acc - 3;
             const int kh = acc < 3 ? 0 : 2;
             const uint32_t lbo = acc < 3 ? 1024u : (uint32_t)(kKwH + 2) * 1024u;
-            const uint32_t a_addr = a_base + (uint32_t)((kd + j) * (kKwH + 2) + kh) * 1024u;
+            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)((kd + j) * (kKwH + 2) + kh) * 1024u, lbo, 1024);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)   // 16 voxel rows (2048 B) per UMMA
-              umma_bf16(tmem_base + (uint32_t)(acc * 64), make_smem_desc(a_addr + k * 2048, lbo, 1024),
-                        make_smem_desc(b_addr + k * 2048, kTileBytes, 1024), idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 8; ++k)   // 16 voxel rows (2048 B = +128 in the descriptor's address field) per UMMA
+              umma_bf16(tmem_base + (uint32_t)(acc * 64), adesc + 128 * k, bdesc + 128 * k, idesc,
+                        (first && k == 0) ? 0u : 1u);
           }
           umma_commit(&b_empty[bs]);
           if (j == 1) {
