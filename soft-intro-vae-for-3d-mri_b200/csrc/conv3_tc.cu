@@ -1044,7 +1044,7 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           mbar_expect_tx(&a_full[s], tile_tx * nu);
           for (int uu = 0; uu < nu; ++uu) {
             const int u = u0 + uu;
-            const int tap = u / g.cin_blocks, cb = u - tap * g.cin_blocks;
+            const int tap = g.cin_blocks == 1 ? u : u / g.cin_blocks, cb = u - tap * g.cin_blocks;
             int od, oh, ow;
             if (g.mode == kTapsPlain) {
               od = tap / 9 - 1; oh = (tap / 3) % 3 - 1; ow = tap % 3 - 1;
