@@ -1278,6 +1278,161 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp_id == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =================================================================================================
+// wgrad of Upsample(2) + Conv3d, Cin = 64: persistent tall-box split-K kernel (twin of conv3_wgrad_kw64_kernel).
+//
+// dWup[p*8 + abc][ci][co] = sum_v x_lo[v + (ad-1+pd, ah-1+ph, aw-1+pw)][ci] * dy_hi[2v + p][co]   (then
+// wgrad_reduce_up_kernel folds the 64 slabs back onto the 27 taps).  A CTA owns one (ph, pw, aw) combination -- i.e. one
+// in-plane w shift aw-1+pw and the two h shifts ah-1+ph -- and a contiguous range of work items (8 x 16 low-res patch x 2
+// planes).  Per item: ONE tall low-res box {64 ch, 8 w, 18 h, 4 d} (72 KB) and the four dy parity tiles (pd x plane).
+// The unit (pd, ad, ah) of plane j reads the box at byte offset ((j + ad + pd) * 18 + ah + ph) * 1024; ah = 0 / 1 are
+// paired into one M = 128 UMMA through the leading-dimension offset (1 patch row), so four accumulators (pd, ad) x 64
+// fp32 columns stay in TMEM over the whole K range.  Partials use the generic [split][p*8+abc][ci][Cout] layout.
+//   L2 -> SMEM bytes per 128 low-res voxels (all 64 slabs): 64*16 + 8*16 = 1152 KB  ->  8 * (72 + 64) / 2 = 544 KB.
+// =================================================================================================
+struct WgUpGeom {
+  int N, D, H, W;                  // low-res lattice
+  int tiles_w, tiles_h, tiles_d;
+  int ntiles;                      // Cout / 64
+  int Cout;
+  long long items, items_per_split;
+};
+
+__global__ void __launch_bounds__(224, 1)   // 7 warps: X producer, MMA issuer, dy producer, 4 epilogue warps
+upconv3_wgrad_tall_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ TmapPack tmDY,
+                          const WgUpGeom g, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + 2 * kKwABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgKwBStages * kTileBytes);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + kWgKwBStages;
+  uint64_t* tmem_full_bar = b_empty + kWgKwBStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int combo = blockIdx.x & 7;              // (ph, pw, aw)
+  const int ntile = blockIdx.x >> 3;
+  const int ph = combo >> 2, pw = (combo >> 1) & 1, aw = combo & 1;
+  const long long it0 = (long long)blockIdx.y * g.items_per_split;
+  const long long it1 = min(g.items, it0 + g.items_per_split);
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDY.m[ph * 2 + pw]);
+    prefetch_tmap(&tmDY.m[4 + ph * 2 + pw]);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWgKwBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](long long item, int& w0, int& h0, int& d0, int& n) {
+    const int tw = (int)(item % g.tiles_w); item /= g.tiles_w;
+    const int th = (int)(item % g.tiles_h); item /= g.tiles_h;
+    const int td = (int)(item % g.tiles_d);
+    n = (int)(item / g.tiles_d);
+    w0 = tw * kKwW; h0 = th * kKwH; d0 = td * 2;
+  };
+
+  if (warp_id == 0) {
+    // ===== X producer: the tall low-res box of this CTA's w shift =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = it0; item < it1; ++item, ++it) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        const int s = it & 1;
+        mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&a_full[s], kKwABytes);
+        tma_load_5d(smem + s * kKwABytes, &tmX, &a_full[s], 0, w0 + aw - 1 + pw, h0 - 1, d0 - 1, n);
+      }
+    }
+  } else if (warp_id == 2) {
+    // ===== dy producer: parity tiles (pd, ph, pw) of planes d0, d0 + 1 (plane d0 + 1 may be out of range: zero fill) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = it0; item < it1; ++item) {
+        int w0, h0, d0, n;
+        decode(item, w0, h0, d0, n);
+        for (int j = 0; j < 2; ++j)
+          for (int pd = 0; pd < 2; ++pd, ++it) {
+            const int s = it % kWgKwBStages;
+            mbar_wait(&b_empty[s], ((it / kWgKwBStages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], kTileBytes);
+            tma_load_5d(smem_b + s * kTileBytes, &tmDY.m[pd * 4 + ph * 2 + pw], &b_full[s], ntile * 64, w0, h0, d0 + j, n);
+          }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    uint32_t a_it = 0, b_it = 0;
+    for (long long item = it0; item < it1; ++item, ++a_it) {
+      const uint32_t s = a_it & 1;
+      mbar_wait(&a_full[s], (a_it >> 1) & 1u);
+      const uint32_t a_base = smem_u32(smem + s * kKwABytes);
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp, ++b_it) {             // (plane j, depth parity pd), pd fastest
+        const int j = jp >> 1, pd = jp & 1;
+        const uint32_t bs = b_it % kWgKwBStages;
+        mbar_wait(&b_full[bs], (b_it / kWgKwBStages) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kTileBytes), kTileBytes, 1024);
+          const bool first = (item == it0 && j == 0);      // first contribution to the accumulators of this pd
+#pragma unroll
+          for (int ad = 0; ad < 2; ++ad) {
+            // units (pd, ad, ah = 0 | 1): box rows ((j + ad + pd) * 18 + ph + ah) * 8, paired through LBO = one patch row
+            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)((j + ad + pd) * (kKwH + 2) + ph) * 1024u, 1024, 1024);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // 16 voxel rows (2048 B = +128 in the descriptor's address field) per UMMA
+              umma_bf16(tmem_base + (uint32_t)((pd * 2 + ad) * 64), adesc + 128 * k, bdesc + 128 * k, idesc,
+                        (first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&b_empty[bs]);
+          if (jp == 3) {
+            umma_commit(&a_empty[s]);
+            if (item == it1 - 1) umma_commit(tmem_full_bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> fp32 partials [split][p*8 + abc][ci][Cout] =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp_id & 3;
+    const int row = q * 32 + lane;
+    const int ah = row >> 6, ci = row & 63;
+#pragma unroll 1
+    for (int acc = 0; acc < 4; ++acc) {
+      const int pd = acc >> 1, ad = acc & 1;
+      const int unit = (pd * 4 + ph * 2 + pw) * 8 + ad * 4 + ah * 2 + aw;
+      float* dst = partial + (((long long)blockIdx.y * 64 + unit) * 64 + ci) * g.Cout + ntile * 64;
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + jj * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(dst + jj * 32 + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // upsample-fused mode: dw[co][ci][k] = sum_s sum_parity partial[s][(parity*8 + abc(k,parity))*cin_blocks + ci/64][ci%64][co]
 // (the transpose of the weight pre-summation: every 3x3x3 tap receives exactly one contribution per output parity)
 __global__ void wgrad_reduce_up_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
@@ -2546,6 +2701,26 @@ static bool wgrad_kw_plan(int N, int D, int H, int W, int Cin, int Cout, int mod
   return force || (eff >= 0.8 && g.items_per_split >= 8);
 }
 
+// Plan of the persistent tall-box upconv wgrad kernel (SIVAE_UPWGRAD_TALL=0 disables it, =force takes every Cin = 64 shape)
+static bool wgrad_up_plan(int N, int D, int H, int W, int Cin, int Cout, int mode, WgUpGeom& g, int& splits) {
+  if (mode != kTapsUpFprop || Cin != 64 || Cout % 64 != 0) return false;
+  const char* e = getenv("SIVAE_UPWGRAD_TALL");
+  if (e != nullptr && e[0] == '0') return false;
+  const bool force = e != nullptr && e[0] == 'f';
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.tiles_w = cdiv(W, kKwW); g.tiles_h = cdiv(H, kKwH); g.tiles_d = cdiv(D, 2);
+  g.ntiles = Cout / 64;
+  g.Cout = Cout;
+  g.items = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
+  const double eff = ((double)W * H * D) / ((double)g.tiles_w * kKwW * g.tiles_h * kKwH * g.tiles_d * 2);
+  int want = num_sms() / (8 * g.ntiles);
+  if (want < 1) want = 1;
+  if ((long long)want > g.items) want = (int)g.items;
+  g.items_per_split = (g.items + want - 1) / want;
+  splits = (int)((g.items + g.items_per_split - 1) / g.items_per_split);
+  return force || (eff >= 0.8 && g.items_per_split >= 8);
+}
+
 static size_t wgrad_ws_bytes(int N, int D, int H, int W, int Cin, int Cout, int mode) {
   if (Cin % 64 || Cout % 64 || N <= 0) return 0;
   WgradGeom g; int nt, ntiles, splits;
@@ -2555,6 +2730,11 @@ static size_t wgrad_ws_bytes(int N, int D, int H, int W, int Cin, int Cout, int 
   if (wgrad_kw_plan(N, D, H, W, Cin, Cout, mode, kg, ksplits)) {
     const size_t kneed = (size_t)ksplits * 27 * 64 * Cout * sizeof(float);
     if (kneed > need) need = kneed;
+  }
+  WgUpGeom ug; int usplits;
+  if (wgrad_up_plan(N, D, H, W, Cin, Cout, mode, ug, usplits)) {
+    const size_t uneed = (size_t)usplits * 64 * 64 * Cout * sizeof(float);
+    if (uneed > need) need = uneed;
   }
   return need;
 }
@@ -2615,6 +2795,38 @@ static int wgrad_impl(const void* x, const void* dy, float* dw, void* ws, size_t
       int blocks = (int)((total + 255) / 256);
       wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, ksplits, 27, 1, Cin, Cout);
       SIVAE_LAUNCH_OK("wgrad_reduce_kernel");
+      return 0;
+    }
+  }
+  {
+    WgUpGeom ug; int usplits;
+    if (wgrad_up_plan(N, D, H, W, Cin, Cout, mode, ug, usplits)) {
+      const size_t uneed = (size_t)usplits * 64 * 64 * Cout * sizeof(float);
+      SIVAE_CHECK(ws != nullptr && ws_bytes >= uneed, "upconv3_wgrad: workspace too small (%zu < %zu)", ws_bytes, uneed);
+      CUtensorMap tX;
+      TmapPack tDY;
+      {
+        uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+        uint64_t strides[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
+        uint32_t box[5] = {64, (uint32_t)kKwW, (uint32_t)(kKwH + 2), 4, 1};
+        if (make_tmap_bf16(&tX, x, 5, dims, strides, box)) return -1;
+      }
+      for (int p = 0; p < 8; ++p)
+        if (make_parity_tmap(&tDY.m[p], dy, N, D, H, W, Cout, p, kKwW, kKwH, 1)) return -1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(upconv3_wgrad_tall_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kWgKwSmem), "cudaFuncSetAttribute(upconv3_wgrad_tall)")) return -1;
+        attr_set = true;
+      }
+      upconv3_wgrad_tall_kernel<<<dim3(8u * (unsigned)ug.ntiles, (unsigned)usplits), 224, kWgKwSmem, st>>>(tX, tDY, ug,
+                                                                                                         (float*)ws);
+      SIVAE_LAUNCH_OK("upconv3_wgrad_tall_kernel");
+      const long long total = 27ll * Cin * Cout;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      wgrad_reduce_up_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, usplits, 1, Cin, Cout);
+      SIVAE_LAUNCH_OK("wgrad_reduce_up_kernel");
       return 0;
     }
   }

@@ -230,8 +230,27 @@ def test_upconv_dgrad(shape):
     _check_bf16(K.upconv3_dgrad(dy, wupT), S.upconv3_dgrad(dy, wupT), f"upconv dgrad {shape}")
 
 
-@pytest.mark.parametrize("shape", UP_SHAPES)
-def test_upconv_wgrad(shape):
+@pytest.mark.parametrize("mode", ["auto", "force", "0"])
+@pytest.mark.parametrize("shape", UP_SHAPES + [(2, 6, 16, 24, 64, 64), (1, 5, 20, 13, 64, 128), (3, 4, 32, 8, 64, 64)])
+def test_upconv_wgrad(shape, mode):
+    """mode: persistent tall-box kernel by the library's choice / forced for every Cin = 64 shape (ragged patches, odd
+    depth) / generic kernel forced (SIVAE_UPWGRAD_TALL)."""
+    import os
+    n, d, h, w, ci, co = shape
+    if mode != "auto" and ci != 64:
+        pytest.skip("kernel choice only exists for Cin = 64")
+    old = os.environ.pop("SIVAE_UPWGRAD_TALL", None)
+    if mode != "auto":
+        os.environ["SIVAE_UPWGRAD_TALL"] = mode
+    try:
+        _upconv_wgrad_check(shape)
+    finally:
+        os.environ.pop("SIVAE_UPWGRAD_TALL", None)
+        if old is not None:
+            os.environ["SIVAE_UPWGRAD_TALL"] = old
+
+
+def _upconv_wgrad_check(shape):
     n, d, h, w, ci, co = shape
     x, _ = _mk(*shape)
     dy = torch.randn(n, 2 * d, 2 * h, 2 * w, co, device=DEV).to(torch.bfloat16)
