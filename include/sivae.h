@@ -245,6 +245,30 @@ int sivae_mse_persample_bwd(const float* x, const float* y, const float* g, floa
                             int B, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Introspective loss assembly (utils/my_trainer.py:260-284 lossE, :301-321 lossD) on the per-sample [B] vectors
+ * r_* = sum of squared errors (sivae_mse_persample_fwd) and k_* = KL (sivae_kl_persample_fwd).
+ *   lossE = 10*( s*(b_rec*mean(r_real) + b_kl*mean(k_real))
+ *                + 0.5*(mean_b exp(-2s(b_rec*r_fake[b] + b_neg*k_fake[b])) + mean_b exp(-2s(b_rec*r_rec[b] + b_neg*k_rec[b]))) )
+ *   out[5] = {lossE, mean(r_real), mean(k_real), exp_elbo_fake, exp_elbo_rec}
+ *   lossD = 10*s*( b_rec*mean(r_real) + 0.5*b_kl*(mean(k_rec)+mean(k_fake)) + gamma_r*0.5*b_rec*(mean(r_rec_rec)+mean(r_fake_rec)) )
+ *   out[6] = {lossD, mean(r_real), mean(k_rec), mean(k_fake), mean(r_rec_rec), mean(r_fake_rec)}
+ * The backward entry points write d(loss * g[0]) / d(vector); any gradient pointer may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int sivae_intro_loss_e_fwd(const float* r_real, const float* k_real, const float* r_fake, const float* k_fake,
+                           const float* r_rec, const float* k_rec, int B, float scale, float beta_rec, float beta_kl,
+                           float beta_neg, float* out, void* stream);
+int sivae_intro_loss_e_bwd(const float* r_fake, const float* k_fake, const float* r_rec, const float* k_rec,
+                           const float* g, int B, float scale, float beta_rec, float beta_kl, float beta_neg,
+                           float* d_r_real, float* d_k_real, float* d_r_fake, float* d_k_fake, float* d_r_rec,
+                           float* d_k_rec, void* stream);
+int sivae_intro_loss_d_fwd(const float* r_real, const float* k_rec, const float* k_fake, const float* r_rec_rec,
+                           const float* r_fake_rec, int B, float scale, float beta_rec, float beta_kl, float gamma_r,
+                           float* out, void* stream);
+int sivae_intro_loss_d_bwd(const float* g, int B, float scale, float beta_rec, float beta_kl, float gamma_r,
+                           float* d_r_real, float* d_k_rec, float* d_k_fake, float* d_r_rec_rec, float* d_r_fake_rec,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout helpers at the module boundary (used by parity tests and for non-unit channel inputs)
  * ---------------------------------------------------------------------------------------------- */
 /* fp32 NCDHW -> bf16 NDHWC and back */

@@ -291,6 +291,40 @@ def to_ncdhw_f32(x):
     return _ncdhw(x).contiguous()
 
 
+def intro_loss_e_fwd(r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, b_rec, b_kl, b_neg):
+    """utils/my_trainer.py:260-284 on per-sample vectors."""
+    ef = (-2 * scale * (b_rec * r_fake + b_neg * k_fake)).exp().mean()
+    er = (-2 * scale * (b_rec * r_rec + b_neg * k_rec)).exp().mean()
+    m_rr, m_kr = r_real.mean(), k_real.mean()
+    loss = 10 * (scale * (b_rec * m_rr + b_kl * m_kr) + 0.5 * (ef + er))
+    return torch.stack([loss, m_rr, m_kr, ef, er]).float()
+
+
+def intro_loss_e_bwd(r_fake, k_fake, r_rec, k_rec, g, scale, b_rec, b_kl, b_neg):
+    b = r_fake.numel()
+    go = 10.0 * g.reshape(-1)[0] / b
+    ef = (-2 * scale * (b_rec * r_fake + b_neg * k_fake)).exp()
+    er = (-2 * scale * (b_rec * r_rec + b_neg * k_rec)).exp()
+    one = torch.ones(b, dtype=torch.float32, device=r_fake.device)
+    return torch.stack([go * scale * b_rec * one, go * scale * b_kl * one, go * 0.5 * ef * (-2 * scale * b_rec),
+                        go * 0.5 * ef * (-2 * scale * b_neg), go * 0.5 * er * (-2 * scale * b_rec),
+                        go * 0.5 * er * (-2 * scale * b_neg)]).float()
+
+
+def intro_loss_d_fwd(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, b_rec, b_kl, gamma_r):
+    """utils/my_trainer.py:301-321 on per-sample vectors."""
+    m = [t.mean() for t in (r_real, k_rec, k_fake, r_rec_rec, r_fake_rec)]
+    loss = 10 * (scale * (b_rec * m[0] + 0.5 * b_kl * (m[1] + m[2]) + gamma_r * 0.5 * b_rec * (m[3] + m[4])))
+    return torch.stack([loss] + m).float()
+
+
+def intro_loss_d_bwd(g, batch, scale, b_rec, b_kl, gamma_r):
+    go = 10.0 * g.reshape(-1)[0] * scale / batch
+    one = torch.ones(batch, dtype=torch.float32, device=g.device)
+    return torch.stack([go * b_rec * one, go * 0.5 * b_kl * one, go * 0.5 * b_kl * one, go * gamma_r * 0.5 * b_rec * one,
+                        go * gamma_r * 0.5 * b_rec * one]).float()
+
+
 def volume_stats(x):
     v = x.reshape(x.shape[0], -1).double()
     return torch.stack([v.mean(1), v.std(1, unbiased=False), v.min(1).values, v.max(1).values], 1).float()

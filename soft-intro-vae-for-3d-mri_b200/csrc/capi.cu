@@ -102,6 +102,13 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+int intro_loss_e_fwd(const float*, const float*, const float*, const float*, const float*, const float*, int, float, float,
+                     float, float, float*, cudaStream_t);
+int intro_loss_e_bwd(const float*, const float*, const float*, const float*, const float*, int, float, float, float, float,
+                     float*, float*, float*, float*, float*, float*, cudaStream_t);
+int intro_loss_d_fwd(const float*, const float*, const float*, const float*, const float*, int, float, float, float, float,
+                     float*, cudaStream_t);
+int intro_loss_d_bwd(const float*, int, float, float, float, float, float*, float*, float*, float*, float*, cudaStream_t);
 size_t volume_stats_workspace_bytes(int);
 int volume_stats(const float*, int, long long, float*, void*, size_t, cudaStream_t);
 int preprocess_clip_minmax(const float*, float*, int, long long, float, float*, void*, size_t, cudaStream_t);
@@ -299,6 +306,27 @@ int sivae_preprocess_clip_minmax(const float* x, float* y, int B, long long n, f
 int sivae_affine_resample(const float* x, float* y, int B, int D, int H, int W, const float* mats, const float* pad,
                           const float* stats, void* stream) {
   return affine_resample(x, y, B, D, H, W, mats, pad, stats, ST(stream));
+}
+int sivae_intro_loss_e_fwd(const float* r_real, const float* k_real, const float* r_fake, const float* k_fake,
+                           const float* r_rec, const float* k_rec, int B, float scale, float b_rec, float b_kl, float b_neg,
+                           float* out, void* stream) {
+  return intro_loss_e_fwd(r_real, k_real, r_fake, k_fake, r_rec, k_rec, B, scale, b_rec, b_kl, b_neg, out, ST(stream));
+}
+int sivae_intro_loss_e_bwd(const float* r_fake, const float* k_fake, const float* r_rec, const float* k_rec, const float* g,
+                           int B, float scale, float b_rec, float b_kl, float b_neg, float* d_r_real, float* d_k_real,
+                           float* d_r_fake, float* d_k_fake, float* d_r_rec, float* d_k_rec, void* stream) {
+  return intro_loss_e_bwd(r_fake, k_fake, r_rec, k_rec, g, B, scale, b_rec, b_kl, b_neg, d_r_real, d_k_real, d_r_fake,
+                          d_k_fake, d_r_rec, d_k_rec, ST(stream));
+}
+int sivae_intro_loss_d_fwd(const float* r_real, const float* k_rec, const float* k_fake, const float* r_rec_rec,
+                           const float* r_fake_rec, int B, float scale, float b_rec, float b_kl, float gamma_r, float* out,
+                           void* stream) {
+  return intro_loss_d_fwd(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, B, scale, b_rec, b_kl, gamma_r, out, ST(stream));
+}
+int sivae_intro_loss_d_bwd(const float* g, int B, float scale, float b_rec, float b_kl, float gamma_r, float* d_r_real,
+                           float* d_k_rec, float* d_k_fake, float* d_r_rec_rec, float* d_r_fake_rec, void* stream) {
+  return intro_loss_d_bwd(g, B, scale, b_rec, b_kl, gamma_r, d_r_real, d_k_rec, d_k_fake, d_r_rec_rec, d_r_fake_rec,
+                          ST(stream));
 }
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream) {

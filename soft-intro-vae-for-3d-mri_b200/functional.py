@@ -354,6 +354,59 @@ def mse_persample(x, y):
     return _MsePerSample.apply(x, y)
 
 
+class _IntroLossE(torch.autograd.Function):
+    """lossE of utils/my_trainer.py:260-284 from the six per-sample vectors, one kernel forward / one backward.
+    -> (lossE, mean r_real, mean k_real, exp_elbo_fake, exp_elbo_rec); only lossE is differentiable."""
+
+    @staticmethod
+    def forward(ctx, r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, b_rec, b_kl, b_neg):
+        vs = [t.contiguous() for t in (r_real, k_real, r_fake, k_fake, r_rec, k_rec)]
+        out = K.intro_loss_e_fwd(*vs, scale, b_rec, b_kl, b_neg)
+        ctx.save_for_backward(vs[2], vs[3], vs[4], vs[5])
+        ctx.hp = (scale, b_rec, b_kl, b_neg)
+        outs = tuple(out[i] for i in range(5))
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        r_fake, k_fake, r_rec, k_rec = ctx.saved_tensors
+        d = K.intro_loss_e_bwd(r_fake, k_fake, r_rec, k_rec, g.contiguous().reshape(1), *ctx.hp)
+        need = ctx.needs_input_grad
+        return tuple(d[i] if need[i] else None for i in range(6)) + (None, None, None, None)
+
+
+def intro_loss_e(r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, b_rec, b_kl, b_neg):
+    return _IntroLossE.apply(r_real, k_real, r_fake, k_fake, r_rec, k_rec, float(scale), float(b_rec), float(b_kl),
+                             float(b_neg))
+
+
+class _IntroLossD(torch.autograd.Function):
+    """lossD of utils/my_trainer.py:301-321 from the five per-sample vectors.
+    -> (lossD, mean r_real, mean k_rec, mean k_fake, mean r_rec_rec, mean r_fake_rec); only lossD is differentiable."""
+
+    @staticmethod
+    def forward(ctx, r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, b_rec, b_kl, gamma_r):
+        vs = [t.contiguous() for t in (r_real, k_rec, k_fake, r_rec_rec, r_fake_rec)]
+        out = K.intro_loss_d_fwd(*vs, scale, b_rec, b_kl, gamma_r)
+        ctx.batch = vs[0].numel()
+        ctx.hp = (scale, b_rec, b_kl, gamma_r)
+        outs = tuple(out[i] for i in range(6))
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        d = K.intro_loss_d_bwd(g.contiguous().reshape(1), ctx.batch, *ctx.hp)
+        need = ctx.needs_input_grad
+        return tuple(d[i] if need[i] else None for i in range(5)) + (None, None, None, None)
+
+
+def intro_loss_d(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, b_rec, b_kl, gamma_r):
+    return _IntroLossD.apply(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, float(scale), float(b_rec), float(b_kl),
+                             float(gamma_r))
+
+
 class _Head1(torch.autograd.Function):
     """Single 1x1 head (ResNetEncoder.conv, models/models.py:105-108): NDHWC -> fp32 [N,d,h,w]."""
 

@@ -65,8 +65,13 @@ class GraphedTrainStep:
                                         reducer_e, reducer_d)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        # every weight must be (re)packed inside the graph at its first use: drop packs made by the warm-up
-        F._pack_cache.clear()
+        # With optim.FusedAdam the plain bf16 weight packs made by the warm-up stay valid for ever (the update kernel
+        # rewrites them in place, torch's version counter never moves): keep them, so the captured step contains no
+        # first-use pack kernels.  With torch optimisers every weight must be (re)packed inside the graph at its first
+        # use after an update: drop the warm-up packs.
+        self.keep_packs = all(getattr(o, "graph_safe", False) for o in (optimizer_e, optimizer_d))
+        if not self.keep_packs:
+            F._pack_cache.clear()
         if not self.split:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
@@ -85,7 +90,11 @@ class GraphedTrainStep:
             self.out = out
             self.graphs = [g0, g1, g2]
             self.graph = g0
-        F._pack_cache.clear()   # the captured packs live in the graph's private pool; do not reuse them eagerly
+        if not self.keep_packs:
+            F._pack_cache.clear()   # the captured packs live in the graph's private pool; do not reuse them eagerly
+        else:
+            # the graph reads the cached pack tensors by address: pin them for the lifetime of this object
+            self._pinned_packs = [v[3] for v in F._pack_cache.values()]
 
     def __call__(self, real_batch: torch.Tensor, noise_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Copies the batch into the captured input buffers (device or pinned-host source) and replays.

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "sivae_mse_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _sz, _vp]),
     "sivae_mse_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "sivae_adam_step": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _vp]),
+    "sivae_intro_loss_e_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),
+    "sivae_intro_loss_e_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sivae_intro_loss_d_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),
+    "sivae_intro_loss_d_bwd": (_i, [_vp, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sivae_volume_stats_workspace_bytes": (_sz, [_i]),
     "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
@@ -428,6 +432,55 @@ def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int
                                 n, d, h, w, c, slope, resample, _p(mask), p, seed, _p(ws), ws.numel(), _stream(y)),
            "sivae_bn_act_bwd")
     return dconv, dres, (aff[0] if need_affine else None), (aff[1] if need_affine else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# introspective loss assembly on the per-sample [B] vectors (utils/my_trainer.py:260-284, :301-321)
+# ----------------------------------------------------------------------------------------------
+def _vecs(*ts):
+    b = ts[0].numel()
+    for t in ts:
+        _req(t, torch.float32, "per-sample vector")
+        assert t.numel() == b
+    return b
+
+
+def intro_loss_e_fwd(r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, b_rec, b_kl, b_neg) -> torch.Tensor:
+    """-> fp32 [5] = (lossE, mean(r_real), mean(k_real), exp_elbo_fake, exp_elbo_rec)."""
+    b = _vecs(r_real, k_real, r_fake, k_fake, r_rec, k_rec)
+    out = torch.empty(5, dtype=torch.float32, device=r_real.device)
+    _check(_L().sivae_intro_loss_e_fwd(_p(r_real), _p(k_real), _p(r_fake), _p(k_fake), _p(r_rec), _p(k_rec), b, scale,
+                                       b_rec, b_kl, b_neg, _p(out), _stream(r_real)), "sivae_intro_loss_e_fwd")
+    return out
+
+
+def intro_loss_e_bwd(r_fake, k_fake, r_rec, k_rec, g, scale, b_rec, b_kl, b_neg) -> torch.Tensor:
+    """-> fp32 [6, B]: gradients w.r.t. (r_real, k_real, r_fake, k_fake, r_rec, k_rec) of lossE * g."""
+    b = _vecs(r_fake, k_fake, r_rec, k_rec)
+    _req(g, torch.float32, "g")
+    d = torch.empty(6, b, dtype=torch.float32, device=r_fake.device)
+    _check(_L().sivae_intro_loss_e_bwd(_p(r_fake), _p(k_fake), _p(r_rec), _p(k_rec), _p(g), b, scale, b_rec, b_kl, b_neg,
+                                       _p(d[0]), _p(d[1]), _p(d[2]), _p(d[3]), _p(d[4]), _p(d[5]), _stream(r_fake)),
+           "sivae_intro_loss_e_bwd")
+    return d
+
+
+def intro_loss_d_fwd(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, b_rec, b_kl, gamma_r) -> torch.Tensor:
+    """-> fp32 [6] = (lossD, mean(r_real), mean(k_rec), mean(k_fake), mean(r_rec_rec), mean(r_fake_rec))."""
+    b = _vecs(r_real, k_rec, k_fake, r_rec_rec, r_fake_rec)
+    out = torch.empty(6, dtype=torch.float32, device=r_real.device)
+    _check(_L().sivae_intro_loss_d_fwd(_p(r_real), _p(k_rec), _p(k_fake), _p(r_rec_rec), _p(r_fake_rec), b, scale, b_rec,
+                                       b_kl, gamma_r, _p(out), _stream(r_real)), "sivae_intro_loss_d_fwd")
+    return out
+
+
+def intro_loss_d_bwd(g, batch: int, scale, b_rec, b_kl, gamma_r) -> torch.Tensor:
+    """-> fp32 [5, B]: gradients w.r.t. (r_real, k_rec, k_fake, r_rec_rec, r_fake_rec) of lossD * g."""
+    _req(g, torch.float32, "g")
+    d = torch.empty(5, batch, dtype=torch.float32, device=g.device)
+    _check(_L().sivae_intro_loss_d_bwd(_p(g), batch, scale, b_rec, b_kl, gamma_r, _p(d[0]), _p(d[1]), _p(d[2]), _p(d[3]),
+                                       _p(d[4]), _stream(g)), "sivae_intro_loss_d_bwd")
+    return d
 
 
 # ----------------------------------------------------------------------------------------------

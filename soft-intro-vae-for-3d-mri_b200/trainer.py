@@ -93,18 +93,17 @@ def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional
     real_mu, real_logvar = model.encode(real_batch)
     z = model.reparameterize(real_mu, real_logvar)
     rec = model.decode(z)
-    loss_rec = calc_reconstruction_loss(real_batch, rec, reduction="mean")
-    lossE_real_kl = calc_kl(real_logvar, real_mu, reduce="mean")
     rec_mu, rec_logvar, z_rec, rec_rec = model.forward(rec.detach())
     fake_mu, fake_logvar, z_fake, rec_fake = model.forward(fake.detach())
-    fake_kl_e = calc_kl(fake_logvar, fake_mu, reduce="none")
-    rec_kl_e = calc_kl(rec_logvar, rec_mu, reduce="none")
-    loss_fake_rec = calc_reconstruction_loss(fake, rec_fake, reduction="none")
-    loss_rec_rec = calc_reconstruction_loss(rec, rec_rec, reduction="none")      # rec NOT detached (Q13)
-    exp_elbo_fake = (-2 * scale * (beta_rec * loss_fake_rec + beta_neg * fake_kl_e)).exp().mean()
-    exp_elbo_rec = (-2 * scale * (beta_rec * loss_rec_rec + beta_neg * rec_kl_e)).exp().mean()
-    lossE = scale * (beta_rec * loss_rec + beta_kl * lossE_real_kl) + 0.5 * (exp_elbo_fake + exp_elbo_rec)
-    lossE = lossE * 10
+    # per-sample vectors (the mse / kl kernels), then the whole :260-284 assembly in one fused kernel
+    r_real = F.mse_persample(real_batch, rec)
+    k_real = F.kl_persample(real_mu, real_logvar)
+    k_fake = F.kl_persample(fake_mu, fake_logvar)
+    k_rec = F.kl_persample(rec_mu, rec_logvar)
+    r_fake = F.mse_persample(fake, rec_fake)
+    r_rec = F.mse_persample(rec, rec_rec)                                        # rec NOT detached (Q13)
+    lossE, loss_rec, lossE_real_kl, exp_elbo_fake, exp_elbo_rec = F.intro_loss_e(
+        r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, beta_rec, beta_kl, beta_neg)
     _zero_grad(optimizer_e, reducer_e)
     lossE.backward()
     out = dict(lossE=lossE.detach(), loss_rec=loss_rec.detach(), kl_real=lossE_real_kl.detach(),
@@ -122,20 +121,19 @@ def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optio
     _set_requires_grad(model.decoder, True)
     fake = model.decode(noise_batch)
     rec = model.decode(z.detach())
-    loss_rec = calc_reconstruction_loss(real_batch, rec, reduction="mean")
     rec_mu, rec_logvar = model.encode(rec)
     z_rec = model.reparameterize(rec_mu, rec_logvar)
     fake_mu, fake_logvar = model.encode(fake)
     z_fake = model.reparameterize(fake_mu, fake_logvar)
     rec_rec = model.decode(z_rec.detach())
     rec_fake = model.decode(z_fake.detach())
-    loss_rec_rec = calc_reconstruction_loss(rec.detach(), rec_rec, reduction="mean")
-    loss_fake_rec = calc_reconstruction_loss(fake.detach(), rec_fake, reduction="mean")
-    rec_kl = calc_kl(rec_logvar, rec_mu, reduce="mean")
-    fake_kl = calc_kl(fake_logvar, fake_mu, reduce="mean")
-    lossD = scale * (beta_rec * loss_rec + 0.5 * beta_kl * (rec_kl + fake_kl)
-                     + gamma_r * 0.5 * beta_rec * (loss_rec_rec + loss_fake_rec))
-    lossD = lossD * 10
+    r_real = F.mse_persample(real_batch, rec)
+    r_rec_rec = F.mse_persample(rec.detach(), rec_rec)
+    r_fake_rec = F.mse_persample(fake.detach(), rec_fake)
+    k_rec = F.kl_persample(rec_mu, rec_logvar)
+    k_fake = F.kl_persample(fake_mu, fake_logvar)
+    lossD, loss_rec, rec_kl, fake_kl, loss_rec_rec, loss_fake_rec = F.intro_loss_d(
+        r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, beta_rec, beta_kl, gamma_r)
     _zero_grad(optimizer_d, reducer_d)
     lossD.backward()
     return dict(lossD=lossD.detach(), loss_rec_d=loss_rec.detach(), rec_kl=rec_kl.detach(), fake_kl=fake_kl.detach(),

@@ -252,3 +252,46 @@ def test_argument_errors_are_reported():
         K.bn_act_fwd(bf(1, 3, 4, 4, 64), torch.ones(64, device=DEV), torch.zeros(64, device=DEV), None, 0.2, 1)  # odd D
     with pytest.raises(K.SivaeError):
         K.reparam_fwd(torch.zeros(4), torch.zeros(4), 0.1)             # CPU tensor
+
+
+# ------------------------------------------------------------------------------------------- loss assembly
+@pytest.mark.parametrize("B", [1, 8, 37])
+def test_intro_loss_assembly_vs_torch_autograd(B):
+    """Fused lossE / lossD assembly (utils/my_trainer.py:260-284, :301-321) and its gradients against the same
+    expressions written with torch ops + autograd."""
+    from sivae_b200 import functional as F
+    torch.manual_seed(B)
+    scale, b_rec, b_kl, b_neg, gamma_r = 8.0 / 614400, 1.0, 0.75, 1024.0, 1e-8
+
+    def vec(lo, hi):
+        return (torch.rand(B, device=DEV) * (hi - lo) + lo).requires_grad_(True)
+
+    # E: magnitudes as at the start of training (r ~ 2e5, k ~ 2e3) -- the exp-ELBO terms then underflow towards 1e-26;
+    # a second set with small values exercises the exponential branch at O(1)
+    for (r_lo, r_hi, k_lo, k_hi) in ((1e5, 4e5, 5e2, 4e3), (1e2, 5e3, 1.0, 30.0)):
+        vs = [vec(r_lo, r_hi), vec(k_lo, k_hi), vec(r_lo, r_hi), vec(k_lo, k_hi), vec(r_lo, r_hi), vec(k_lo, k_hi)]
+        r_real, k_real, r_fake, k_fake, r_rec, k_rec = vs
+        ef = (-2 * scale * (b_rec * r_fake + b_neg * k_fake)).exp().mean()
+        er = (-2 * scale * (b_rec * r_rec + b_neg * k_rec)).exp().mean()
+        ref = 10 * (scale * (b_rec * r_real.mean() + b_kl * k_real.mean()) + 0.5 * (ef + er))
+        gref = torch.autograd.grad(ref, vs)
+        vs2 = [v.detach().clone().requires_grad_(True) for v in vs]
+        got, m_rr, m_kr, gef, ger = F.intro_loss_e(*vs2, scale, b_rec, b_kl, b_neg)
+        ggot = torch.autograd.grad(got, vs2)
+        assert float(got) == pytest.approx(float(ref), rel=2e-6)
+        assert float(gef) == pytest.approx(float(ef), rel=1e-5, abs=1e-37) and float(ger) == pytest.approx(float(er), rel=1e-5, abs=1e-37)
+        assert float(m_rr) == pytest.approx(float(r_real.mean()), rel=2e-6)
+        for a, b in zip(ggot, gref):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-30), float((a - b).abs().max())
+    vs = [vec(1e5, 4e5), vec(5e2, 4e3), vec(5e2, 4e3), vec(1e5, 4e5), vec(1e5, 4e5)]
+    r_real, k_rec, k_fake, r_rr, r_fr = vs
+    ref = 10 * (scale * (b_rec * r_real.mean() + 0.5 * b_kl * (k_rec.mean() + k_fake.mean())
+                         + gamma_r * 0.5 * b_rec * (r_rr.mean() + r_fr.mean())))
+    gref = torch.autograd.grad(ref, vs)
+    vs2 = [v.detach().clone().requires_grad_(True) for v in vs]
+    outs = F.intro_loss_d(*vs2, scale, b_rec, b_kl, gamma_r)
+    ggot = torch.autograd.grad(outs[0], vs2)
+    assert float(outs[0]) == pytest.approx(float(ref), rel=2e-6)
+    assert float(outs[2]) == pytest.approx(float(k_rec.mean()), rel=2e-6)
+    for a, b in zip(ggot, gref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-30)
