@@ -142,6 +142,16 @@ int sivae_bn_train_coeffs(const void* y_bf16, long long nvox, int C,
                           float* mean, float* invstd, float* scale, float* shift,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Train-mode BatchNorm3d statistics + coefficients + apply (+ residual) + (Leaky)ReLU in ONE call, no resampling and no
+ * dropout (models/models.py:18-19, :22 + :39-41): out = act(bn(y) (+ res)); mean / invstd / scale / shift and the running
+ * statistics as sivae_bn_train_coeffs.  Tensors up to 3 Mi elements run as a single launch of one 16-CTA thread-block
+ * cluster (partials exchanged through distributed shared memory); larger ones as statistics / finalize / apply.
+ * workspace: sivae_bn_workspace_bytes(C). */
+int sivae_bn_train_act_fwd(const void* y_bf16, const void* res_bf16, void* out_bf16, int N, int D, int H, int W, int C,
+                           const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           long long* num_batches_tracked, float momentum, float eps, float slope,
+                           float* mean, float* invstd, float* scale, float* shift,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* out = resample( dropout( act( y*scale[c]+shift[c] (+ res) ) ) )
  *   act(t) = t>0 ? t : slope*t        (slope 0.2 = LeakyReLU(0.2), slope 0 = ReLU)
  *   dropout: keep-mask (uint8 NDHWC, 0/1) if mask != NULL, else Philox(seed) if p > 0, else none;

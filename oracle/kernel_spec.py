@@ -188,6 +188,14 @@ def bn_act_fwd(y, scale, shift, res, slope, resample, mask=None, p=0.0, seed=0):
     return _resample(a, resample).contiguous().to(y.dtype)
 
 
+SMALL_BN_ELEMS = 3 << 20
+
+
+def bn_train_act_fwd(y, res, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, slope):
+    mean, invstd, scale, shift = bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps)
+    return bn_act_fwd(y, scale, shift, res, slope, 0), mean, invstd
+
+
 def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope, resample, mask=None, p=0.0, seed=0,
                need_dres=False, need_affine=True):
     c = y.shape[-1]

@@ -102,6 +102,8 @@ size_t mse_workspace_bytes(int, long long);
 int mse_persample_fwd(const float*, const float*, float*, int, long long, void*, size_t, cudaStream_t);
 int mse_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, cudaStream_t);
 int adam_step(const sivae_adam_tensor*, int, const float*, float, float, float, long long*, cudaStream_t);
+int bn_train_act_fwd(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, float*, float*,
+                     long long*, float, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 int intro_loss_e_fwd(const float*, const float*, const float*, const float*, const float*, const float*, int, float, float,
                      float, float, float*, cudaStream_t);
 int intro_loss_e_bwd(const float*, const float*, const float*, const float*, const float*, int, float, float, float, float,
@@ -327,6 +329,12 @@ int sivae_intro_loss_d_bwd(const float* g, int B, float scale, float b_rec, floa
                            float* d_k_rec, float* d_k_fake, float* d_r_rec_rec, float* d_r_fake_rec, void* stream) {
   return intro_loss_d_bwd(g, B, scale, b_rec, b_kl, gamma_r, d_r_real, d_k_rec, d_k_fake, d_r_rec_rec, d_r_fake_rec,
                           ST(stream));
+}
+int sivae_bn_train_act_fwd(const void* y, const void* res, void* out, int N, int D, int H, int W, int C, const float* gamma,
+                           const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps, float slope,
+                           float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes, void* stream) {
+  return bn_train_act_fwd(y, res, out, N, D, H, W, C, gamma, beta, rm, rv, nbt, momentum, eps, slope, mean, invstd, scale,
+                          shift, ws, ws_bytes, ST(stream));
 }
 int sivae_adam_step(const sivae_adam_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2,
                     float eps, long long* step, void* stream) {

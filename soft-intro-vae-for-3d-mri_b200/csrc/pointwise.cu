@@ -8,6 +8,8 @@
 
 #include "sivae_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace sivae {
 
 static constexpr int kBnThreads = 256;
@@ -781,6 +783,301 @@ int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, co
   return 0;
 }
 
+// =================================================================================================
+// Small tensors (the 256-channel layers at the latent resolution: 2.4 M elements, 4.9 MB): the three launches
+// statistics -> finalize -> apply (and reduce -> finalize -> apply in backward) cost ~20 us, mostly launch latency and
+// tails.  One thread-block CLUSTER of 16 CTAs does all three phases in a single launch: every CTA reduces its slice of the
+// voxels, the per-channel partials are exchanged through distributed shared memory (cluster.map_shared_rank) between two
+// cluster barriers, and the second pass over the slice hits L2.  Deterministic (fixed rank order, fp64 finalize).
+// =================================================================================================
+namespace cg = cooperative_groups;
+static constexpr int kSmallCluster = 16, kSmallThreads = 512, kSmallMaxC = 256, kSmallUnroll = 4;
+static constexpr long long kSmallMaxElems = 3ll << 20;     // 3 Mi elements (6 MB of bf16)
+
+struct SmallSlice { long long v0, v1; };
+__device__ __forceinline__ SmallSlice small_slice(long long nvox, unsigned rank) {
+  const long long per = (nvox + kSmallCluster - 1) / kSmallCluster;
+  SmallSlice s;
+  s.v0 = per * rank;
+  s.v1 = s.v0 + per < nvox ? s.v0 + per : nvox;
+  if (s.v0 > nvox) s.v0 = nvox;
+  return s;
+}
+
+// block-level reduction of per-thread (a[8], b[8]) over the threads that share a channel chunk -> part[0][c], part[1][c]
+__device__ __forceinline__ void small_block_reduce(const float (&a)[8], const float (&b)[8], int C, int cpc,
+                                                   float (*red)[17], float (*part)[kSmallMaxC]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = a[k];
+    red[threadIdx.x][8 + k] = b[k];
+  }
+  __syncthreads();
+  const int lanes_v = kSmallThreads / cpc;
+  for (int j = threadIdx.x; j < C; j += kSmallThreads) {
+    const int chunk = j >> 3, k = j & 7;
+    float x = 0.f, y = 0.f;
+    for (int lv = 0; lv < lanes_v; ++lv) {
+      x += red[lv * cpc + chunk][k];
+      y += red[lv * cpc + chunk][8 + k];
+    }
+    part[0][j] = x;
+    part[1][j] = y;
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+bn_small_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
+                    __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                    float* __restrict__ mean_o, float* __restrict__ invstd_o, float* __restrict__ scale_o,
+                    float* __restrict__ shift_o, long long nvox, int C, float slope) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  __shared__ float red[kSmallThreads][17];
+  __shared__ float part[2][kSmallMaxC];
+  __shared__ float sc_s[kSmallMaxC], sh_s[kSmallMaxC];
+  const int cpc = C >> 3, chunk = threadIdx.x % cpc, lanes_v = kSmallThreads / cpc;
+  const SmallSlice sl = small_slice(nvox, rank);
+  // ---- phase 1: per-channel sums of this CTA's voxel slice
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long v = sl.v0 + threadIdx.x / cpc; v < sl.v1; v += (long long)lanes_v * kSmallUnroll) {
+    uint4 raw[kSmallUnroll];
+#pragma unroll
+    for (int u = 0; u < kSmallUnroll; ++u)
+      if (v + (long long)u * lanes_v < sl.v1) raw[u] = *reinterpret_cast<const uint4*>(y + (v + (long long)u * lanes_v) * C + chunk * 8);
+#pragma unroll
+    for (int u = 0; u < kSmallUnroll; ++u)
+      if (v + (long long)u * lanes_v < sl.v1) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += f[k];
+          s2[k] = fmaf(f[k], f[k], s2[k]);
+        }
+      }
+  }
+  small_block_reduce(s1, s2, C, cpc, red, part);
+  cluster.sync();
+  // ---- phase 2: every CTA reduces the 16 partial rows (fixed rank order) and derives scale / shift
+  for (int c = threadIdx.x; c < C; c += kSmallThreads) {
+    double a = 0.0, b = 0.0;
+    for (unsigned r = 0; r < kSmallCluster; ++r) {
+      const float* rp = cluster.map_shared_rank(&part[0][0], r);
+      a += (double)rp[c];
+      b += (double)rp[kSmallMaxC + c];
+    }
+    const double n = (double)nvox, mean = a / n;
+    double var = b / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    sc_s[c] = g * invstd;
+    sh_s[c] = bt - (float)mean * g * invstd;
+    if (rank == 0) {
+      mean_o[c] = (float)mean;
+      invstd_o[c] = invstd;
+      scale_o[c] = sc_s[c];
+      shift_o[c] = sh_s[c];
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) {
+        const double unb = nvox > 1 ? var * n / (n - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+      }
+    }
+  }
+  if (rank == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+  cluster.sync();     // remote reads are finished before any CTA may exit; sc_s / sh_s visible block-wide
+  // ---- phase 3: apply (second pass over the slice: L2 hits)
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = sc_s[chunk * 8 + k]; sh[k] = sh_s[chunk * 8 + k]; }
+  for (long long v = sl.v0 + threadIdx.x / cpc; v < sl.v1; v += (long long)lanes_v * kSmallUnroll) {
+    uint4 ry[kSmallUnroll], rr[kSmallUnroll];
+#pragma unroll
+    for (int u = 0; u < kSmallUnroll; ++u) {
+      const long long vv = v + (long long)u * lanes_v;
+      if (vv < sl.v1) {
+        ry[u] = *reinterpret_cast<const uint4*>(y + vv * C + chunk * 8);
+        if (res != nullptr) rr[u] = *reinterpret_cast<const uint4*>(res + vv * C + chunk * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSmallUnroll; ++u) {
+      const long long vv = v + (long long)u * lanes_v;
+      if (vv < sl.v1) {
+        float f[8], a[8];
+        unpack8(ry[u], f);
+        if (res != nullptr) {
+          float r[8];
+          unpack8(rr[u], r);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]) + r[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = f[k] > 0.f ? f[k] : slope * f[k];
+        st8(out + vv * C + chunk * 8, a);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+bn_small_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ res, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    __nv_bfloat16* __restrict__ dconv, __nv_bfloat16* __restrict__ dres, float* dgamma, float* dbeta,
+                    long long nvox, int C, float slope) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  __shared__ float red[kSmallThreads][17];
+  __shared__ float part[2][kSmallMaxC];
+  __shared__ float c1_s[kSmallMaxC], c2_s[kSmallMaxC];
+  const int cpc = C >> 3, chunk = threadIdx.x % cpc, lanes_v = kSmallThreads / cpc;
+  const SmallSlice sl = small_slice(nvox, rank);
+  float mu[8], is[8], ga[8], be[8];
+  ldf8(mean + chunk * 8, mu); ldf8(invstd + chunk * 8, is); ldf8(gamma + chunk * 8, ga); ldf8(beta + chunk * 8, be);
+  // dt = g * act'(bn(y) (+ res)),  xhat = (y - mean) * invstd
+  auto elem = [&](const uint4& ry, const uint4& rg, const uint4& rr, float (&dt)[8], float (&xh)[8]) {
+    float f[8], gp[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unpack8(ry, f);
+    unpack8(rg, gp);
+    if (res != nullptr) unpack8(rr, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      xh[k] = (f[k] - mu[k]) * is[k];
+      const float t = fmaf(xh[k], ga[k], be[k]) + r[k];
+      dt[k] = gp[k] * (t > 0.f ? 1.f : slope);
+    }
+  };
+  // ---- phase 1: sum(dt), sum(dt * xhat)
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long v = sl.v0 + threadIdx.x / cpc; v < sl.v1; v += (long long)lanes_v * 2) {
+    uint4 ry[2], rg[2], rr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long vv = v + (long long)u * lanes_v;
+      if (vv < sl.v1) {
+        ry[u] = *reinterpret_cast<const uint4*>(y + vv * C + chunk * 8);
+        rg[u] = *reinterpret_cast<const uint4*>(g + vv * C + chunk * 8);
+        if (res != nullptr) rr[u] = *reinterpret_cast<const uint4*>(res + vv * C + chunk * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (v + (long long)u * lanes_v < sl.v1) {
+        float dt[8], xh[8];
+        elem(ry[u], rg[u], rr[u], dt, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += dt[k];
+          s2[k] = fmaf(dt[k], xh[k], s2[k]);
+        }
+      }
+  }
+  small_block_reduce(s1, s2, C, cpc, red, part);
+  cluster.sync();
+  for (int c = threadIdx.x; c < C; c += kSmallThreads) {
+    double a = 0.0, b = 0.0;
+    for (unsigned r = 0; r < kSmallCluster; ++r) {
+      const float* rp = cluster.map_shared_rank(&part[0][0], r);
+      a += (double)rp[c];
+      b += (double)rp[kSmallMaxC + c];
+    }
+    c1_s[c] = (float)(a / (double)nvox);
+    c2_s[c] = (float)(b / (double)nvox);
+    if (rank == 0) {
+      if (dbeta) dbeta[c] = (float)a;
+      if (dgamma) dgamma[c] = (float)b;
+    }
+  }
+  cluster.sync();
+  // ---- phase 3: dconv = gamma * invstd * (dt - mean(dt) - xhat * mean(dt * xhat)),  dres = dt
+  float c1[8], c2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { c1[k] = c1_s[chunk * 8 + k]; c2[k] = c2_s[chunk * 8 + k]; }
+  for (long long v = sl.v0 + threadIdx.x / cpc; v < sl.v1; v += (long long)lanes_v * 2) {
+    uint4 ry[2], rg[2], rr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long vv = v + (long long)u * lanes_v;
+      if (vv < sl.v1) {
+        ry[u] = *reinterpret_cast<const uint4*>(y + vv * C + chunk * 8);
+        rg[u] = *reinterpret_cast<const uint4*>(g + vv * C + chunk * 8);
+        if (res != nullptr) rr[u] = *reinterpret_cast<const uint4*>(res + vv * C + chunk * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long vv = v + (long long)u * lanes_v;
+      if (vv < sl.v1) {
+        float dt[8], xh[8], o[8];
+        elem(ry[u], rg[u], rr[u], dt, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ga[k] * is[k] * (dt[k] - c1[k] - xh[k] * c2[k]);
+        st8(dconv + vv * C + chunk * 8, o);
+        if (dres != nullptr) st8(dres + vv * C + chunk * 8, dt);
+      }
+    }
+  }
+}
+
+static bool small_path_ok(long long nvox, int C) {
+  const bool disabled = getenv("SIVAE_NO_BN_CLUSTER") != nullptr;   // parity tests compare both paths
+  return !disabled && C <= kSmallMaxC && C >= 8 && (kSmallThreads % (C / 8)) == 0 && nvox * C <= kSmallMaxElems &&
+         nvox >= kSmallCluster;
+}
+
+template <class Kernel, class... Args>
+static int launch_small_cluster(Kernel kernel, const char* name, cudaStream_t st, Args... args) {
+  static bool attr_set[2] = {false, false};
+  (void)attr_set;
+  if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), name)) return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kSmallCluster, 1, 1);
+  cfg.blockDim = dim3(kSmallThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kSmallCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (check_cuda(cudaLaunchKernelEx(&cfg, kernel, args...), name)) return -1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// Train-mode BatchNorm statistics + coefficients + apply (+ residual, (Leaky)ReLU) in one call; no resampling, no
+// dropout.  Small tensors take the single-launch cluster kernel, larger ones the statistics / finalize / apply kernels.
+int bn_act_fwd(const void* y, const float* scale, const float* shift, const void* res, void* out, int N, int D, int H,
+               int W, int C, float slope, int resample, const uint8_t* mask, float p, unsigned long long seed,
+               cudaStream_t st);
+int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, const float* beta, float* rm, float* rv,
+                    long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+int bn_train_act_fwd(const void* y, const void* res, void* out, int N, int D, int H, int W, int C, const float* gamma,
+                     const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps, float slope,
+                     float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SIVAE_CHECK(channels_ok(C), "bn_train_act_fwd: unsupported channel count %d", C);
+  const long long nvox = (long long)N * D * H * W;
+  SIVAE_CHECK(nvox > 0, "bn_train_act_fwd: empty tensor");
+  if (small_path_ok(nvox, C))
+    return launch_small_cluster(bn_small_fwd_kernel, "bn_small_fwd_kernel", st, (const __nv_bfloat16*)y,
+                                (const __nv_bfloat16*)res, (__nv_bfloat16*)out, gamma, beta, rm, rv, nbt, momentum, eps,
+                                mean, invstd, scale, shift, nvox, C, slope);
+  if (int rc = bn_train_coeffs(y, nvox, C, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift, ws,
+                               ws_bytes, st))
+    return rc;
+  return bn_act_fwd(y, scale, shift, res, out, N, D, H, W, C, slope, SIVAE_RESAMPLE_NONE, nullptr, 0.f, 0ull, st);
+}
+
 int bn_coeffs_from_partials(const float* partial, int nblocks, long long nvox, int C, const float* gamma,
                             const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
                             float* mean, float* invstd, float* scale, float* shift, cudaStream_t st) {
@@ -835,6 +1132,10 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   float* partial = (float*)ws;
   float* coef = partial + (size_t)kBnMaxBlocks * 2 * C;
   const __nv_bfloat16 *gg = (const __nv_bfloat16*)g, *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
+  if (resample == SIVAE_RESAMPLE_NONE && mask == nullptr && p <= 0.f && small_path_ok(nvox, C))
+    return launch_small_cluster(bn_small_bwd_kernel, "bn_small_bwd_kernel", st, (const __nv_bfloat16*)g,
+                                (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, mean, invstd, gamma, beta,
+                                (__nv_bfloat16*)dconv, (__nv_bfloat16*)dres, dgamma, dbeta, nvox, C, slope);
   const bool plain = resample == SIVAE_RESAMPLE_NONE && res == nullptr && mask == nullptr && dres == nullptr;
   if (plain) {
     const SeedRef sr = make_seed_ref(seed);

@@ -142,6 +142,16 @@ class _ConvBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, res, bn: BnState, slope: float, resample: int, pre_up: bool):
         wf, wd = _packed(weight, pre_up)
+        small = (bn.training and resample == K.RESAMPLE_NONE
+                 and x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * (8 if pre_up else 1) * wf.shape[1] <= K.SMALL_BN_ELEMS)
+        if small:
+            # small layers (latent resolution): convolution, then statistics + coefficients + apply as ONE cluster launch
+            y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
+            out, mean, invstd = K.bn_train_act_fwd(y, res, gamma, beta, bn.running_mean, bn.running_var,
+                                                   bn.num_batches_tracked, bn.momentum, bn.eps, slope)
+            ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
+            ctx.cfg = (slope, resample, bn.training, pre_up)
+            return out
         if bn.training:
             # convolution + batch statistics in one C-ABI call (the sums come out of the conv epilogue)
             conv_bn = K.upconv3_fprop_bn if pre_up else K.conv3_igemm_bn

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "sivae_conv3_to1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _u64, _vp, _sz, _vp]),
     "sivae_bn_workspace_bytes": (_sz, [_i]),
     "sivae_bn_train_coeffs": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sivae_bn_train_act_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp,
+                                    _vp, _vp, _sz, _vp]),
     "sivae_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _f, _u64, _vp]),
     "sivae_bn_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i,
                               _vp, _f, _u64, _vp, _sz, _vp]),
@@ -413,6 +415,31 @@ def bn_act_fwd(y, scale, shift, res, slope: float, resample: int, mask=None, p: 
     _check(_L().sivae_bn_act_fwd(_p(y), _p(scale), _p(shift), _p(res), _p(out), n, d, h, w, c, slope, resample,
                                  _p(mask), p, seed, _stream(y)), "sivae_bn_act_fwd")
     return out
+
+
+SMALL_BN_ELEMS = 3 << 20     # tensors up to this size take the single-launch cluster kernel of sivae_bn_train_act_fwd
+
+
+def bn_train_act_fwd(y, res, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float, eps: float,
+                     slope: float):
+    """out = act(bn_train(y) (+ res)) with the batch statistics, coefficients and the apply in one C-ABI call
+    (single launch for small tensors).  -> (out, mean, invstd)."""
+    _req(y, torch.bfloat16, "y")
+    n, d, h, w, c = y.shape
+    if res is not None:
+        _req(res, torch.bfloat16, "res")
+        assert res.shape == y.shape
+    if num_batches_tracked is not None:
+        _req(num_batches_tracked, torch.int64, "num_batches_tracked")
+    lib = _L()
+    ws = _workspace(y.device, lib.sivae_bn_workspace_bytes(c), "bn")
+    out = torch.empty_like(y)
+    coef = torch.empty(4, c, dtype=torch.float32, device=y.device)
+    _check(lib.sivae_bn_train_act_fwd(_p(y), _p(res), _p(out), n, d, h, w, c, _p(gamma), _p(beta), _p(running_mean),
+                                      _p(running_var), _p(num_batches_tracked), momentum, eps, slope, _p(coef[0]),
+                                      _p(coef[1]), _p(coef[2]), _p(coef[3]), _p(ws), ws.numel(), _stream(y)),
+           "sivae_bn_train_act_fwd")
+    return out, coef[0], coef[1]
 
 
 def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int, mask=None, p: float = 0.0,

@@ -295,3 +295,48 @@ def test_intro_loss_assembly_vs_torch_autograd(B):
     assert float(outs[2]) == pytest.approx(float(k_rec.mean()), rel=2e-6)
     for a, b in zip(ggot, gref):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-30)
+
+
+# ------------------------------------------------------------------------------------------- cluster-fused small BN
+@pytest.mark.parametrize("shape", [(8, 10, 12, 10, 256), (2, 5, 6, 5, 128), (1, 4, 4, 4, 64), (3, 7, 9, 11, 256), (1, 2, 2, 4, 8)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bn_cluster_small_tensors(shape, with_res):
+    """sivae_bn_train_act_fwd / sivae_bn_act_bwd on small tensors run as ONE launch of a 16-CTA cluster (partials through
+    distributed shared memory).  Must agree with the specification and with the generic multi-kernel path
+    (SIVAE_NO_BN_CLUSTER=1), including running statistics, ragged voxel slices and the residual branch."""
+    import os
+    n, d, h, w, c = shape
+    y, g = bf(*shape), bf(*shape)
+    res = bf(*shape) if with_res else None
+    gamma, beta = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV)
+
+    def run():
+        rm, rv, nbt = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+        out, mean, invstd = K.bn_train_act_fwd(y, res, gamma, beta, rm, rv, nbt, 0.1, 1e-5, 0.2)
+        dconv, dres, dgam, dbet = K.bn_act_bwd(g, y, res, mean, invstd, gamma, beta, 0.2, 0, need_dres=with_res)
+        return out, mean, invstd, rm, rv, int(nbt), dconv, dres, dgam, dbet
+
+    old = os.environ.pop("SIVAE_NO_BN_CLUSTER", None)
+    try:
+        a = run()
+        os.environ["SIVAE_NO_BN_CLUSTER"] = "1"
+        b = run()
+    finally:
+        os.environ.pop("SIVAE_NO_BN_CLUSTER", None)
+        if old is not None:
+            os.environ["SIVAE_NO_BN_CLUSTER"] = old
+    rm, rv, nbt = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+    s_out, s_mean, s_invstd = S.bn_train_act_fwd(y, res, gamma, beta, rm, rv, nbt, 0.1, 1e-5, 0.2)
+    s_dconv, s_dres, s_dgam, s_dbet = S.bn_act_bwd(g, y, res, s_mean, s_invstd, gamma, beta, 0.2, 0, need_dres=with_res)
+    for got in (a, b):
+        assert_bf16_close(got[0], s_out, "out")
+        assert_f32_close(got[1], s_mean, "mean", 1e-5)
+        assert_f32_close(got[2], s_invstd, "invstd", 1e-5)
+        assert_f32_close(got[3], rm, "running_mean", 1e-5)
+        assert_f32_close(got[4], rv, "running_var", 1e-5)
+        assert got[5] == 1
+        assert_bf16_close(got[6], s_dconv, "dconv", rel=2 ** -6)
+        if with_res:
+            assert_bf16_close(got[7], s_dres, "dres")
+        assert_f32_close(got[8], s_dgam, "dgamma", 2e-4)
+        assert_f32_close(got[9], s_dbet, "dbeta", 2e-4)
