@@ -144,8 +144,9 @@ int sivae_bn_train_coeffs(const void* y_bf16, long long nvox, int C,
 
 /* Train-mode BatchNorm3d statistics + coefficients + apply (+ residual) + (Leaky)ReLU in ONE call, no resampling and no
  * dropout (models/models.py:18-19, :22 + :39-41): out = act(bn(y) (+ res)); mean / invstd / scale / shift and the running
- * statistics as sivae_bn_train_coeffs.  Tensors up to 3 Mi elements run as a single launch of one 16-CTA thread-block
- * cluster (partials exchanged through distributed shared memory); larger ones as statistics / finalize / apply.
+ * statistics as sivae_bn_train_coeffs.  Runs as statistics / finalize / apply launches; with SIVAE_BN_CLUSTER=1 in the
+ * environment tensors up to 3 Mi elements run as a single launch of one 16-CTA thread-block cluster (partials exchanged
+ * through distributed shared memory) -- an experiment that measured slower inside the training step.
  * workspace: sivae_bn_workspace_bytes(C). */
 int sivae_bn_train_act_fwd(const void* y_bf16, const void* res_bf16, void* out_bf16, int N, int D, int H, int W, int C,
                            const float* gamma, const float* beta, float* running_mean, float* running_var,

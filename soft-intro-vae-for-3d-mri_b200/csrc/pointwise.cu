@@ -784,9 +784,10 @@ int bn_train_coeffs(const void* y, long long nvox, int C, const float* gamma, co
 }
 
 // =================================================================================================
-// Small tensors (the 256-channel layers at the latent resolution: 2.4 M elements, 4.9 MB): the three launches
-// statistics -> finalize -> apply (and reduce -> finalize -> apply in backward) cost ~20 us, mostly launch latency and
-// tails.  One thread-block CLUSTER of 16 CTAs does all three phases in a single launch: every CTA reduces its slice of the
+// EXPERIMENT (opt-in, see small_path_ok).  Small tensors (the 256-channel layers at the latent resolution: 2.4 M
+// elements, 4.9 MB): the three launches statistics -> finalize -> apply (and reduce -> finalize -> apply in backward)
+// cost ~20 us, mostly launch latency and tails.  One thread-block CLUSTER of 16 CTAs does all three phases in a single
+// launch: every CTA reduces its slice of the
 // voxels, the per-channel partials are exchanged through distributed shared memory (cluster.map_shared_rank) between two
 // cluster barriers, and the second pass over the slice hits L2.  Deterministic (fixed rank order, fp64 finalize).
 // =================================================================================================
@@ -1027,8 +1028,10 @@ bn_small_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
 }
 
 static bool small_path_ok(long long nvox, int C) {
-  const bool disabled = getenv("SIVAE_NO_BN_CLUSTER") != nullptr;   // parity tests compare both paths
-  return !disabled && C <= kSmallMaxC && C >= 8 && (kSmallThreads % (C / 8)) == 0 && nvox * C <= kSmallMaxElems &&
+  // OPT-IN (SIVAE_BN_CLUSTER=1): parity-tested, but measured SLOWER in the step (68.5 vs 67.5 ms, A/B on one box): one
+  // 16-CTA cluster cannot keep enough loads in flight to beat three short launches that spread over all 148 SMs.
+  const bool enabled = getenv("SIVAE_BN_CLUSTER") != nullptr;
+  return enabled && C <= kSmallMaxC && C >= 8 && (kSmallThreads % (C / 8)) == 0 && nvox * C <= kSmallMaxElems &&
          nvox >= kSmallCluster;
 }
 

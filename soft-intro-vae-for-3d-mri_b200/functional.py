@@ -145,7 +145,8 @@ class _ConvBnAct(torch.autograd.Function):
         small = (bn.training and resample == K.RESAMPLE_NONE
                  and x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * (8 if pre_up else 1) * wf.shape[1] <= K.SMALL_BN_ELEMS)
         if small:
-            # small layers (latent resolution): convolution, then statistics + coefficients + apply as ONE cluster launch
+            # small layers (latent resolution): convolution, then statistics + coefficients + apply behind one C-ABI call
+            # (a single cluster launch when SIVAE_BN_CLUSTER=1; three short launches by default, which measured faster)
             y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
             out, mean, invstd = K.bn_train_act_fwd(y, res, gamma, beta, bn.running_mean, bn.running_var,
                                                    bn.num_batches_tracked, bn.momentum, bn.eps, slope)
