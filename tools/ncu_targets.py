@@ -29,6 +29,7 @@ targets = [
     lambda: K.conv3_wgrad(y, g),
     lambda: K.upconv3_fprop(xlo, wup),
     lambda: K.upconv3_dgrad(g, wupT),
+    lambda: K.upconv3_wgrad(xlo, g),
     lambda: K.bn_train_coeffs(y, gamma, beta, None, None, None, 0.1, 1e-5),
     lambda: K.bn_act_fwd(y, scale, shift, None, 0.2, 0),
     lambda: K.bn_act_fwd(y, scale, shift, None, 0.2, 1),
