@@ -227,3 +227,57 @@ def test_graphed_step_runs_and_redraws_dropout():
     assert int(sd["decoder.blocks.0.1.num_batches_tracked"]) == 3 * 8 + 2 * 8
     assert not torch.equal(w0, net.encoder.blocks[1][0].block[0].weight)
     assert int(F.dropout_state.epoch) >= 5
+
+
+def _graphed_losses(split: bool, fused_adam: bool, steps=3):
+    """Losses of `steps` graph replays from a fixed seed (dropout / eps streams re-keyed identically)."""
+    from sivae_b200 import parallel as P
+    torch.manual_seed(11)
+    F.manual_seed(11)
+    net = sivae_b200.SoftIntroVAE(64, [[64, 1, 2], [64, 1, 2], [64, 1, 2]]).to(DEV)
+    net.apply(T.init_weights_he)
+    net.train()
+    if fused_adam:
+        opt_e, opt_d = sivae_b200.FusedAdam(net.encoder.parameters(), lr=2e-4), sivae_b200.FusedAdam(net.decoder.parameters(), lr=2e-4)
+    else:
+        opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4, capturable=True)
+        opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4, capturable=True)
+    red = (P.FlatGradReducer(net.encoder.parameters()), P.FlatGradReducer(net.decoder.parameters())) if split else (None, None)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    real = torch.rand(2, 1, 16, 24, 16, device=DEV, generator=g)
+    noise = torch.randn(2, 1, 2, 3, 2, device=DEV, generator=g)
+    torch.cuda.manual_seed(99)                                         # randn_like stream of the reparameterisation
+    step = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real, noise, warmup=1, reducer_e=red[0], reducer_d=red[1])
+    assert len(step.graphs) == (3 if split else 1)
+    vals = []
+    for _ in range(steps):
+        out = step(real, noise)
+        vals.append([float(out[k]) for k in ("lossE", "lossD", "loss_rec", "kl_real")])
+    return vals, net
+
+
+def test_split_graph_path_single_rank_matches_whole_step_graph():
+    """The multi-rank step (three CUDA graphs with the gradient exchange between the replays, gradients living in
+    parallel.FlatGradReducer's flat buffers, optim.FusedAdam) on ONE rank -- the all-reduce is the identity -- must
+    train exactly like the whole-step graph: same kernels, same order, same random streams."""
+    a, net_a = _graphed_losses(split=False, fused_adam=True)
+    b, net_b = _graphed_losses(split=True, fused_adam=True)
+    for va, vb in zip(a, b):
+        for x, y in zip(va, vb):
+            assert math.isfinite(x) and x == pytest.approx(y, rel=1e-5), (a, b)
+    for (k, p), (_, q) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), k
+    # gradients of the split path are views of the flat exchange buffers; unused parameters keep grad None
+    assert net_b.encoder.blocks[1][0].block[0].weight.grad.untyped_storage().data_ptr() != 0
+    unused = [p for n, p in net_b.named_parameters() if "shortcut" in n]
+    assert unused and all(p.grad is None for p in unused)
+
+
+def test_fused_adam_graph_matches_torch_adam_graph():
+    """optim.FusedAdam vs torch.optim.Adam(capturable=True) inside the whole-step graph: same losses over 3 updates
+    (the first update moves every weight by +-lr, so this is sensitive to any difference in the update rule)."""
+    a, _ = _graphed_losses(split=False, fused_adam=True)
+    b, _ = _graphed_losses(split=False, fused_adam=False)
+    for va, vb in zip(a, b):
+        for x, y in zip(va, vb):
+            assert x == pytest.approx(y, rel=2e-3), (a, b)
