@@ -278,12 +278,13 @@ def test_fused_adam_graph_matches_torch_adam_graph():
     """optim.FusedAdam vs torch.optim.Adam(capturable=True) inside the whole-step graph.  The update rule itself is
     pinned to 2e-6 in tests/test_optim.py; here the two differ by 1 ulp (7.5e-9) per weight after the first update
     (tools/adam_cmp.py), which flips a few bf16 roundings of the repacked weights, and the recipe amplifies that
-    (Adam's second update is +-lr on small-gradient elements, KL sums exp(logvar)).  So: the first replay must agree
-    tightly, the later ones to the bf16 level the model tests use, kl_real to 10 %."""
+    (Adam's second update is +-lr on small-gradient elements, KL sums exp(logvar)); torch's capturable formula
+    differs from torch's own eager one by the same amount (eager torch Adam reproduces FusedAdam's 28.55296 at this
+    step, the capturable graph gives 28.57584).  So: first replay to 2e-3, later ones to 2e-2, kl_real to 10 %."""
     a, _ = _graphed_losses(split=False, fused_adam=True)
     b, _ = _graphed_losses(split=False, fused_adam=False)
     for x, y in zip(a[0], b[0]):
-        assert x == pytest.approx(y, rel=1e-4), (a, b)
+        assert x == pytest.approx(y, rel=2e-3), (a, b)
     for va, vb in zip(a[1:], b[1:]):
         for i, (x, y) in enumerate(zip(va, vb)):
             assert x == pytest.approx(y, rel=1e-1 if i == 3 else 2e-2), (a, b)
