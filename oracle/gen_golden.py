@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt from the UNMODIFIED reference (authoring container only).
 
-    python -m oracle.gen_golden            # writes tests/golden/{sivae_small,vae_small,loss_kat}.pt
+    python -m oracle.gen_golden            # writes tests/golden/{sivae_small,vae_small,loss_kat,fc_small}.pt
 
 The reference has no golden vectors of its own, so these
 files -- outputs of the reference's own modules (models/models.py, models/vaemodel.py,
@@ -226,6 +226,111 @@ def gen_loss_kat(ref_lossf, ref_trainer):
     )
 
 
+def _sub(t):
+    """Strided 1/64 subsample of a [B,1,D,H,W] volume batch (keeps the fixture small) + its full fp64 sum."""
+    return dict(sub=t.detach()[:, :, ::4, ::4, ::4].clone(), sum=float(t.detach().double().sum()))
+
+
+def gen_fc_small():
+    """FC-latent variant: the reference's models/mymodel.py SoftIntroVAE and one iteration of
+    utils/trainer_fc.py:214-293 (without the optimiser step) at the only input size the model accepts
+    (80x96x80 -> 5x6x5 before the Linear head, mymodel.py:125), with narrow channels so it runs on CPU in seconds.
+    ``real`` / ``noise`` are regenerated from the recorded CPU seeds at test time."""
+    import importlib
+    ref_my = importlib.import_module("models.mymodel")
+    ref_tfc = importlib.import_module("utils.trainer_fc")
+    chans, z_ch, B = (4, 4, 8, 8), 16, 2
+    torch.manual_seed(2024)
+    net = ref_my.SoftIntroVAE(*chans, z_ch)
+    net.apply(ref_tfc.init_weights_he)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    g = torch.Generator().manual_seed(555)
+    real = torch.rand(B, 1, 80, 96, 80, generator=g)
+    noise = torch.randn(B, z_ch, generator=g)
+    out = {"chans": chans, "z_ch": z_ch, "data_seed": 555, "batch": B, "sd0": _clone_sd(net.state_dict()),
+           "keys": list(net.state_dict().keys()), "real_sum": float(real.double().sum()), "noise": noise}
+
+    net.eval()
+    with torch.no_grad():
+        mu, lv = net.encode(real)
+        x_re = net.decode(mu)
+    out["eval"] = dict(mu=mu, logvar=lv, x_re_of_mu=_sub(x_re))
+
+    beta_rec, beta_neg, beta_kl, gamma_r = 1.0, 1024.0, 0.75, 1e-8
+    scale = 8.0 / (80 * 96 * 80)                                             # trainer_fc.py:179
+    calc_kl, crl = ref_tfc.calc_kl, ref_tfc.calc_reconstruction_loss
+    net.train()
+    with RecordingRandnLike() as rr:
+        for p_ in net.encoder.parameters():
+            p_.requires_grad = True
+        for p_ in net.decoder.parameters():
+            p_.requires_grad = False
+        fake = net.decode(noise)
+        real_mu, real_lv = net.encode(real)
+        z = net.reparameterize(real_mu, real_lv)
+        rec = net.decode(z)
+        loss_rec = crl(real, rec, loss_type="mse", reduction="mean")
+        kl_real = calc_kl(real_lv, real_mu, reduce="mean")
+        rec_mu, rec_lv, z_rec, rec_rec = net.forward(rec.detach())
+        fake_mu, fake_lv, z_fake, rec_fake = net.forward(fake.detach())
+        fake_kl_e = calc_kl(fake_lv, fake_mu, reduce="none")
+        rec_kl_e = calc_kl(rec_lv, rec_mu, reduce="none")
+        loss_fake_rec = crl(fake, rec_fake, loss_type="mse", reduction="none")
+        loss_rec_rec = crl(rec, rec_rec, loss_type="mse", reduction="none")
+        exp_elbo_fake = (-2 * scale * (beta_rec * loss_fake_rec + beta_neg * fake_kl_e)).exp().mean()
+        exp_elbo_rec = (-2 * scale * (beta_rec * loss_rec_rec + beta_neg * rec_kl_e)).exp().mean()
+        lossE = scale * (beta_rec * loss_rec + beta_kl * kl_real) + 0.5 * (exp_elbo_fake + exp_elbo_rec)
+        lossE = lossE * 10
+        net.zero_grad()
+        lossE.backward()
+        gradsE = {k: p_.grad.clone() for k, p_ in net.named_parameters() if p_.grad is not None}
+        termsE = dict(loss_rec=loss_rec, kl_real=kl_real, exp_elbo_fake=exp_elbo_fake, exp_elbo_rec=exp_elbo_rec,
+                      fake_kl_e=fake_kl_e.mean(), rec_kl_e=rec_kl_e.mean(),
+                      loss_fake_rec_e=loss_fake_rec.mean(), loss_rec_rec_e=loss_rec_rec.mean(), lossE=lossE)
+        fwdE = dict(fake=_sub(fake), real_mu=real_mu.detach(), real_logvar=real_lv.detach(), z=z.detach(),
+                    rec=_sub(rec), rec_rec=_sub(rec_rec), rec_fake=_sub(rec_fake))
+
+        for p_ in net.encoder.parameters():
+            p_.requires_grad = False
+        for p_ in net.decoder.parameters():
+            p_.requires_grad = True
+        for p_ in net.parameters():
+            p_.grad = None
+        fake = net.decode(noise)
+        rec = net.decode(z.detach())
+        loss_rec = crl(real, rec, loss_type="mse", reduction="mean")
+        rec_mu, rec_lv = net.encode(rec)
+        z_rec = net.reparameterize(rec_mu, rec_lv)
+        fake_mu, fake_lv = net.encode(fake)
+        z_fake = net.reparameterize(fake_mu, fake_lv)
+        rec_rec = net.decode(z_rec.detach())
+        rec_fake = net.decode(z_fake.detach())
+        loss_rec_rec = crl(rec.detach(), rec_rec, loss_type="mse", reduction="mean")
+        loss_fake_rec = crl(fake.detach(), rec_fake, loss_type="mse", reduction="mean")
+        rec_kl = calc_kl(rec_lv, rec_mu, reduce="mean")
+        fake_kl = calc_kl(fake_lv, fake_mu, reduce="mean")
+        lossD = scale * (beta_rec * loss_rec + 0.5 * beta_kl * (rec_kl + fake_kl)
+                         + gamma_r * 0.5 * beta_rec * (loss_rec_rec + loss_fake_rec))
+        lossD = lossD * 10
+        lossD.backward()
+        gradsD = {k: p_.grad.clone() for k, p_ in net.named_parameters() if p_.grad is not None}
+        termsD = dict(loss_rec_d=loss_rec, rec_kl=rec_kl, fake_kl=fake_kl,
+                      loss_rec_rec_d=loss_rec_rec, loss_fake_rec_d=loss_fake_rec, lossD=lossD)
+    terms = {k: float(v.detach()) for k, v in {**termsE, **termsD}.items()}
+    out["step"] = dict(
+        terms=terms, gradsE=gradsE, gradsD=gradsD, fwdE=fwdE, eps=[e.clone() for e in rr.draws],
+        buffers_after={k: v.clone() for k, v in net.state_dict().items()
+                       if k.endswith(("running_mean", "running_var", "num_batches_tracked"))},
+        hyper=dict(beta_rec=beta_rec, beta_neg=beta_neg, beta_kl=beta_kl, gamma_r=gamma_r, scale=scale),
+    )
+    assert len(rr.draws) == 5, len(rr.draws)
+    return out
+
+
 def main():
     ref_models, ref_vaemodel, ref_lossf, ref_trainer = import_reference()
     torch.set_num_threads(1)           # deterministic reduction order for the fixtures
@@ -233,6 +338,7 @@ def main():
     torch.save(gen_sivae_small(ref_models, ref_trainer), os.path.join(GOLDEN, "sivae_small.pt"))
     torch.save(gen_vae_small(ref_vaemodel, ref_lossf, ref_trainer), os.path.join(GOLDEN, "vae_small.pt"))
     torch.save(gen_loss_kat(ref_lossf, ref_trainer), os.path.join(GOLDEN, "loss_kat.pt"))
+    torch.save(gen_fc_small(), os.path.join(GOLDEN, "fc_small.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

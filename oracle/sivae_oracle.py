@@ -13,6 +13,8 @@ when the reference checkout is present, directly by ``tests/test_oracle_vs_refer
 Reference citations (paths relative to the reference checkout):
   * topology         models/models.py:8-145, 213-223, 257-300 (LeakyReLU(0.2) + Dropout)
                      models/vaemodel.py:8-130, 215-230        (ReLU, no Dropout)
+  * FC-latent variant models/mymodel.py:51-143 (encoder), :146-230 (decoder), :262-290 (SoftIntroVAE);
+                     loop = utils/trainer_fc.py:214-293 (same update rule, noise [B, z_ch], fixed scale)
   * plain-VAE loss   models/lossf.py:5-24
   * introspective    utils/my_trainer.py:38-48 (calc_kl), :62-78 (calc_reconstruction_loss),
     loss + step      :236-325 (E update / D update)
@@ -138,6 +140,8 @@ def encoder_features(sd, x, cfg: NetCfg, training: bool, feed: MaskFeed, prefix=
 
 def encode(sd, x, cfg: NetCfg, training: bool, feed: Optional[MaskFeed] = None, prefix="encoder"):
     """VAEResNetEncoder.forward, models.py:219-223 -> (mu, logvar)."""
+    if isinstance(cfg, FcCfg):
+        return fc_encode(sd, x, cfg, training, prefix)
     feed = feed or MaskFeed()
     h = encoder_features(sd, x, cfg, training, feed, prefix)
     mu = F.conv3d(h, sd[f"{prefix}.mu.weight"], sd[f"{prefix}.mu.bias"])
@@ -147,6 +151,8 @@ def encode(sd, x, cfg: NetCfg, training: bool, feed: Optional[MaskFeed] = None, 
 
 def decode(sd, z, cfg: NetCfg, training: bool, feed: Optional[MaskFeed] = None, prefix="decoder") -> Tensor:
     """ResNetDecoder.forward, models.py:116-145."""
+    if isinstance(cfg, FcCfg):
+        return fc_decode(sd, z, cfg, training, prefix)
     feed = feed or MaskFeed()
     h = F.conv3d(z, sd[f"{prefix}.blocks.0.0.weight"], sd[f"{prefix}.blocks.0.0.bias"])
     h = _act(_bn(sd, f"{prefix}.blocks.0.1", h, training), cfg.slope)
@@ -158,6 +164,76 @@ def decode(sd, z, cfg: NetCfg, training: bool, feed: Optional[MaskFeed] = None, 
     h = F.conv3d(h, sd[f"{prefix}.blocks.{k}.0.weight"], sd[f"{prefix}.blocks.{k}.0.bias"], 1, 1)
     h = F.relu(h)
     return feed.apply(h, cfg.p_dec_tail, training)
+
+
+@dataclasses.dataclass(frozen=True)
+class FcCfg:
+    """models/mymodel.py: SoftIntroVAE(first_ch, second_ch, third_ch, forth_ch, z_ch).  ``grid`` is the spatial size
+    in front of the Linear heads -- the reference hard-codes 5x6x5 (mymodel.py:125,151,220: 80x96x80 inputs / 16)."""
+
+    first_ch: int
+    second_ch: int
+    third_ch: int
+    forth_ch: int
+    z_ch: int
+    grid: Tuple[int, int, int] = (5, 6, 5)
+    slope: float = 0.2
+
+
+def _cbl(sd, pre, i, x, training, slope=0.2, act=True):
+    """Conv3d(bias=True) -> BatchNorm3d -> [LeakyReLU(0.2)] at Sequential indices i, i+1 (mymodel.py:56-58 etc.)."""
+    h = F.conv3d(x, sd[f"{pre}.{i}.weight"], sd[f"{pre}.{i}.bias"], 1, 1)
+    h = _bn(sd, f"{pre}.{i + 1}", h, training)
+    return F.leaky_relu(h, slope) if act else h
+
+
+def fc_encode(sd, x, cfg: FcCfg, training: bool, prefix="encoder"):
+    """ResNetVAEencoder.forward, mymodel.py:127-143 -> (mu, logvar) [B, z_ch].  block8 exists but never runs."""
+    p, s = prefix, cfg.slope
+    h = _cbl(sd, f"{p}.block1", 0, x, training, s)
+    h = _cbl(sd, f"{p}.block1", 3, h, training, s)
+    h = F.avg_pool3d(h, 2)                                                     # :129
+    h = _cbl(sd, f"{p}.block2", 0, h, training, s)
+    h = _cbl(sd, f"{p}.block2", 3, h, training, s)
+    h = F.avg_pool3d(h, 2)                                                     # :131
+    h = _cbl(sd, f"{p}.block3", 0, h, training, s)
+    h = _cbl(sd, f"{p}.block3", 3, h, training, s)
+    h = F.avg_pool3d(h, 2)                                                     # :133
+    h = _cbl(sd, f"{p}.block4short", 0, h, training, s)
+    r = _cbl(sd, f"{p}.block5", 0, h, training, s)                             # activation INSIDE the branch
+    h = F.leaky_relu(h + r, s)                                                 # :136
+    h = _cbl(sd, f"{p}.block6", 0, h, training, s)
+    h = F.avg_pool3d(h, 2)                                                     # block6[3]
+    h = _cbl(sd, f"{p}.block6", 4, h, training, s)
+    r = _cbl(sd, f"{p}.block7", 0, h, training, s)
+    r = _cbl(sd, f"{p}.block7", 3, r, training, s, act=False)
+    h = F.leaky_relu(h + r, s)                                                 # :139
+    h = h.reshape(h.shape[0], -1)                                              # NCDHW flatten, :140
+    y = F.linear(h, sd[f"{p}.fc.weight"], sd[f"{p}.fc.bias"])
+    mu, lv = y.chunk(2, dim=1)
+    return mu, lv
+
+
+def fc_decode(sd, z, cfg: FcCfg, training: bool, prefix="decoder") -> Tensor:
+    """ResNetDecoder.forward, mymodel.py:217-230: [B, z_ch] -> [B,1,16*grid]."""
+    p, s = prefix, cfg.slope
+    y = F.relu(F.linear(z.reshape(z.shape[0], -1), sd[f"{p}.dfc.0.weight"], sd[f"{p}.dfc.0.bias"]))
+    y = y.reshape(y.shape[0], cfg.forth_ch, *cfg.grid)
+    r = _cbl(sd, f"{p}.block1", 0, y, training, s)
+    r = _cbl(sd, f"{p}.block1", 3, r, training, s, act=False)
+    y = F.leaky_relu(y + r, s)                                                 # :221
+    y = _cbl(sd, f"{p}.block2u", 0, y, training, s)
+    y = F.interpolate(y, scale_factor=2.0, mode="nearest")
+    y = _cbl(sd, f"{p}.block2u", 4, y, training, s)
+    r = _cbl(sd, f"{p}.block3", 0, y, training, s)
+    r = _cbl(sd, f"{p}.block3", 3, r, training, s, act=False)
+    y = F.leaky_relu(y + r, s)                                                 # :224
+    for blk in ("block4u", "block5u", "block6u"):
+        y = _cbl(sd, f"{p}.{blk}", 0, y, training, s)
+        y = F.interpolate(y, scale_factor=2.0, mode="nearest")
+        y = _cbl(sd, f"{p}.{blk}", 4, y, training, s)
+    y = F.conv3d(y, sd[f"{p}.last_block.0.weight"], sd[f"{p}.last_block.0.bias"], 1, 1)
+    return F.relu(y)
 
 
 def reparameterize(mu: Tensor, logvar: Tensor, eps) -> Tensor:

@@ -94,3 +94,61 @@ def test_plain_vae_step(golden_dir):
         torch.testing.assert_close(grads[k], ref, rtol=2e-3, atol=1e-4 * float(ref.abs().max()) + 1e-9, msg=k)
     for k, v in st["buffers_after"].items():
         torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6, msg=k)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FC-latent variant (models/mymodel.py + utils/trainer_fc.py), SURVEY 8f NEXT-1
+# ---------------------------------------------------------------------------------------------------------------
+def fc_inputs(g):
+    """Regenerate the fixture's inputs from its recorded CPU seed (the volumes are too large to commit)."""
+    gen = torch.Generator().manual_seed(g["data_seed"])
+    real = torch.rand(g["batch"], 1, 80, 96, 80, generator=gen)
+    noise = torch.randn(g["batch"], g["z_ch"], generator=gen)
+    assert float(real.double().sum()) == g["real_sum"] and torch.equal(noise, g["noise"])
+    return real, noise
+
+
+def bias_in_front_of_bn(k, tensors):
+    """Conv3d biases followed by a train-mode BatchNorm3d: mathematically zero gradient, round-off noise only."""
+    return k.endswith(".bias") and "last_block" not in k and tensors[k.replace(".bias", ".weight")].dim() == 5
+
+
+def test_fc_eval_forward(golden_dir):
+    g = _load(golden_dir, "fc_small.pt")
+    real, _ = fc_inputs(g)
+    cfg = O.FcCfg(*g["chans"], g["z_ch"])
+    sd = {k: v.clone() for k, v in g["sd0"].items()}
+    mu, lv = O.encode(sd, real, cfg, False)
+    x_re = O.decode(sd, mu, cfg, False)
+    torch.testing.assert_close(mu, g["eval"]["mu"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(lv, g["eval"]["logvar"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(x_re[:, :, ::4, ::4, ::4], g["eval"]["x_re_of_mu"]["sub"], rtol=1e-5, atol=1e-6)
+    assert float(x_re.double().sum()) == pytest.approx(g["eval"]["x_re_of_mu"]["sum"], rel=1e-6)
+
+
+def test_fc_soft_intro_step(golden_dir):
+    g = _load(golden_dir, "fc_small.pt")
+    st = g["step"]
+    real, noise = fc_inputs(g)
+    cfg = O.FcCfg(*g["chans"], g["z_ch"])
+    sd = {k: v.clone() for k, v in g["sd0"].items()}
+    assert list(sd.keys()) == g["keys"]
+    hp = O.StepHyper(**st["hyper"])
+    terms, gE, gD = O.soft_intro_step_grads(sd, cfg, real, noise, st["eps"], None, hp)
+    for k, v in st["terms"].items():
+        assert terms[k] == pytest.approx(v, rel=5e-5, abs=1e-30), k
+    assert set(gE) == set(st["gradsE"]) and set(gD) == set(st["gradsD"])
+    assert not any(".block8." in k for k in gE)            # block8 is built but never run (mymodel.py:108-117)
+    allref = {**st["gradsE"], **st["gradsD"]}
+    for k, got in {**gE, **gD}.items():
+        ref = allref[k]
+        if bias_in_front_of_bn(k, allref):
+            wscale = float(allref[k.replace(".bias", ".weight")].abs().max())
+            assert float(got.abs().max()) <= 1e-3 * wscale and float(ref.abs().max()) <= 1e-3 * wscale, k
+            continue
+        torch.testing.assert_close(got, ref, rtol=2e-3, atol=1e-4 * float(ref.abs().max()) + 1e-12, msg=k)
+    for k, v in st["buffers_after"].items():
+        torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6, msg=k)
+    assert int(sd["encoder.block1.1.num_batches_tracked"]) == 5
+    assert int(sd["decoder.block1.1.num_batches_tracked"]) == 8
+    assert int(sd["encoder.block8.1.num_batches_tracked"]) == 0
