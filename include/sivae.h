@@ -335,6 +335,31 @@ int sivae_preprocess_clip_minmax(const float* x, float* y, int B, long long n, f
 int sivae_affine_resample(const float* x, float* y, int B, int D, int H, int W, const float* mats, const float* pad,
                           const float* stats, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * FC-latent variant (SURVEY.md section 8f NEXT-1): the Linear heads of models/mymodel.py (:125 fc, :150-153 dfc+ReLU)
+ * and the layout changes around them.  x [B][K], y / dy [B][J], W / dW [J][K] (torch nn.Linear layout), bias / db [J],
+ * all fp32 row-major on the device.  Weight-streaming kernels (HBM-bound for B <= 8), fp32 FMA accumulation,
+ * deterministic split reductions.  workspace: sivae_linear_workspace_bytes(B, K, J) for fwd and dgrad.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sivae_linear_workspace_bytes(int B, int K, int J);
+/* y = act(x W^T + bias); act 0 = none (mymodel.py:141), 1 = ReLU (mymodel.py:152); bias may be NULL. */
+int sivae_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int J, int act,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* dx = dy W */
+int sivae_linear_dgrad(const float* dy, const float* W, float* dx, int B, int K, int J, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* dW = dy^T x, db = column sums of dy (db may be NULL) */
+int sivae_linear_wgrad(const float* x, const float* dy, float* dW, float* db, int B, int K, int J, void* stream);
+/* x.view(B, -1) of an NCDHW tensor (mymodel.py:140) from the NDHWC bf16 trunk: dst[b][c*S + s] = src[b][s][c], c < C <= Cp
+ * (Cp = padded channel count); with gate != NULL entries whose gate[b][c*S + s] <= 0 are zeroed (ReLU gradient). */
+int sivae_ndhwc_to_flat(const void* src, float* dst, int B, int S, int C, int Cp, const float* gate, void* stream);
+/* y.view(B, C, d, h, w) (mymodel.py:219) into NDHWC bf16 with channels zero-padded to Cp. */
+int sivae_flat_to_ndhwc(const float* src, void* dst, int B, int S, int C, int Cp, void* stream);
+/* out = LeakyReLU_slope(a + b) on n bf16 elements (n % 8 == 0) -- mymodel.py:136, where the skip branch carries its own
+ * activation; and dz = g * (out > 0 ? 1 : slope), the gradient with respect to both a and b. */
+int sivae_add_act_fwd(const void* a, const void* b, void* out, long long n, float slope, void* stream);
+int sivae_add_act_bwd(const void* g, const void* out, void* dz, long long n, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -371,6 +371,44 @@ def affine_resample(x, mats, pad=None, stats=None):
     return y[:, 0]
 
 
+def linear_fwd(x, weight, bias, relu=False):
+    """nn.Linear (+ ReLU): mymodel.py:125,:150-153."""
+    y = F.linear(x, weight, bias)
+    return F.relu(y) if relu else y
+
+
+def linear_dgrad(dy, weight):
+    return dy @ weight
+
+
+def linear_wgrad(x, dy, need_bias=True):
+    return dy.t() @ x, (dy.sum(0) if need_bias else None)
+
+
+def ndhwc_to_flat(h, c, gate=None):
+    """NDHWC [B,d,h,w,Cp] -> fp32 [B, c*S] in NCDHW flatten order (mymodel.py:140), optionally gated by gate > 0."""
+    b = h.shape[0]
+    out = h[..., :c].permute(0, 4, 1, 2, 3).reshape(b, -1).float()
+    return out if gate is None else out * (gate > 0).float()
+
+
+def flat_to_ndhwc(y, c, cp, grid):
+    """fp32 [B, c*S] -> NDHWC [B,*grid,cp] in the activation dtype, channels zero-padded (mymodel.py:219)."""
+    b = y.shape[0]
+    v = y.reshape(b, c, *grid).permute(0, 2, 3, 4, 1)
+    if cp != c:
+        v = torch.cat([v, torch.zeros(*v.shape[:-1], cp - c, dtype=v.dtype, device=v.device)], dim=-1)
+    return v.contiguous().to(ACT_DTYPE)
+
+
+def add_act_fwd(a, b, slope):
+    return F.leaky_relu(a.float() + b.float(), slope).to(ACT_DTYPE)
+
+
+def add_act_bwd(g, out, slope):
+    return torch.where(out.float() > 0, g.float(), g.float() * slope).to(ACT_DTYPE)
+
+
 def similarity_topk(queries, database, k, metric="cosine"):
     """Top-k similarity (cosine, or negative squared L2), best first, ties -> lower database index."""
     q, d = queries.double(), database.double()

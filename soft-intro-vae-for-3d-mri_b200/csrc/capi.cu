@@ -117,6 +117,14 @@ int preprocess_clip_minmax(const float*, float*, int, long long, float, float*, 
 int affine_resample(const float*, float*, int, int, int, int, const float*, const float*, const float*, cudaStream_t);
 int upconv3_fprop_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
                      float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+size_t linear_workspace_bytes(int, int, int);
+int linear_fwd(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+int linear_dgrad(const float*, const float*, float*, int, int, int, void*, size_t, cudaStream_t);
+int linear_wgrad(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+int ndhwc_to_flat(const void*, float*, int, int, int, int, const float*, cudaStream_t);
+int flat_to_ndhwc(const float*, void*, int, int, int, int, cudaStream_t);
+int add_act_fwd(const void*, const void*, void*, long long, float, cudaStream_t);
+int add_act_bwd(const void*, const void*, void*, long long, float, cudaStream_t);
 size_t similarity_workspace_bytes(int, int);
 int similarity_topk(const float*, const float*, int, int, int, int, int, float*, int*, void*, size_t, cudaStream_t);
 int c1_to_c64_bn(const float*, const float*, const float*, void*, int, int, int, int, int, const float*, const float*,
@@ -284,6 +292,30 @@ int sivae_c1_to_c64_bn(const float* x1, const float* w, const float* bias, void*
                        size_t ws_pack_bytes, void* ws_bn, size_t ws_bn_bytes, void* stream) {
   return c1_to_c64_bn(x1, w, bias, y, N, D, H, W, flip, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift,
                       ws_pack, ws_pack_bytes, ws_bn, ws_bn_bytes, ST(stream));
+}
+size_t sivae_linear_workspace_bytes(int B, int K, int J) { return linear_workspace_bytes(B, K, J); }
+int sivae_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int J, int act, void* ws,
+                     size_t ws_bytes, void* stream) {
+  return linear_fwd(x, W, bias, y, B, K, J, act, ws, ws_bytes, ST(stream));
+}
+int sivae_linear_dgrad(const float* dy, const float* W, float* dx, int B, int K, int J, void* ws, size_t ws_bytes,
+                       void* stream) {
+  return linear_dgrad(dy, W, dx, B, K, J, ws, ws_bytes, ST(stream));
+}
+int sivae_linear_wgrad(const float* x, const float* dy, float* dW, float* db, int B, int K, int J, void* stream) {
+  return linear_wgrad(x, dy, dW, db, B, K, J, ST(stream));
+}
+int sivae_ndhwc_to_flat(const void* src, float* dst, int B, int S, int C, int Cp, const float* gate, void* stream) {
+  return ndhwc_to_flat(src, dst, B, S, C, Cp, gate, ST(stream));
+}
+int sivae_flat_to_ndhwc(const float* src, void* dst, int B, int S, int C, int Cp, void* stream) {
+  return flat_to_ndhwc(src, dst, B, S, C, Cp, ST(stream));
+}
+int sivae_add_act_fwd(const void* a, const void* b, void* out, long long n, float slope, void* stream) {
+  return add_act_fwd(a, b, out, n, slope, ST(stream));
+}
+int sivae_add_act_bwd(const void* g, const void* out, void* dz, long long n, float slope, void* stream) {
+  return add_act_bwd(g, out, dz, n, slope, ST(stream));
 }
 size_t sivae_similarity_workspace_bytes(int nq, int nd) { return similarity_workspace_bytes(nq, nd); }
 int sivae_similarity_topk(const float* q, const float* db, int nq, int nd, int dim, int metric, int k, float* out_scores,

@@ -441,6 +441,87 @@ class _Head1(torch.autograd.Function):
 def head1(h, w, b):
     return _Head1.apply(h, w, b)
 
+# ------------------------------------------------------------------------------------------------
+# FC-latent variant (models/mymodel.py): Linear heads and the activation-carrying skip connection
+# ------------------------------------------------------------------------------------------------
+class _FcHead(torch.autograd.Function):
+    """``x.view(B,-1) -> Linear`` (mymodel.py:140-141): h NDHWC [B,d,h,w,Cp] -> fp32 [B,J]; weight fp32 [J, c*d*h*w]."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, c: int):
+        xf = K.ndhwc_to_flat(h, c)
+        w = weight.detach().contiguous()
+        y = K.linear_fwd(xf, w, bias, relu=False)
+        ctx.save_for_backward(xf, w)
+        ctx.geom = (c, h.shape[-1], tuple(h.shape[1:4]))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, w = ctx.saved_tensors
+        c, cp, grid = ctx.geom
+        need_h, need_w, need_b = ctx.needs_input_grad[:3]
+        dy = dy.contiguous()
+        dh = K.flat_to_ndhwc(K.linear_dgrad(dy, w), c, cp, grid) if need_h else None
+        dw = db = None
+        if need_w or need_b:
+            dw, db = K.linear_wgrad(xf, dy, need_bias=bool(need_b))
+        return dh, (dw if need_w else None), db, None
+
+
+def fc_head(h, weight, bias, c: int):
+    return _FcHead.apply(h, weight, bias, c)
+
+
+class _DfcHead(torch.autograd.Function):
+    """``Linear -> ReLU -> view(B, C, d, h, w)`` (mymodel.py:150-153,:219): z fp32 [B,K] -> NDHWC [B,d,h,w,cp]."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias, c: int, cp: int, grid):
+        z = z.reshape(z.shape[0], -1).contiguous().float()
+        w = weight.detach().contiguous()
+        y = K.linear_fwd(z, w, bias, relu=True)
+        ctx.save_for_backward(z, y, w)
+        ctx.c = c
+        return K.flat_to_ndhwc(y, c, cp, grid)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, y, w = ctx.saved_tensors
+        need_z, need_w, need_b = ctx.needs_input_grad[:3]
+        dy = K.ndhwc_to_flat(g.contiguous(), ctx.c, gate=y)          # ReLU gradient folded into the layout change
+        dz = K.linear_dgrad(dy, w) if need_z else None
+        dw = db = None
+        if need_w or need_b:
+            dw, db = K.linear_wgrad(z, dy, need_bias=bool(need_b))
+        return dz, (dw if need_w else None), db, None, None, None
+
+
+def dfc_head(z, weight, bias, c: int, cp: int, grid):
+    return _DfcHead.apply(z, weight, bias, c, cp, grid)
+
+
+class _AddAct(torch.autograd.Function):
+    """LeakyReLU(a + b) where b already went through its own activation (mymodel.py:135-136)."""
+
+    @staticmethod
+    def forward(ctx, a, b, slope: float):
+        out = K.add_act_fwd(a.contiguous(), b.contiguous(), slope)
+        ctx.save_for_backward(out)
+        ctx.slope = slope
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        dz = K.add_act_bwd(g.contiguous(), out, ctx.slope)
+        return (dz if ctx.needs_input_grad[0] else None), (dz if ctx.needs_input_grad[1] else None), None
+
+
+def add_act(a, b, slope: float):
+    return _AddAct.apply(a, b, slope)
+
+
 
 # ----------------------------------------------------------------------------------------------
 # reparameterisation noise: torch's generator by default (randn_like, as the reference), or an

@@ -82,6 +82,14 @@ _SIGNATURES = {
     "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
     "sivae_affine_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sivae_linear_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sivae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sivae_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "sivae_linear_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sivae_ndhwc_to_flat": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sivae_flat_to_ndhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sivae_add_act_fwd": (_i, [_vp, _vp, _vp, _ll, _f, _vp]),
+    "sivae_add_act_bwd": (_i, [_vp, _vp, _vp, _ll, _f, _vp]),
     "sivae_similarity_workspace_bytes": (_sz, [_i, _i]),
     "sivae_similarity_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sivae_ncdhw_f32_to_ndhwc_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
@@ -607,6 +615,96 @@ def similarity_topk(queries: torch.Tensor, database: torch.Tensor, k: int, metri
                                      _p(scores), _p(index), _p(ws), ws.numel(), _stream(queries)),
            "sivae_similarity_topk")
     return scores, index
+
+
+# ----------------------------------------------------------------------------------------------
+# FC-latent variant (SURVEY section 8f NEXT-1): Linear heads, layout changes, add + activation
+# ----------------------------------------------------------------------------------------------
+def linear_fwd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False):
+    """y = act(x @ weight.T + bias): x fp32 [B,K], weight fp32 [J,K] (nn.Linear layout), bias fp32 [J] -> fp32 [B,J]."""
+    _req(x, torch.float32, "x")
+    _req(weight, torch.float32, "weight")
+    b, k = x.shape
+    j, k2 = weight.shape
+    assert k == k2 and (bias is None or bias.numel() == j)
+    lib = _L()
+    ws = _workspace(x.device, lib.sivae_linear_workspace_bytes(b, k, j), "linear")
+    y = torch.empty(b, j, dtype=torch.float32, device=x.device)
+    _check(lib.sivae_linear_fwd(_p(x), _p(weight), _p(bias), _p(y), b, k, j, int(relu), _p(ws), ws.numel(), _stream(x)),
+           "sivae_linear_fwd")
+    return y
+
+
+def linear_dgrad(dy: torch.Tensor, weight: torch.Tensor):
+    """dx = dy @ weight: dy fp32 [B,J], weight fp32 [J,K] -> fp32 [B,K]."""
+    _req(dy, torch.float32, "dy")
+    _req(weight, torch.float32, "weight")
+    b, j = dy.shape
+    j2, k = weight.shape
+    assert j == j2
+    lib = _L()
+    ws = _workspace(dy.device, lib.sivae_linear_workspace_bytes(b, k, j), "linear")
+    dx = torch.empty(b, k, dtype=torch.float32, device=dy.device)
+    _check(lib.sivae_linear_dgrad(_p(dy), _p(weight), _p(dx), b, k, j, _p(ws), ws.numel(), _stream(dy)),
+           "sivae_linear_dgrad")
+    return dx
+
+
+def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, need_bias: bool = True):
+    """-> (dW fp32 [J,K] = dy.T @ x, db fp32 [J] = dy.sum(0) or None)."""
+    _req(x, torch.float32, "x")
+    _req(dy, torch.float32, "dy")
+    b, k = x.shape
+    b2, j = dy.shape
+    assert b == b2
+    dw = torch.empty(j, k, dtype=torch.float32, device=x.device)
+    db = torch.empty(j, dtype=torch.float32, device=x.device) if need_bias else None
+    _check(_L().sivae_linear_wgrad(_p(x), _p(dy), _p(dw), _p(db), b, k, j, _stream(x)), "sivae_linear_wgrad")
+    return dw, db
+
+
+def ndhwc_to_flat(h: torch.Tensor, c: int, gate: Optional[torch.Tensor] = None):
+    """NDHWC bf16 [B,d,h,w,Cp] -> fp32 [B, c*d*h*w] in NCDHW flatten order (x.view(B,-1), mymodel.py:140); entries whose
+    ``gate`` (fp32, same shape as the result) is <= 0 are zeroed."""
+    _req(h, torch.bfloat16, "h")
+    b, cp = h.shape[0], h.shape[-1]
+    s = h.numel() // (b * cp)
+    out = torch.empty(b, c * s, dtype=torch.float32, device=h.device)
+    if gate is not None:
+        _req(gate, torch.float32, "gate")
+        assert gate.shape == out.shape
+    _check(_L().sivae_ndhwc_to_flat(_p(h), _p(out), b, s, c, cp, _p(gate), _stream(h)), "sivae_ndhwc_to_flat")
+    return out
+
+
+def flat_to_ndhwc(y: torch.Tensor, c: int, cp: int, grid):
+    """fp32 [B, c*S] (NCDHW flatten order, S = prod(grid)) -> NDHWC bf16 [B,*grid,cp], channels zero-padded."""
+    _req(y, torch.float32, "y")
+    b = y.shape[0]
+    s = grid[0] * grid[1] * grid[2]
+    assert y.shape[1] == c * s
+    out = torch.empty(b, grid[0], grid[1], grid[2], cp, dtype=torch.bfloat16, device=y.device)
+    _check(_L().sivae_flat_to_ndhwc(_p(y), _p(out), b, s, c, cp, _stream(y)), "sivae_flat_to_ndhwc")
+    return out
+
+
+def add_act_fwd(a: torch.Tensor, b: torch.Tensor, slope: float):
+    """LeakyReLU_slope(a + b) on bf16 tensors of equal shape (mymodel.py:136)."""
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    assert a.shape == b.shape
+    out = torch.empty_like(a)
+    _check(_L().sivae_add_act_fwd(_p(a), _p(b), _p(out), a.numel(), float(slope), _stream(a)), "sivae_add_act_fwd")
+    return out
+
+
+def add_act_bwd(g: torch.Tensor, out: torch.Tensor, slope: float):
+    """Gradient of add_act_fwd with respect to either operand: g * (out > 0 ? 1 : slope)."""
+    _req(g, torch.bfloat16, "g")
+    _req(out, torch.bfloat16, "out")
+    dz = torch.empty_like(g)
+    _check(_L().sivae_add_act_bwd(_p(g), _p(out), _p(dz), g.numel(), float(slope), _stream(g)), "sivae_add_act_bwd")
+    return dz
 
 
 # ----------------------------------------------------------------------------------------------

@@ -137,3 +137,98 @@ def test_loss_functions_match_known_answers(golden_dir):
         torch.testing.assert_close(torch.stack(sivae_b200.lossf.normal_loss(y, mu, lv, x)), g["lossf_normal"])
         assert torch.equal(F.reparameterize(mu, lv, 0.1), g["z_val"])
         assert torch.equal(F.reparameterize(mu, lv, g["eps"]), g["z_train"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FC-latent variant (models/mymodel.py), SURVEY 8f NEXT-1
+# ---------------------------------------------------------------------------------------------------------------
+def test_fc_state_dict_contract(golden_dir):
+    g = _load(golden_dir, "fc_small.pt")
+    net = sivae_b200.mymodel.SoftIntroVAE(*g["chans"], g["z_ch"])
+    sd = net.state_dict()
+    assert list(sd.keys()) == g["keys"]
+    for k, v in g["sd0"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+    net.load_state_dict(g["sd0"], strict=True)
+    assert net.z_ch == g["z_ch"]
+    # BASELINE config 2 (600z_main.py:179): Linear(38400, 1200) and Linear(600, 38400)
+    big = sivae_b200.mymodel.SoftIntroVAE(32, 64, 128, 256, 600)
+    assert tuple(big.encoder.fc.weight.shape) == (1200, 38400)
+    assert tuple(big.decoder.dfc[0].weight.shape) == (38400, 600)
+
+
+def fc_small_net(grid=(1, 1, 1), chans=(4, 4, 8, 8), z_ch=6, seed=31):
+    torch.manual_seed(seed)
+    net = sivae_b200.mymodel.SoftIntroVAE(*chans, z_ch, latent_grid=grid)
+    net.apply(T.init_weights_he)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    return net
+
+
+def test_fc_step_matches_oracle_small_grid():
+    from oracle import sivae_oracle as O
+    from tests.test_oracle_vs_golden import bias_in_front_of_bn
+    grid, chans, z_ch, B = (1, 1, 1), (4, 4, 8, 8), 6, 2
+    net = fc_small_net(grid, chans, z_ch)
+    net.train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(8)
+    real = torch.rand(B, 1, 16, 16, 16, generator=gen)
+    noise = torch.randn(B, z_ch, generator=gen)
+    eps = [torch.randn(B, z_ch, generator=gen) for _ in range(5)]
+    hp = dict(beta_rec=1.0, beta_neg=1024.0, beta_kl=0.75, gamma_r=1e-8, scale=8.0 / 16 ** 3)
+    ref_terms, gE, gD = O.soft_intro_step_grads(sd, O.FcCfg(*chans, z_ch, grid), real, noise, eps, None, O.StepHyper(**hp))
+
+    opt_e = torch.optim.SGD(net.encoder.parameters(), lr=0.0)
+    opt_d = torch.optim.SGD(net.decoder.parameters(), lr=0.0)
+    F.noise_state.eps_feed = iter(eps)
+    try:
+        with emulated_kernels():
+            terms = T.soft_intro_train_step(net, real, noise, opt_e, opt_d, T.StepHyper(**hp))
+    finally:
+        F.noise_state.eps_feed = None
+    for k in ("lossE", "lossD", "loss_rec", "kl_real", "exp_elbo_fake", "exp_elbo_rec", "rec_kl", "fake_kl",
+              "loss_rec_d", "loss_rec_rec_d", "loss_fake_rec_d"):
+        assert float(terms[k]) == pytest.approx(ref_terms[k], rel=2e-4, abs=1e-30), k
+    allref = {**gE, **gD}
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    absorbed = {k for k in allref if bias_in_front_of_bn(k, allref) and not k.endswith("encoder.block1.0.bias")}
+    assert set(grads) == set(allref) - absorbed          # biases in front of a train-mode BN keep grad None
+    assert not any(".block8." in k for k in grads)
+    for k, got in grads.items():
+        ref = allref[k]
+        if k == "encoder.block1.0.bias":                  # stem bias: computed, but mathematically zero
+            assert float(got.abs().max()) <= 1e-3 * float(allref["encoder.block1.0.weight"].abs().max())
+            continue
+        torch.testing.assert_close(got, ref, rtol=2e-3, atol=1e-4 * float(ref.abs().max()) + 1e-12, msg=k)
+    after = net.state_dict()
+    for k, v in sd.items():
+        if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+            torch.testing.assert_close(after[k], v, rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_fc_eval_forward_matches_oracle_small_grid():
+    from oracle import sivae_oracle as O
+    grid, chans, z_ch = (1, 2, 1), (4, 4, 8, 8), 6
+    net = fc_small_net(grid, chans, z_ch, seed=32)
+    with torch.no_grad():                                  # non-trivial running statistics
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    net.eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    real = torch.rand(2, 1, 16, 32, 16, generator=torch.Generator().manual_seed(9))
+    cfg = O.FcCfg(*chans, z_ch, grid)
+    mu_r, lv_r = O.encode(sd, real, cfg, False)
+    x_r = O.decode(sd, mu_r, cfg, False)
+    with emulated_kernels(), torch.no_grad():
+        mu, lv = net.encode(real)
+        x_re = net.decode(mu)
+    torch.testing.assert_close(mu, mu_r, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(lv, lv_r, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x_re, x_r, rtol=1e-4, atol=1e-5)
