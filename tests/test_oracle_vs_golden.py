@@ -7,7 +7,16 @@ import torch
 
 from oracle import sivae_oracle as O
 
-torch.set_num_threads(1)
+
+
+@pytest.fixture(autouse=True)
+def _single_thread():
+    """The fixtures were generated with one CPU thread (oracle/gen_golden.py); other test modules change the global
+    thread count at import, and the summation order of conv3d's weight gradient follows it."""
+    old = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(old)
 
 
 def _load(golden_dir, name):
