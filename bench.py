@@ -147,6 +147,25 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+FC600 = dict(chans=(32, 64, 128, 256), z_ch=600, grid=(5, 6, 5), batch=4)
+
+
+def fc_gflop_per_volume_step(chans, z_ch, grid):
+    """Reference-equivalent FLOPs of one trainer_fc iteration per volume (direct-convolution count, as SURVEY 8d):
+    13 encoder-sized and 19 decoder-sized passes (fwd 5E+8D, dgrad 5E+7D, wgrad 3E+4D)."""
+    c1, c2, c3, c4 = chans
+    s = grid[0] * grid[1] * grid[2]
+    v = [s * 8 ** i for i in range(5)]                        # voxels at latent .. full resolution
+    conv = lambda ci, co, vox: 2.0 * 27 * ci * co * vox        # noqa: E731
+    enc = (conv(1, c1, v[4]) + conv(c1, c1, v[4]) + conv(c1, c1, v[3]) + conv(c1, c2, v[3]) + conv(c2, c2, v[2])
+           + conv(c2, c3, v[2]) + 3 * conv(c3, c3, v[1]) + conv(c3, c4, v[0]) + 2 * conv(c4, c4, v[0])
+           + 2.0 * c4 * s * 2 * z_ch)
+    dec = (2.0 * z_ch * c4 * s + 3 * conv(c4, c4, v[0]) + conv(c4, c3, v[1]) + 3 * conv(c3, c3, v[1])
+           + conv(c3, c2, v[2]) + conv(c2, c2, v[2]) + conv(c2, c1, v[3]) + conv(c1, c1, v[3]) + conv(c1, c1, v[4])
+           + conv(c1, 1, v[4]))
+    return (13 * enc + 19 * dec) / 1e9
+
+
 def run_ours(args):
     import torch.distributed as dist
     import sivae_b200
@@ -160,8 +179,14 @@ def run_ours(args):
     K.device_check()
     B = args.batch
     D, H, W = args.vol
+    fc = args.workload == "fc600"
+    if fc and tuple(args.vol) != VOL:
+        raise SystemExit("the FC-latent variant hard-codes 80x96x80 inputs (mymodel.py:125)")
     torch.manual_seed(77)                                   # identical init on every rank
-    net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
+    if fc:
+        net = sivae_b200.mymodel.SoftIntroVAE(*FC600["chans"], FC600["z_ch"])
+    else:
+        net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
     net.apply(T.init_weights_he)
     net.to(dev).train()
     # N = 1: the whole step is one CUDA graph.  N > 1: three graphs with the two NCCL gradient all-reduces issued
@@ -177,11 +202,11 @@ def run_ours(args):
     Reducer = P.FlatGradReducer if use_graph else P.GradReducer
     red_e = Reducer(net.encoder.parameters()) if world > 1 else None
     red_d = Reducer(net.decoder.parameters()) if world > 1 else None
-    hp = T.StepHyper()
+    hp = T.StepHyper(scale=sivae_b200.trainer_fc.SCALE) if fc else T.StepHyper()
     torch.manual_seed(1234 + rank)                          # disjoint synthetic shards / noise per rank
     F.manual_seed(1234 + rank)
     real_host = torch.rand(B, 1, D, H, W).pin_memory()
-    noise_host = torch.randn(B, 1, D // 8, H // 8, W // 8).pin_memory()
+    noise_host = (torch.randn(B, FC600["z_ch"]) if fc else torch.randn(B, 1, D // 8, H // 8, W // 8)).pin_memory()
     real_dev, noise_dev = real_host.to(dev), noise_host.to(dev)
 
     def barrier():
@@ -284,7 +309,8 @@ def run_ours(args):
     value = vols / (ms / 1e3)
     e2e = vols / (ms_e2e / 1e3)
     vol_scale = (D * H * W) / float(VOL[0] * VOL[1] * VOL[2])     # FLOPs scale with the voxel count (fully convolutional)
-    gflop_step = GFLOP_PER_VOLUME_STEP * vol_scale
+    gflop_step = (fc_gflop_per_volume_step(FC600["chans"], FC600["z_ch"], FC600["grid"]) if fc
+                  else GFLOP_PER_VOLUME_STEP * vol_scale)
     peak_tf, peak_gbs, peak_src = _peaks()
     dom = ksum.get("conv3_igemm", dict(launches=0, ms=0.0, work=0.0, by_shape={}))
     achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
@@ -310,9 +336,11 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "z-1200main.py Soft-IntroVAE(64,[[64,1,2],[128,1,2],[256,2,2]]) "
-                                   f"latent {D // 8}x{H // 8}x{W // 8} (z={D * H * W // 512}), {D}x{H}x{W}, "
-                                   "one E+D train step incl. 2 Adam steps",
+            "config": {"workload": ("600z_main.py mymodel.SoftIntroVAE(32,64,128,256,600) FC-latent variant, 80x96x80, "
+                                    "one trainer_fc E+D train step incl. 2 Adam steps" if fc else
+                                    "z-1200main.py Soft-IntroVAE(64,[[64,1,2],[128,1,2],[256,2,2]]) "
+                                    f"latent {D // 8}x{H // 8}x{W // 8} (z={D * H * W // 512}), {D}x{H}x{W}, "
+                                    "one E+D train step incl. 2 Adam steps"),
                        "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
                        "gflop_per_volume_step": gflop_step, "cuda_graph": graphed is not None,
@@ -321,7 +349,13 @@ def run_ours(args):
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
                                       "d2h_bytes_per_step": int(res.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roofline, "loss": {"lossE": lossE, "lossD": lossD}}
-    if world == 1 and not args.no_cpu_baseline:
+    if fc:
+        line["roofline"]["traffic"] = None
+        line["roofline"]["note"] = ("channel counts below 64 run zero-padded to 64 (tcgen05 tile width): the 32-channel "
+                                    "full-resolution layers execute 4x their reference-equivalent FLOPs; 'achieved' "
+                                    "counts executed (padded) FLOPs of the conv kernels, 'whole_step_tflops' "
+                                    "reference-equivalent ones")
+    if world == 1 and not args.no_cpu_baseline and not fc:
         threads = os.cpu_count() or 1
         step = cpu_reference_step_factory(threads=threads)
         step((16, 24, 16))
@@ -347,6 +381,9 @@ def main():
     ap.add_argument("--vol", type=int, nargs=3, default=list(VOL), metavar=("D", "H", "W"),
                     help="volume extents (headline 80 96 80; 160 192 160 = the ~5M-voxel L-shape, use --batch 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="z1200", choices=["z1200", "fc600"],
+                    help="z1200: the headline conv-latent net (BASELINE config 3); fc600: the FC-latent variant "
+                         "mymodel.SoftIntroVAE(32,64,128,256,600) of 600z_main.py (BASELINE config 2, batch 4)")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel/per-shape timing table here")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the fused optimiser")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
