@@ -1663,7 +1663,15 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   if (make_weight_tmap(&tmB, wpack, 27, Cout, Cin, block_n)) return -1;
   const ToOneEpilogue ep{};
   if (block_n == 256) return launch_igemm<256, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 256, ep, st);
-  if (block_n == 128) return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
+  // Grids that leave every SM at most one CTA (latent-resolution layers of small batches) are bound by the TMA
+  // round-trip of a 3-stage ring (one k-step per latency/3): a 6-stage ring keeps twice the bytes in flight.  With more
+  // CTAs than SMs the 3-stage kernel wins because two of its CTAs share an SM (SIVAE_DEEP_RING=0 disables, =1 forces).
+  if (block_n == 128) {
+    const char* e = getenv("SIVAE_DEEP_RING");
+    const bool deep = e ? e[0] == '1' : tiles * (Cout / 128) <= (long long)num_sms();
+    if (deep) return launch_igemm<128, 6, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
+    return launch_igemm<128, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 128, ep, st);
+  }
   return launch_igemm<64, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 64, ep, st);
 }
 

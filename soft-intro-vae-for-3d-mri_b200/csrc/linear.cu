@@ -79,13 +79,27 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int 
       }
     }
   }
+  // 32 partial sums per lane, 32 lanes: butterfly that halves the live values each step (31 shuffles instead of 160);
+  // lane l ends up holding the warp total of value l = r * 8 + b
+  float v[32];
 #pragma unroll
   for (int r = 0; r < kLinRowsPerWarp; ++r)
 #pragma unroll
-    for (int b = 0; b < kLinB; ++b) {
-      const float s = warp_sum(acc[r][b]);
-      if (lane == 0 && j0 + r < J && b < B) partial[((size_t)blockIdx.y * B + b) * J + j0 + r] = s;
+    for (int b = 0; b < kLinB; ++b) v[r * kLinB + b] = acc[r][b];
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
+  }
+  {
+    const int r = lane / kLinB, b = lane % kLinB;
+    if (j0 + r < J && b < B) partial[((size_t)blockIdx.y * B + b) * J + j0 + r] = v[0];
+  }
 }
 
 // out[b][i] = act(bias[i] + sum_s partial[(s*B + b)*n + i]);  act: 0 none, 1 ReLU
@@ -198,24 +212,51 @@ linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
-static int fwd_splits(int K, int J) {
-  const int row_blocks = cdiv(J, kLinRowsPerCta);
-  int ks = cdiv(2 * num_sms(), row_blocks);
-  ks = max(1, min(ks, cdiv(K, kLinKC)));
-  return ks;
+// Split factors are chosen so that the grid fills a whole number of waves of resident CTAs (a 304-CTA grid on 296 slots
+// runs for two CTA lifetimes): slots = occupancy x SM count, queried once per kernel.
+template <typename Kern>
+static int resident_slots(Kern kern) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ <= 0) occ = 2;
+  return occ * num_sms();
 }
-static int dgrad_splits(int K, int J, int vec) {
+static int fwd_splits(int K, int J, int vec) {
+  static int slots4 = 0, slots1 = 0;
+  if (!slots4) { slots4 = resident_slots(linear_fwd_kernel<4>); slots1 = resident_slots(linear_fwd_kernel<1>); }
+  const int slots = vec == 4 ? slots4 : slots1;
+  const int row_blocks = cdiv(J, kLinRowsPerCta);
+  // cost model: waves x (k-range of one CTA + a fixed per-CTA overhead worth ~512 columns)
+  int best = 1;
+  long long best_cost = -1;
+  for (int ks = 1; ks <= cdiv(K, kLinKC); ++ks) {
+    const long long cost = (long long)cdiv((long long)row_blocks * ks, slots) * (cdiv(K, ks) + 512);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ks; }
+  }
+  return best;
+}
+static int dgrad_splits(int B, int K, int J, int vec) {
+  static int slots4 = 0, slots1 = 0;
+  if (!slots4) { slots4 = resident_slots(linear_dgrad_kernel<4>); slots1 = resident_slots(linear_dgrad_kernel<1>); }
+  const int slots = vec == 4 ? slots4 : slots1;
   const int col_blocks = cdiv(K, 64 * vec);
-  int js = cdiv(4 * num_sms(), col_blocks);
-  js = max(1, min(js, cdiv(J, 64)));
-  return js;
+  // cost model in units of weight rows per CTA: waves x (rows of one CTA + ~24 rows of fixed overhead) plus the partial
+  // buffer's write + read traffic (2 B js rows per column block, spread over the resident CTAs)
+  int best = 1;
+  double best_cost = -1.0;
+  const int js_max = min(cdiv(J, 32), 512);
+  for (int js = 1; js <= js_max; ++js) {
+    const double waves = (double)cdiv((long long)col_blocks * js, slots);
+    const double cost = waves * (cdiv(J, js) + 24) + (double)col_blocks * 2.0 * B * js / slots;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = js; }
+  }
+  return best;
 }
 
 size_t linear_workspace_bytes(int B, int K, int J) {
   if (B <= 0 || K <= 0 || J <= 0) return 0;
   const int vec = (K % 4 == 0) ? 4 : 1;
   const size_t bb = (size_t)min(B, kLinB);
-  const size_t f = (size_t)fwd_splits(K, J) * bb * J, d = (size_t)dgrad_splits(K, J, vec) * bb * K;
+  const size_t f = (size_t)fwd_splits(K, J, vec) * bb * J, d = (size_t)dgrad_splits((int)bb, K, J, vec) * bb * K;
   return (f > d ? f : d) * sizeof(float);
 }
 
@@ -224,8 +265,8 @@ int linear_fwd(const float* x, const float* W, const float* bias, float* y, int 
   SIVAE_CHECK(B > 0 && K > 0 && J > 0, "linear_fwd: empty problem (B=%d K=%d J=%d)", B, K, J);
   SIVAE_CHECK(act == 0 || act == 1, "linear_fwd: act must be 0 (none) or 1 (ReLU)");
   SIVAE_CHECK(ws != nullptr && ws_bytes >= linear_workspace_bytes(B, K, J), "linear_fwd: workspace too small");
-  const int ks = fwd_splits(K, J);
   const int vec = (K % 4 == 0) ? 4 : 1;
+  const int ks = fwd_splits(K, J, vec);
   int kps = cdiv(K, ks);
   kps = (kps + 3) / 4 * 4;
   float* partial = static_cast<float*>(ws);
@@ -249,7 +290,7 @@ int linear_dgrad(const float* dy, const float* W, float* dx, int B, int K, int J
   SIVAE_CHECK(B > 0 && K > 0 && J > 0, "linear_dgrad: empty problem (B=%d K=%d J=%d)", B, K, J);
   SIVAE_CHECK(ws != nullptr && ws_bytes >= linear_workspace_bytes(B, K, J), "linear_dgrad: workspace too small");
   const int vec = (K % 4 == 0) ? 4 : 1;
-  const int js = dgrad_splits(K, J, vec);
+  const int js = dgrad_splits(min(B, kLinB), K, J, vec);
   const int jps = cdiv(J, js);
   float* partial = static_cast<float*>(ws);
   for (int b0 = 0; b0 < B; b0 += kLinB) {

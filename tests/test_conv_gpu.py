@@ -30,13 +30,16 @@ SHAPES = [
 # (SIVAE_CONV_KD=force), tap-by-tap forced (SIVAE_CONV_KD=0) and the opt-in kw-slab kernel forced (SIVAE_CONV_KW=force).
 KW_MODES = ["auto", "force", "0"]
 CONV_MODES = {"auto": {}, "kd_force": {"SIVAE_CONV_KD": "force"}, "tapwise": {"SIVAE_CONV_KD": "0"},
-              "kw_force": {"SIVAE_CONV_KD": "0", "SIVAE_CONV_KW": "force"}}
+              "kw_force": {"SIVAE_CONV_KD": "0", "SIVAE_CONV_KW": "force"},
+              # the 6-stage operand ring of the Cout % 128 == 0 kernel (taken by itself only for grids <= one CTA per SM)
+              "deep_ring": {"SIVAE_CONV_KD": "0", "SIVAE_DEEP_RING": "1"},
+              "shallow_ring": {"SIVAE_CONV_KD": "0", "SIVAE_DEEP_RING": "0"}}
 
 
 @pytest.fixture(params=list(CONV_MODES))
 def kwmode(request):
     import os
-    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW")
+    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW", "SIVAE_DEEP_RING")
     old = {k: os.environ.get(k) for k in keys}
     for k in keys:
         os.environ.pop(k, None)
