@@ -45,3 +45,38 @@ def test_loss_curve_200_steps_gpu():
     # and training must actually make progress in every arm
     for arm in ("ours", "oracle", "control"):
         assert sum(c[arm]["loss_rec"][-10:]) < 0.7 * sum(c[arm]["loss_rec"][:10]), arm
+
+
+FC_SMALL = dict(chans=(4, 4, 8, 8), z_ch=6, grid=(1, 1, 1))
+
+
+def test_fc_loss_curve_wiring_cpu():
+    """FC-latent variant (mymodel.py / trainer_fc.py): 3 Adam steps of the module shells on the kernel specification
+    track the oracle (the conv biases in front of BatchNorm random-walk in the oracle, stay put in ours: no effect on
+    train-mode outputs)."""
+    with emulated_kernels():
+        c = L.run(steps=3, vol=(16, 16, 16), batch=3, n_batches=2, device="cpu", fc=FC_SMALL)
+    dev = L.deviations(c)
+    for k, v in dev.items():
+        assert v["max"] < 5e-3, (k, v)
+
+
+@pytest.mark.gpu
+def test_fc_loss_curve_100_steps_gpu():
+    """100 Adam steps of mymodel.SoftIntroVAE(16,32,32,64,32) on 32x48x32 volumes (latent grid 2x3x2), same criterion as
+    the headline test: no further from the fp32 oracle than the oracle under torch.autocast(bfloat16) is."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    c = L.run(steps=100, vol=(32, 48, 32), batch=4, n_batches=4, control=True,
+              fc=dict(chans=(16, 32, 32, 64), z_ch=32, grid=(2, 3, 2)))
+    ours, ctrl = L.deviations(c, "ours"), L.deviations(c, "control")
+    for k in ours:
+        print(f"{k:12s} ours median {ours[k]['median']:.3g} smooth_max {ours[k]['smooth_max']:.3g}   "
+              f"control median {ctrl[k]['median']:.3g} smooth_max {ctrl[k]['smooth_max']:.3g}")
+    for k in ours:
+        assert ours[k]["median"] <= 1.5 * ctrl[k]["median"] + 0.03, (k, ours[k], ctrl[k])
+        assert ours[k]["smooth_max"] <= 1.5 * ctrl[k]["smooth_max"] + 0.10, (k, ours[k], ctrl[k])
+    for k in ("lossE", "loss_rec", "kl_real"):
+        assert ours[k]["first"] < 1e-2, (k, ours[k])
+    for arm in ("ours", "oracle", "control"):
+        assert sum(c[arm]["loss_rec"][-10:]) < 0.9 * sum(c[arm]["loss_rec"][:10]), arm

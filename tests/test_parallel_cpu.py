@@ -143,3 +143,42 @@ def _flat_worker(rank, world, port, q):
 def test_flat_grad_reducer_world2_gloo():
     res = _run_world(_flat_worker)
     assert res[0] == res[1]
+
+
+def _fc_worker(rank, world, port, q):
+    """The FC-latent variant (mymodel.py) through the trainer step on two ranks with different data: the kernels are
+    replaced by their executable specification (CPU), gradients go through FlatGradReducer, Adam keeps the replicas
+    identical; biases in front of a train-mode BatchNorm and the never-run block8 keep grad None on both ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), GLOO_SOCKET_IFNAME="lo")
+    torch.set_num_threads(2)
+    import sivae_b200
+    from sivae_b200 import parallel as P
+    from sivae_b200 import trainer as T
+    from tests.emu import emulated_kernels
+    P.init_distributed("gloo")
+    torch.manual_seed(3)                                   # identical init on every rank
+    net = sivae_b200.mymodel.SoftIntroVAE(4, 4, 8, 8, 6, latent_grid=(1, 1, 1))
+    net.apply(T.init_weights_he)
+    net.train()
+    opt_e = torch.optim.Adam(net.encoder.parameters(), lr=2e-4)
+    opt_d = torch.optim.Adam(net.decoder.parameters(), lr=2e-4)
+    red_e, red_d = P.FlatGradReducer(net.encoder.parameters()), P.FlatGradReducer(net.decoder.parameters())
+    hp = T.StepHyper(scale=sivae_b200.trainer_fc.SCALE)
+    with emulated_kernels():
+        for step in range(2):
+            torch.manual_seed(50 + 7 * step + rank)        # rank-specific shard and noise
+            real, noise = torch.rand(2, 1, 16, 16, 16), torch.randn(2, 6)
+            terms = T.soft_intro_train_step(net, real, noise, opt_e, opt_d, hp, red_e, red_d)
+            assert all(float(v) == float(v) for v in terms.values())
+    none = sorted(k for k, p in net.named_parameters() if p.grad is None)
+    assert any(".block8." in k for k in none) and "encoder.block2.0.bias" in none and "encoder.fc.bias" not in none
+    flat = torch.cat([p.detach().flatten() for p in net.parameters()])
+    q.put((rank, (none, flat.tolist())))
+    dist.destroy_process_group()
+
+
+def test_fc_variant_world2_gloo():
+    res = _run_world(_fc_worker)
+    assert res[0][0] == res[1][0]          # same set of gradient-less parameters
+    assert res[0][1] == res[1][1]          # bit-identical replicas after two E+D iterations

@@ -51,7 +51,9 @@ def synthetic_volumes(n, vol, gen):
 
 
 def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setting=((64, 1, 2), (128, 1, 2), (256, 2, 2)),
-        lr=2e-4, seed=77, device="cuda", verbose=False, control=False):
+        lr=2e-4, seed=77, device="cuda", verbose=False, control=False, fc=None):
+    """``fc`` = dict(chans=(c1,c2,c3,c4), z_ch=..., grid=(gd,gh,gw)) selects the FC-latent variant (models/mymodel.py +
+    utils/trainer_fc.py: vector noise, no dropout, scale fixed at 8/(80*96*80)); ``vol`` must then be 16 * grid."""
     import sivae_b200
     from sivae_b200 import functional as F, trainer as T
     from oracle import sivae_oracle as O
@@ -61,11 +63,17 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
     dev = torch.device(device)
     bs = [list(b) for b in block_setting]
     d, h, w = vol
-    lat = (batch, 1, d // 8, h // 8, w // 8)
-    cfg = O.NetCfg.soft_intro(in_ch, bs)
+    if fc is not None:
+        assert tuple(vol) == tuple(16 * g_ for g_ in fc["grid"]), "FC-latent variant: vol must be 16 * grid"
+        lat = (batch, fc["z_ch"])
+        cfg = O.FcCfg(*fc["chans"], fc["z_ch"], tuple(fc["grid"]))
+    else:
+        lat = (batch, 1, d // 8, h // 8, w // 8)
+        cfg = O.NetCfg.soft_intro(in_ch, bs)
 
     torch.manual_seed(seed)
-    net = sivae_b200.SoftIntroVAE(in_ch, bs)
+    net = (sivae_b200.mymodel.SoftIntroVAE(*fc["chans"], fc["z_ch"], latent_grid=tuple(fc["grid"])) if fc is not None
+           else sivae_b200.SoftIntroVAE(in_ch, bs))
     net.apply(T.init_weights_he)
     net.to(dev).train()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}          # oracle's private copy
@@ -96,6 +104,8 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
     opt_e = torch.optim.Adam(net.encoder.parameters(), lr=lr)
     opt_d = torch.optim.Adam(net.decoder.parameters(), lr=lr)
     hp, ohp = T.StepHyper(), O.StepHyper()
+    if fc is not None:
+        hp, ohp = T.StepHyper(scale=8.0 / (80 * 96 * 80)), O.StepHyper(scale=8.0 / (80 * 96 * 80))   # trainer_fc.py:179
 
     gen = torch.Generator().manual_seed(1234)
     data = synthetic_volumes(batch * n_batches, vol, gen).to(dev)
@@ -106,6 +116,8 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
 
     def draw_masks():
         ms = []
+        if fc is not None:
+            return ms                                      # mymodel.py has no Dropout
         for ch in order:
             if ch == "E":
                 ms.append(torch.rand(batch, in_ch, d, h, w, device=dev, generator=g) >= 0.35)
@@ -146,13 +158,13 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
         for k in TERMS:
             curves["ours"][k].append(float(terms[k]))
         # ---- oracle
-        oterms, _, _ = O.soft_intro_step_grads(sd, cfg, real, noise, eps, [m.float() for m in masks], ohp,
-                                               apply_update=apply_update)
+        omasks = None if fc is not None else [m.float() for m in masks]
+        oterms, _, _ = O.soft_intro_step_grads(sd, cfg, real, noise, eps, omasks, ohp, apply_update=apply_update)
         for k in TERMS:
             curves["oracle"][k].append(float(oterms[k]))
         if control:
             with torch.autocast(dev.type, dtype=torch.bfloat16):
-                cterms, _, _ = O.soft_intro_step_grads(sd_c, cfg, real, noise, eps, [m.float() for m in masks], ohp,
+                cterms, _, _ = O.soft_intro_step_grads(sd_c, cfg, real, noise, eps, omasks, ohp,
                                                        apply_update=apply_update_c)
             for k in TERMS:
                 curves["control"][k].append(float(cterms[k]))
@@ -190,10 +202,16 @@ def main():
     ap.add_argument("--n-batches", type=int, default=4)
     ap.add_argument("--out", default=None, help="prefix for <out>.json / <out>.md")
     ap.add_argument("--control", action="store_true", help="also train the oracle under bf16 autocast")
+    ap.add_argument("--fc", type=int, nargs=5, default=None, metavar=("C1", "C2", "C3", "C4", "Z"),
+                    help="FC-latent variant mymodel.SoftIntroVAE(C1,C2,C3,C4,Z); the latent grid is vol/16")
     a = ap.parse_args()
-    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True, control=a.control)
+    fc = None
+    if a.fc is not None:
+        fc = dict(chans=tuple(a.fc[:4]), z_ch=a.fc[4], grid=tuple(v // 16 for v in a.vol))
+    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True, control=a.control, fc=fc)
     dev = deviations(curves)
-    lines = [f"# Loss-curve parity, {a.steps} steps, headline net, volumes {a.vol}, batch {a.batch}, "
+    netname = f"mymodel.SoftIntroVAE{tuple(a.fc)} (FC-latent variant)" if a.fc is not None else "headline net"
+    lines = [f"# Loss-curve parity, {a.steps} steps, {netname}, volumes {a.vol}, batch {a.batch}, "
              f"{a.n_batches} synthetic batches cycled, identical init / noise / eps / dropout masks", "",
              "ours = libsivae.so (bf16 activations) ; oracle = torch fp32 restatement of the reference on the same GPU", "",
              "| term | oracle first | oracle last | ours last | rel.dev median | p90 | max | 10-step-mean max |",
