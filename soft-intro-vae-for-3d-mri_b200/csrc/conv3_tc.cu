@@ -1650,11 +1650,19 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   fill_geom(g, N, D, H, W, Cin, kTapsPlain);
   const long long tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
   SIVAE_CHECK(tiles < (1ll << 31), "conv3_igemm: too many tiles");
-  // N = 256 tiles (opt-in, SIVAE_N256=1) for the 256-channel layers at the latent resolution (80 voxel tiles): one wave of
-  // 80 CTAs instead of 160 CTAs on 148 SMs.  Measured SLOWER (71 vs 64 us per conv + statistics): the doubly loaded SMs
-  // of the N = 128 grid overlap their two CTAs well, while 68 idle SMs cost more than the saved A re-reads.
-  const int block_n = (Cout % 256 == 0 && tiles <= num_sms() && getenv("SIVAE_N256") != nullptr) ? 256
-                      : (Cout % 128 == 0) ? 128 : 64;
+  // Tile width for Cout % 256 == 0 at the latent resolution (80 voxel tiles at batch 8): N = 128 gives 160 CTAs on 148
+  // SMs, N = 256 one wave of 80 CTAs that each read their A tile once.  With a 3-stage ring N = 256 measured SLOWER
+  // (55.8 vs 51.0 us per launch: 68 idle SMs cost more than the saved A re-reads), with a 4-stage ring (4 x 48 KB)
+  // FASTER (46.9 us, step 66.6 -> 65.7 ms): the k-step rate of these one-CTA-per-SM chains is TMA latency / ring depth.
+  // Grids whose N = 128 form already fits one wave keep N = 128 with the 6-stage ring below (more CTAs, deeper ring).
+  // SIVAE_N256: 0 = never, 1 = 3-stage, 4 = 4-stage whenever tiles <= SMs; unset = the rule above.
+  int n256_stages = 0;
+  if (Cout % 256 == 0 && tiles <= num_sms()) {
+    const char* e = getenv("SIVAE_N256");
+    if (e != nullptr) n256_stages = e[0] == '4' ? 4 : e[0] == '1' ? 3 : 0;
+    else if (tiles * (Cout / 128) > (long long)num_sms()) n256_stages = 4;
+  }
+  const int block_n = n256_stages ? 256 : (Cout % 128 == 0) ? 128 : 64;
   TmapPack tmA, tmC;
   CUtensorMap tmB;
   if (make_act_tmap(&tmA.m[0], x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
@@ -1662,7 +1670,10 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
   for (int i = 1; i < 8; ++i) { tmA.m[i] = tmA.m[0]; tmC.m[i] = tmC.m[0]; }
   if (make_weight_tmap(&tmB, wpack, 27, Cout, Cin, block_n)) return -1;
   const ToOneEpilogue ep{};
-  if (block_n == 256) return launch_igemm<256, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 256, ep, st);
+  if (block_n == 256) {
+    if (n256_stages == 4) return launch_igemm<256, 4, 0>(tmA, tmB, tmC, g, tiles, Cout / 256, ep, st);
+    return launch_igemm<256, 3, 0>(tmA, tmB, tmC, g, tiles, Cout / 256, ep, st);
+  }
   // Grids that leave every SM at most one CTA (latent-resolution layers of small batches) are bound by the TMA
   // round-trip of a 3-stage ring (one k-step per latency/3): a 6-stage ring keeps twice the bytes in flight.  With more
   // CTAs than SMs the 3-stage kernel wins because two of its CTAs share an SM (SIVAE_DEEP_RING=0 disables, =1 forces).
