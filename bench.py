@@ -333,7 +333,8 @@ def run_ours(args):
                 "timing": ("CUDA events around every launch of the kernel in one eager step of the same run"
                            if graphed is not None else "CUDA events around every launch inside the timed region"),
                 "whole_step_tflops": value / world * gflop_step / 1e3}
-    line = {"metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": ("train volumes/sec (Soft-IntroVAE FC-latent z=600, 80x96x80)" if fc else METRIC), "value": value,
+            "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": ("600z_main.py mymodel.SoftIntroVAE(32,64,128,256,600) FC-latent variant, 80x96x80, "

@@ -1,0 +1,8 @@
+#!/bin/bash
+# round-end verification: all GPU tests, smoke(), headline bench (with cpu baseline + kernel table), fc600 bench
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+echo "== all gpu tests"; timeout 1800 python -m pytest tests -q -m gpu --tb=short -x > gpurun_out/t_all.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/t_all.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/smoke.log
+echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 --kernel-table gpurun_out/kernel_table.txt > gpurun_out/bench.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench.log | cut -c1-400; head -12 gpurun_out/kernel_table.txt
+echo "== fc600"; timeout 600 python bench.py --workload fc600 --batch 4 --steps 5 --warmup 3 --kernel-table gpurun_out/fc600_kernel_table.txt > gpurun_out/fc600_bench.json 2> gpurun_out/fc600_bench.err; echo "rc=$?"; cut -c1-200 gpurun_out/fc600_bench.json
