@@ -51,18 +51,24 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  The sampler is started before the warm-up (nvidia-smi
+    needs about a second to deliver its first line) and ``mark()`` is called when the timed region begins: only
+    samples from then on are reported (if the region is shorter than one period, the samples taken under the same
+    load during the warm-up are used and the result says so)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.proc, self.lines, self.index = None, [], index
+        self.proc, self.lines, self.index, self.first = None, [], index, 0
+
+    def mark(self):
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -77,7 +83,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = self.lines[self.first:]
+        note = "timed region"
+        if len(window) < 2:
+            window, note = self.lines, "warm-up + timed region (timed region shorter than two sampling periods)"
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -89,21 +99,39 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": note}
 
 
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU path (torch fp32, oneDNN) via the oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step_factory(vol=VOL, batch=1, threads=None):
-    """One full Soft-IntroVAE E+D iteration of the headline net on the host cores (fp32, gradients for both
-    phases; the Adam update itself is negligible).  /root/reference does not exist on the GPU box, so this is
-    the oracle port (oracle/sivae_oracle.py, validated against the reference in tests/)."""
+def cpu_reference_step_factory(vol=VOL, batch=1, threads=None, workload="z1200"):
+    """One full Soft-IntroVAE E+D iteration of the headline net (or, workload "fc600", of the FC-latent variant
+    mymodel.SoftIntroVAE(32,64,128,256,600)) on the host cores (fp32, gradients for both phases; the Adam update
+    itself is negligible).  /root/reference does not exist on the GPU box, so this is the oracle port
+    (oracle/sivae_oracle.py, validated against the reference in tests/)."""
     from oracle import sivae_oracle as O
     torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(77)
-    cfg = O.NetCfg.soft_intro(IN_CH, BLOCK_SETTING)
     import sivae_b200
+    if workload == "fc600":
+        small = O.FcCfg(*FC600["chans"], FC600["z_ch"], (1, 1, 1))
+        cfg = O.FcCfg(*FC600["chans"], FC600["z_ch"], FC600["grid"])
+        nets = {}
+        for c in (small, cfg):                                     # parameter holders only (never run on CPU)
+            net = sivae_b200.mymodel.SoftIntroVAE(*FC600["chans"], FC600["z_ch"], latent_grid=c.grid)
+            net.apply(sivae_b200.init_weights_he)
+            nets[c.grid] = {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+        def step(v=vol):
+            c = cfg if tuple(v) == tuple(vol) else small
+            d, h, w = (16 * g for g in c.grid)
+            real = torch.rand(batch, 1, d, h, w)
+            noise = torch.randn(batch, FC600["z_ch"])
+            eps = [torch.randn(batch, FC600["z_ch"]) for _ in range(5)]
+            O.soft_intro_step_grads(nets[c.grid], c, real, noise, eps, None, O.StepHyper(scale=8.0 / (80 * 96 * 80)))
+        return step
+    cfg = O.NetCfg.soft_intro(IN_CH, BLOCK_SETTING)
     net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)          # parameter holder only (never run on CPU)
     net.apply(sivae_b200.init_weights_he)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
@@ -122,21 +150,27 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    step = cpu_reference_step_factory(threads=threads)
+    fc = getattr(args, "workload", "z1200") == "fc600"
+    batch = 2 if fc else 1            # the FC-latent variant normalises over B*150 values at the latent grid: keep B >= 2
+    step = cpu_reference_step_factory(threads=threads, workload="fc600" if fc else "z1200", batch=batch)
     for _ in range(args.warmup):
-        step((16, 24, 16))            # warm-up on a reduced volume keeps the run bounded
+        step((16, 16, 16) if fc else (16, 24, 16))   # warm-up on a reduced volume keeps the run bounded
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    val = args.steps * 1 / dt
-    sample = (f"{args.steps} x (1 volume 80x96x80, one full E+D iteration, headline net, fp32 torch-CPU/oneDNN, "
-              f"{threads} threads); warm-up on 16x24x16")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "volumes/s", "n_gpus": args.gpus,
+    val = args.steps * batch / dt
+    sample = (f"{args.steps} x ({batch} volume(s) 80x96x80, one full E+D iteration, "
+              f"{'mymodel.SoftIntroVAE(32,64,128,256,600)' if fc else 'headline net'}, fp32 torch-CPU/oneDNN, "
+              f"{threads} threads); warm-up on a reduced volume")
+    line = {"impl": "reference", "metric": ("train volumes/sec (Soft-IntroVAE FC-latent z=600, 80x96x80)" if fc else METRIC),
+            "value": val, "unit": "volumes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "z-1200main.py Soft-IntroVAE z=1200, 80x96x80, one E+D train step",
-                       "local_batch": 1, "device": "host CPU"},
+            "config": {"workload": ("600z_main.py mymodel.SoftIntroVAE(32,64,128,256,600) FC-latent variant, 80x96x80, one "
+                                    "trainer_fc E+D train step" if fc else
+                                    "z-1200main.py Soft-IntroVAE z=1200, 80x96x80, one E+D train step"),
+                       "local_batch": batch, "device": "host CPU"},
             "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -177,6 +211,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     K.device_check()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()                                     # early: nvidia-smi takes ~1 s to deliver its first sample
     B = args.batch
     D, H, W = args.vol
     fc = args.workload == "fc600"
@@ -267,9 +304,8 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 1)):
         step_resident()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark()
     n0 = K.launch_count()
     with K.KernelTimer() as kt:
         ms, terms = timed(step_resident, args.steps)
@@ -356,15 +392,17 @@ def run_ours(args):
                                     "full-resolution layers execute 4x their reference-equivalent FLOPs; 'achieved' "
                                     "counts executed (padded) FLOPs of the conv kernels, 'whole_step_tflops' "
                                     "reference-equivalent ones")
-    if world == 1 and not args.no_cpu_baseline and not fc:
+    if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        step = cpu_reference_step_factory(threads=threads)
-        step((16, 24, 16))
+        cb = 2 if fc else 1
+        step = cpu_reference_step_factory(threads=threads, workload=args.workload, batch=cb)
+        step((16, 16, 16) if fc else (16, 24, 16))
         t0 = time.perf_counter()
         step()
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "volumes/s", "cores": threads, "kind": "port",
-                                "sample": "1 volume 80x96x80, one full E+D iteration of the headline net, fp32 "
+        line["cpu_baseline"] = {"value": cb / dt, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                "sample": f"{cb} volume(s) 80x96x80, one full E+D iteration of "
+                                          f"{'mymodel.SoftIntroVAE(32,64,128,256,600)' if fc else 'the headline net'}, fp32 "
                                           f"torch-CPU/oneDNN on {threads} threads ({dt:.1f} s)"}
     print(json.dumps(line), flush=True)
     if world > 1:
