@@ -1,5 +1,6 @@
 #!/bin/bash
-# round-end verification: all GPU tests, smoke(), headline bench (with cpu baseline + kernel table), fc600 bench
+# Round-end verification on one B200 (run through gpurun):  bash tools/gpu/verify.sh
+# all GPU tests, __graft_entry__.smoke(), headline bench (cpu baseline + per-kernel table), FC-latent bench.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 echo "== all gpu tests"; timeout 1800 python -m pytest tests -q -m gpu --tb=short -x > gpurun_out/t_all.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/t_all.log
