@@ -14,10 +14,10 @@ reparameterisation eps and dropout keep-masks, with Adam(lr 2e-4) as utils/my_tr
            and the KL terms are sums of exp(logvar) (kl_real jumps by 4-6 orders of magnitude at step 1), so two
            roundings of the same trajectory separate quickly.  Parity is therefore stated relative to the control.
 
-and the per-step loss terms are compared.  Used by tests/test_loss_curve_gpu.py (short run, asserted) and from the
+and the per-step loss terms are compared.  Test infrastructure (it trains the oracle side by side with the product): used by tests/test_loss_curve.py (short runs, asserted) and from the
 command line to write profiles/*_loss_curve.{json,md}:
 
-    python tools/loss_curve.py --steps 200 --vol 40 48 40 --batch 4 --out profiles/r01_loss_curve
+    python tests/loss_curve.py --steps 200 --vol 40 48 40 --batch 4 --out profiles/r01_loss_curve
 """
 import argparse
 import json

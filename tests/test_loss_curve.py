@@ -1,5 +1,5 @@
 """Loss-curve parity over many optimiser steps (north_star: "loss-curve parity to the reference over 200 synthetic
-steps"): tools/loss_curve.py trains the drop-in model and the fp32 oracle side by side with Adam on identical
+steps"): tests/loss_curve.py trains the drop-in model and the fp32 oracle side by side with Adam on identical
 batches / noise / eps / dropout masks.
 
 CPU: the host logic (module shells, autograd wiring, phase freezing, Adam) with libsivae.so replaced by the fp32
@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from tests.emu import emulated_kernels
-from tools import loss_curve as L
+from tests import loss_curve as L
 
 
 def test_loss_curve_wiring_cpu():
