@@ -130,7 +130,7 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
     // ===== TMA producer =====
     // Nested tap / K-block loops with incremental stage and phase counters: no per-iteration divisions in the single
     // producing thread (its bookkeeping has to stay well below the ~400 cycles a K block's MMAs take).
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)g.rows * 128u + (uint32_t)B_BYTES;
       int s = 0;
       uint32_t ph = 0;
@@ -162,24 +162,24 @@ conv3_igemm_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__
       }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024), bdesc = make_smem_desc(a_addr + kTileBytes, 16, 1024);
+    // ===== MMA issuer: one elected thread runs the whole loop (a per-step elect + __syncwarp costs more issue slots
+    // than the four UMMAs of a K block; the descriptors are base + stage * constant) =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+      uint32_t s = 0, ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = desc0 + (uint64_t)(s * (uint32_t)(STAGE_BYTES >> 4));
+        const uint64_t bdesc = adesc + (uint64_t)(kTileBytes >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 64-channel K block = 4 x UMMA_K(16); +32 bytes = +2 in the (address >> 4) field
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA store =====
@@ -317,7 +317,7 @@ conv3_kw64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp_id == 0) {
     // ===== A producer: one tall box per kw shift, two buffers, running ahead across work items =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         int nb, w0, h0, d0, n;
@@ -332,7 +332,7 @@ conv3_kw64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp_id == 2) {
     // ===== B producer: weight slab of tap (kd, kh, kw) in MMA order =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         const int nb = (int)(item % g.nblk);
@@ -517,7 +517,7 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp_id == 0) {
     // ===== A producer: per (kh, kw) pass the P + 2 input planes of the chunk, one 16 KB tile each =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         int w0, h0, d0, n;
@@ -536,7 +536,7 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp_id == 2) {
     // ===== B producer: the three kd slabs of one (kh, kw), stacked =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x)
         for (int pass = 0; pass < 9; ++pass)
@@ -550,28 +550,30 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: one elected thread for the whole loop =====
     // The tile loop is fully unrolled so that column offsets, slab offsets and instruction descriptors are immediates:
     // a single thread issues every UMMA, and its bookkeeping must stay well below the ~600 cycles a tile's MMAs take.
-    uint32_t a_it = 0, b_it = 0, acc_it = 0;
-    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
-      const uint32_t as = acc_it & 1;
-      mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 256u;
-      for (int pc = 0; pc < 9 * g.cin_blocks; ++pc, ++b_it) {   // (pass, K block) pairs, K block fastest
-        const uint32_t bs = b_it % kKdBStages;
-        mbar_wait(&b_full[bs], (b_it / kKdBStages) & 1u);
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kKdBBytes), 16, 1024);
-        const bool pass0 = (pc == 0);                            // first tap, first K block: overwrite
-        const bool last = (pc == 9 * g.cin_blocks - 1);
+    // Ring slots / phases are counters with a wrap, descriptors are base + slot * constant, and there is no per-step
+    // elect / __syncwarp (see upconv3_fused_kernel for the measurement behind this).
+    if (elect_one()) {
+      uint32_t sa = 0, pa = 0, bs = 0, pb = 0, acc_it = 0;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 16, 1024);
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+        const uint32_t as = acc_it & 1;
+        mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256u;
+        for (int pc = 0; pc < 9 * g.cin_blocks; ++pc) {   // (pass, K block) pairs, K block fastest
+          mbar_wait(&b_full[bs], pb);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(bs * (uint32_t)(kKdBBytes >> 4));
+          const bool pass0 = (pc == 0);                            // first tap, first K block: overwrite
+          const bool last = (pc == 9 * g.cin_blocks - 1);
 #pragma unroll
-        for (int t = 0; t < kKdP + 2; ++t, ++a_it) {
-          const uint32_t sa = a_it % kKdAStages;
-          mbar_wait(&a_full[sa], (a_it / kKdAStages) & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kTileBytes), 16, 1024);
+          for (int t = 0; t < kKdP + 2; ++t) {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            const uint64_t adesc = adesc0 + (uint64_t)(sa * (uint32_t)(kTileBytes >> 4));
             // input plane t of the chunk feeds output plane i = t - kd through tap kd, 0 <= i < P  (all compile time)
             constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
             const int kd_lo0 = t - (kKdP - 1) > 0 ? t - (kKdP - 1) : 0;
@@ -598,8 +600,9 @@ conv3_kd3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_commit(&b_empty[bs]);
               if (last) umma_commit(&acc_full[as]);
             }
+            if (++sa == kKdAStages) { sa = 0; pa ^= 1u; }
           }
-          __syncwarp();
+          if (++bs == kKdBStages) { bs = 0; pb ^= 1u; }
         }
       }
     }
@@ -765,7 +768,7 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp_id == 0) {
     // ===== A producer: per depth tap the 9 shifted low-res tiles (x cin_blocks K blocks) =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         int w0, h0, d, pd, n;
@@ -787,7 +790,7 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp_id == 2) {
     // ===== B producer: the 1..4 weight slabs of a shifted tile, stacked in unit order =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
         const int pd = (int)(item & 1);
@@ -811,32 +814,41 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer =====
-    uint32_t a_it = 0, b_it = 0, acc_it = 0;
-    for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
-      const uint32_t as = acc_it & 1;
-      mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 256u;
-      uint32_t sa = 0;
-      for (int cb = 0; cb < g.cin_blocks; ++cb)
-        for (int ad = 0; ad < 2; ++ad) {
-          const uint32_t first = (cb == 0 && ad == 0) ? 0u : 1u;   // steps 0, 1 of the first tap overwrite all 4 parities
-          const bool last = (cb == g.cin_blocks - 1 && ad == 1);
+    // ===== MMA issuer: ONE thread for the whole loop =====
+    // The issue loop is a single dependent instruction stream: at ~85 SASS instructions per 4-UMMA step (a warp-wide
+    // elect + reconvergence, ring indices by division, descriptors rebuilt from shared-memory addresses) it ran at
+    // ~680 cycles per step against 256 cycles of tensor work (ncu: tensor pipe 37 % active, the issuing warp never
+    // waiting on a barrier).  So: no per-step elect / __syncwarp, ring slot + phase kept as counters with a wrap,
+    // descriptors = base + slot * constant.  elect.sync (not lane == 0): only then does the compiler treat the region
+    // as uniform and feed UTCHMMA / UTCBAR from uniform registers; under a lane test it wraps EVERY tcgen05
+    // instruction in its own elect loop (~9 extra instructions each).
+    if (elect_one()) {
+      uint32_t sa_next = 0, pa = 0, sa = 0;          // A ring: next slot to take, its phase, slot in use
+      uint32_t sb = 0, pb = 0;                       // B ring
+      uint32_t acc_it = 0;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 16, 1024);
+      for (long long item = blockIdx.x; item < g.items; item += gridDim.x, ++acc_it) {
+        const uint32_t as = acc_it & 1;
+        mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256u;
+        for (int cb = 0; cb < g.cin_blocks; ++cb)
+          for (int ad = 0; ad < 2; ++ad) {
+            const uint32_t first = (cb == 0 && ad == 0) ? 0u : 1u;   // steps 0, 1 of the first tap overwrite all 4 parities
+            const bool last = (cb == g.cin_blocks - 1 && ad == 1);
 #pragma unroll
-          for (int t = 0; t < kUpSteps; ++t, ++b_it) {
-            constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc128 = make_idesc_bf16(128, 128, 0, 0);
-            if (up_step_c(t).new_a) {
-              sa = a_it % kUpAStages;
-              mbar_wait(&a_full[sa], (a_it / kUpAStages) & 1u);
-              ++a_it;
-            }
-            const uint32_t sb = b_it % kUpBStages;
-            mbar_wait(&b_full[sb], (b_it / kUpBStages) & 1u);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kTileBytes), 16, 1024);
-              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * kUpBSlot), 16, 1024);
+            for (int t = 0; t < kUpSteps; ++t) {
+              constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc128 = make_idesc_bf16(128, 128, 0, 0);
+              if (up_step_c(t).new_a) {
+                sa = sa_next;
+                mbar_wait(&a_full[sa], pa);
+                if (++sa_next == kUpAStages) { sa_next = 0; pa ^= 1u; }
+              }
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint64_t adesc = adesc0 + (uint64_t)(sa * (uint32_t)(kTileBytes >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(sb * (uint32_t)(kUpBSlot >> 4));
               if (up_step_c(t).stacked) {
                 const uint32_t col = (uint32_t)(up_step_c(t).pw[0] * 2 + up_step_c(t).ph[0]) * 64u;
 #pragma unroll
@@ -855,10 +867,10 @@ upconv3_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (up_step_c(t).rel_a) umma_commit(&a_empty[sa]);
               umma_commit(&b_empty[sb]);
               if (last && t == kUpSteps - 1) umma_commit(&acc_full[as]);
+              if (++sb == kUpBStages) { sb = 0; pb ^= 1u; }
             }
-            __syncwarp();
           }
-        }
+      }
     }
   } else {
     // ===== epilogue (warps 3..6 <-> TMEM lane quadrants 3,0,1,2): four parity tiles per item =====
@@ -1010,7 +1022,7 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t tile_tx = (uint32_t)g.rows * 128u;
 
   if (warp_id == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t a_it = 0, b_it = 0;
       // voxel-box coordinates advance incrementally (one 64-bit decode per CTA, none per box)
       int w0, h0, d0, n;
@@ -1059,20 +1071,21 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
   } else if (warp_id == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
-    const int k16s = rows_pad / 16;
-    uint32_t a_it = 0, b_it = 0;
-    for (long long kb = kb0; kb < kb1; ++kb) {
-      const int bs = b_it % B_STAGES;
-      mbar_wait(&b_full[bs], (b_it / B_STAGES) & 1u);
-      const uint32_t b_addr = smem_u32(smem_b + bs * B_STAGE_BYTES);
-      for (int lp = 0; lp < npairs; ++lp) {
-        const int as = a_it % A_STAGES;
-        mbar_wait(&a_full[as], (a_it / A_STAGES) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + as * A_STAGE_BYTES), g.a_lbo, g.a_sbo);
-          const uint64_t bdesc = make_smem_desc(b_addr, g.b_lbo, g.b_sbo);
+    // one elected thread issues the whole loop (no per-step elect / __syncwarp; ring counters with a wrap; descriptors
+    // = base + stage * constant)
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
+      const int k16s = rows_pad / 16;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), g.a_lbo, g.a_sbo);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), g.b_lbo, g.b_sbo);
+      uint32_t as = 0, pa = 0, bs = 0, pb = 0;
+      for (long long kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&b_full[bs], pb);
+        const uint64_t bdesc = bdesc0 + (uint64_t)(bs * (uint32_t)(B_STAGE_BYTES >> 4));
+        for (int lp = 0; lp < npairs; ++lp) {
+          mbar_wait(&a_full[as], pa);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)(as * (uint32_t)(A_STAGE_BYTES >> 4));
           for (int k = 0; k < k16s; ++k)  // 16 voxel rows (2048 B = +128 in the descriptor's address field) per UMMA
             umma_bf16(tmem_base + (uint32_t)(lp * NT), adesc + 128 * k, bdesc + 128 * k, idesc,
                       (kb > kb0 || k > 0) ? 1u : 0u);
@@ -1081,11 +1094,10 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             umma_commit(&b_empty[bs]);
             if (kb == kb1 - 1) umma_commit(tmem_full_bar);
           }
+          if (++as == A_STAGES) { as = 0; pa ^= 1u; }
         }
-        __syncwarp();
-        ++a_it;
+        if (++bs == B_STAGES) { bs = 0; pb ^= 1u; }
       }
-      ++b_it;
     }
   } else {
     mbar_wait(tmem_full_bar, 0);
@@ -1183,7 +1195,7 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 
   if (warp_id == 0) {
     // ===== X producer: the tall box of this CTA's kw shift =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = it0; item < it1; ++item, ++it) {
         int w0, h0, d0, n;
@@ -1196,7 +1208,7 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else if (warp_id == 2) {
     // ===== dy producer: the two output-gradient tiles of the item (depth d0 + 1 may be out of range: zero fill) =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = it0; item < it1; ++item) {
         int w0, h0, d0, n;
@@ -1210,19 +1222,19 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-    uint32_t a_it = 0, b_it = 0;
-    for (long long item = it0; item < it1; ++item, ++a_it) {
-      const uint32_t s = a_it & 1;
-      mbar_wait(&a_full[s], (a_it >> 1) & 1u);
-      const uint32_t a_base = smem_u32(smem + s * kKwABytes);
-      for (int j = 0; j < 2; ++j, ++b_it) {
-        const uint32_t bs = b_it % kWgKwBStages;
-        mbar_wait(&b_full[bs], (b_it / kWgKwBStages) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kTileBytes), kTileBytes, 1024);
+    // ===== MMA issuer: one elected thread for the whole loop =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), kTileBytes, 1024);
+      uint32_t a_it = 0, bs = 0, pb = 0;
+      for (long long item = it0; item < it1; ++item, ++a_it) {
+        const uint32_t s = a_it & 1;
+        mbar_wait(&a_full[s], (a_it >> 1) & 1u);
+        const uint32_t a_base = smem_u32(smem + s * kKwABytes);
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&b_full[bs], pb);
+          tc_fence_after();
+          const uint64_t bdesc = bdesc0 + (uint64_t)(bs * (uint32_t)(kTileBytes >> 4));
           const bool first = (item == it0 && j == 0);
 #pragma unroll
           for (int acc = 0; acc < 5; ++acc) {
@@ -1241,8 +1253,8 @@ conv3_wgrad_kw64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             umma_commit(&a_empty[s]);
             if (item == it1 - 1) umma_commit(tmem_full_bar);
           }
+          if (++bs == kWgKwBStages) { bs = 0; pb ^= 1u; }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -1343,7 +1355,7 @@ upconv3_wgrad_tall_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 
   if (warp_id == 0) {
     // ===== X producer: the tall low-res box of this CTA's w shift =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = it0; item < it1; ++item, ++it) {
         int w0, h0, d0, n;
@@ -1356,7 +1368,7 @@ upconv3_wgrad_tall_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
   } else if (warp_id == 2) {
     // ===== dy producer: parity tiles (pd, ph, pw) of planes d0, d0 + 1 (plane d0 + 1 may be out of range: zero fill) =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long item = it0; item < it1; ++item) {
         int w0, h0, d0, n;
@@ -1371,21 +1383,21 @@ upconv3_wgrad_tall_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       }
     }
   } else if (warp_id == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-    uint32_t a_it = 0, b_it = 0;
-    for (long long item = it0; item < it1; ++item, ++a_it) {
-      const uint32_t s = a_it & 1;
-      mbar_wait(&a_full[s], (a_it >> 1) & 1u);
-      const uint32_t a_base = smem_u32(smem + s * kKwABytes);
+    // ===== MMA issuer: one elected thread for the whole loop =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), kTileBytes, 1024);
+      uint32_t a_it = 0, bs = 0, pb = 0;
+      for (long long item = it0; item < it1; ++item, ++a_it) {
+        const uint32_t s = a_it & 1;
+        mbar_wait(&a_full[s], (a_it >> 1) & 1u);
+        const uint32_t a_base = smem_u32(smem + s * kKwABytes);
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp, ++b_it) {             // (plane j, depth parity pd), pd fastest
-        const int j = jp >> 1, pd = jp & 1;
-        const uint32_t bs = b_it % kWgKwBStages;
-        mbar_wait(&b_full[bs], (b_it / kWgKwBStages) & 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + bs * kTileBytes), kTileBytes, 1024);
+        for (int jp = 0; jp < 4; ++jp) {                     // (plane j, depth parity pd), pd fastest
+          const int j = jp >> 1, pd = jp & 1;
+          mbar_wait(&b_full[bs], pb);
+          tc_fence_after();
+          const uint64_t bdesc = bdesc0 + (uint64_t)(bs * (uint32_t)(kTileBytes >> 4));
           const bool first = (item == it0 && j == 0);      // first contribution to the accumulators of this pd
 #pragma unroll
           for (int ad = 0; ad < 2; ++ad) {
@@ -1401,8 +1413,8 @@ upconv3_wgrad_tall_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             umma_commit(&a_empty[s]);
             if (item == it1 - 1) umma_commit(tmem_full_bar);
           }
+          if (++bs == kWgKwBStages) { bs = 0; pb ^= 1u; }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -1950,7 +1962,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp_id == 0) {
     // ===== TMA producer: weights once, then one input plane at a time =====
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(b_full, kHBBytes);
       tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
       tma_load_3d(smem_b + 32 * 128, &tmB, b_full, 0, 0, 1);
@@ -1968,30 +1980,33 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp_id == 1) {
     // ===== MMA issuer: per input plane 2 M-tiles x 4 K steps of UMMA 128 x 64 x 16, one TMEM slot per M-tile =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
-    mbar_wait(b_full, 0);
-    const uint32_t b_addr = smem_u32(smem_b);
-    uint32_t it = 0, sl = 0;
-    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
-      int w0, h0, d_lo, d_hi, n;
-      decode(item, w0, h0, d_lo, d_hi, n);
-      for (int z = d_lo - 1; z <= d_hi; ++z, ++it) {
-        const uint32_t s = it % kSASlots;
-        mbar_wait(&a_full[s], (it / kSASlots) & 1u);
-        const uint32_t a_addr = smem_u32(smem + s * kSASlot);
-        for (int m = 0; m < 2; ++m, ++sl) {
-          const uint32_t slot = sl % kHSlots;
-          mbar_wait(&slot_empty[slot], ((sl / kHSlots) & 1u) ^ 1u);
-          tc_fence_after();
-          if (elect_one()) {
+    // One elected thread for the whole loop: with 4 UMMAs of N = 64 (128 cycles of tensor work) per M-tile, a per-step
+    // elect + __syncwarp and rebuilt descriptors (~85 instructions, ~680 cycles) made the issuer the pace setter.
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(b_full, 0);
+      const uint64_t bdesc = make_smem_desc(smem_u32(smem_b), 16, 1024);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+      uint32_t s = 0, pa = 0, slot = 0, ps = 1;               // ps: phase to wait for on slot_empty (starts "free")
+      for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        int w0, h0, d_lo, d_hi, n;
+        decode(item, w0, h0, d_lo, d_hi, n);
+        for (int z = d_lo - 1; z <= d_hi; ++z) {
+          mbar_wait(&a_full[s], pa);
+          const uint64_t adesc = adesc0 + (uint64_t)(s * (uint32_t)(kSASlot >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + slot * 64u, make_smem_desc(a_addr + m * kTileBytes + k * 32, 16, 1024),
-                        make_smem_desc(b_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+          for (int m = 0; m < 2; ++m) {
+            mbar_wait(&slot_empty[slot], ps);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // +32 bytes per K step = +2 in the descriptor's (address >> 4) field
+              umma_bf16(tmem_base + slot * 64u, adesc + (uint64_t)(m * (kTileBytes >> 4) + 2 * k), bdesc + 2 * k, idesc,
+                        k != 0 ? 1u : 0u);
             umma_commit(&slot_full[slot]);
             if (m == 1) umma_commit(&a_empty[s]);
+            if (++slot == kHSlots) { slot = 0; ps ^= 1u; }
           }
-          __syncwarp();
+          if (++s == kSASlots) { s = 0; pa ^= 1u; }
         }
       }
     }
@@ -2149,33 +2164,33 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
 
   if (warp_id == 4) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(b_full, kC1BBytes);
       tma_load_3d(smem_b, &tmB, b_full, 0, 0, 0);
       tma_load_3d(smem_b + 64 * 128, &tmB, b_full, 0, 0, 1);
     }
     __syncwarp();
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
-    mbar_wait(b_full, 0);
-    const uint32_t b_addr = smem_u32(smem_b);
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-      const uint32_t s = it & 1, ph = (it >> 1) & 1u;
-      mbar_wait(&acc_empty[s], ph ^ 1u);
-      mbar_wait(&a_full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * kC1ABytes);
+    if (elect_one()) {                       // one elected thread issues the whole loop
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(b_full, 0);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 16, 1024);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const uint32_t s = it & 1, ph = (it >> 1) & 1u;
+        mbar_wait(&acc_empty[s], ph ^ 1u);
+        mbar_wait(&a_full[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(s * (uint32_t)(kC1ABytes >> 4));
 #pragma unroll
         for (int kk = 0; kk < 6; ++kk) {   // K block 0: 4 steps [x_hi | x_lo], K block 1: 2 steps [x_hi]
           const int kb = kk >> 2, k = kk & 3;
-          umma_bf16(tmem_base + s * 64u, make_smem_desc(a_addr + kb * kTileBytes + k * 32, 16, 1024),
-                    make_smem_desc(b_addr + kb * 64 * 128 + k * 32, 16, 1024), idesc, kk != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + s * 64u, adesc + (uint64_t)(kb * (kTileBytes >> 4) + 2 * k),
+                    bdesc0 + (uint64_t)(kb * (64 * 128 >> 4) + 2 * k), idesc, kk != 0 ? 1u : 0u);
         }
         umma_commit(&a_empty[s]);
         umma_commit(&acc_full[s]);
       }
-      __syncwarp();
     }
   } else if (warp_id < 4) {
     // ===== builders: one A row (output voxel) per thread =====
@@ -2427,7 +2442,7 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
   };
 
   if (warp_id == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (long long it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % kWg1Stages);
         mbar_wait(&empty[s], (uint32_t)((it / kWg1Stages) & 1) ^ 1u);
@@ -2438,23 +2453,24 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
       }
     }
   } else if (warp_id == 5) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-    for (long long it = 0; it < my_tiles; ++it) {
-      const int s = (int)(it % kWg1Stages);
-      const uint32_t ph = (uint32_t)((it / kWg1Stages) & 1);
-      mbar_wait(&a_full[s], ph);
-      mbar_wait(&b_full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE), b_addr = smem_u32(smem_b + s * B_STAGE);
+    if (elect_one()) {                       // one elected thread issues the whole loop
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), kTileBytes, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), kTileBytes, 1024);
+      uint32_t s = 0, ph = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        mbar_wait(&a_full[s], ph);
+        mbar_wait(&b_full[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(s * (uint32_t)(A_STAGE >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)(s * (uint32_t)(B_STAGE >> 4));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // 16 voxel rows per UMMA
-          umma_bf16(tmem_base, make_smem_desc(a_addr + k * 2048, kTileBytes, 1024),
-                    make_smem_desc(b_addr + k * 2048, kTileBytes, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // 16 voxel rows (2048 B = +128 in the descriptor's address field) per UMMA
+          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
         if (it == my_tiles - 1) umma_commit(tmem_full_bar);
+        if (++s == kWg1Stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
     }
   } else {
     const int row = threadIdx.x;                          // voxel row of the tile
