@@ -25,6 +25,27 @@ def test_product_path_fails_loudly_without_cuda():
         T.calc_kl(torch.zeros(2, 1, 2, 2, 2), torch.zeros(2, 1, 2, 2, 2))
 
 
+def test_every_product_entry_fails_loudly_without_cuda():
+    """No CPU or PyTorch fallback anywhere on the product path: FC-latent variant, optimiser, retrieval, pipeline."""
+    err = sivae_b200.kernels.SivaeError
+    fc = sivae_b200.mymodel.SoftIntroVAE(4, 4, 8, 8, 6, latent_grid=(1, 1, 1))
+    with pytest.raises(err):
+        fc(torch.rand(1, 1, 16, 16, 16))
+    with pytest.raises(err):
+        fc.decode(torch.randn(2, 6))
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(err):
+        sivae_b200.FusedAdam([p], lr=1e-3).step()
+    with pytest.raises(err):
+        sivae_b200.topk_similar(torch.randn(3, 4), torch.randn(5, 4), k=2)
+    with pytest.raises(err):
+        sivae_b200.pipeline.preprocess(torch.rand(1, 1, 4, 4, 4))
+    with pytest.raises(err):
+        sivae_b200.lossf.normal_loss(torch.rand(1, 1, 4, 4, 4), torch.zeros(1, 1, 1, 1, 1), torch.zeros(1, 1, 1, 1, 1),
+                                     torch.rand(1, 1, 4, 4, 4))
+
+
 def test_state_dict_contract(golden_dir):
     g = _load(golden_dir, "sivae_small.pt")
     net = sivae_b200.SoftIntroVAE(g["in_ch"], g["block_setting"])
