@@ -82,6 +82,8 @@ _SIGNATURES = {
     "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
     "sivae_affine_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sivae_conv3_igemm_splitk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "sivae_conv3_igemm_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "sivae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
@@ -251,8 +253,18 @@ def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
     assert wpack.shape == (27, co, ci), (wpack.shape, ci)
     y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
     flops = 2.0 * 27 * ci * co * n * d * h * w
+    lib = _L()
+    if os.environ.get("SIVAE_SPLITK") == "1":
+        # EXPERIMENTAL (see include/sivae.h): split-K over the taps for shapes with too few voxel tiles to fill the GPU
+        nbytes = lib.sivae_conv3_igemm_splitk_workspace_bytes(n, d, h, w, ci, co)
+        if nbytes > 0:
+            ws = _workspace(x.device, nbytes, "splitk")
+            _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
+                   lambda: _check(lib.sivae_conv3_igemm_ws(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _p(ws), ws.numel(),
+                                                           _stream(x)), "sivae_conv3_igemm_ws"))
+            return y
     _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
-           lambda: _check(_L().sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
+           lambda: _check(lib.sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
                           "sivae_conv3_igemm"))
     return y
 
