@@ -14,7 +14,6 @@ requires grad (the trainer freezes encoder / decoder per phase, utils/my_trainer
 """
 from __future__ import annotations
 
-import os
 import weakref
 from typing import Optional
 
@@ -136,27 +135,6 @@ def drop_packs(weight: torch.Tensor, up: Optional[bool] = None):
         _pack_cache.pop((id(weight), kind), None)
 
 
-_side_streams = {}
-SMALL_BWD_VOXELS = 16384          # N*D*H*W of the output gradient up to which dgrad / wgrad overlap on two streams
-
-
-def _side_stream(device):
-    st = _side_streams.get(device)
-    if st is None:
-        st = torch.cuda.Stream(device)
-        _side_streams[device] = st
-    return st
-
-
-def _overlap_small_bwd(dconv: torch.Tensor) -> bool:
-    # opt-in (SIVAE_BWD_OVERLAP=1): measured neutral in the step (66.4 vs 66.4 ms headline, 38.3 vs 38.6 ms FC-latent
-    # variant, A/B/A/B on one box) -- these grids already put one CTA on nearly every SM and each CTA owns the SM's
-    # shared memory, so the second kernel has nowhere to run
-    if not dconv.is_cuda or os.environ.get("SIVAE_BWD_OVERLAP", "0") != "1":
-        return False
-    return dconv.numel() // dconv.shape[-1] <= SMALL_BWD_VOXELS
-
-
 class _ConvBnAct(torch.autograd.Function):
     """``pre_up``: a nearest Upsample(2) sits in front of the convolution (UpsampleBuildingkBlock, models.py:58-59);
     it is folded into the convolution (8 output parities x 8 pre-summed taps) instead of being materialised."""
@@ -200,18 +178,6 @@ class _ConvBnAct(torch.autograd.Function):
                                                   need_dres=bool(need_res and res is not None),
                                                   need_affine=bool(need_g or need_b))
         dx = dw = None
-        if need_x and need_w and _overlap_small_bwd(dconv):
-            # experiment (see _overlap_small_bwd): dgrad and wgrad of a latent-resolution layer only share the input
-            # dconv, so the weight gradient can run on a side stream (fork / join around the pair; inside a CUDA-graph
-            # capture this becomes two parallel branches)
-            cur = torch.cuda.current_stream(dconv.device)
-            side = _side_stream(dconv.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                dw = K.upconv3_wgrad(x, dconv) if pre_up else K.conv3_wgrad(x, dconv)
-            dx = K.upconv3_dgrad(dconv, wd) if pre_up else K.conv3_igemm(dconv, wd)
-            cur.wait_stream(side)
-            return dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), dres, None, None, None, None
         if need_x:
             dx = K.upconv3_dgrad(dconv, wd) if pre_up else K.conv3_igemm(dconv, wd)
         if need_w:

@@ -93,14 +93,36 @@ class GraphedTrainStep:
         if not self.keep_packs:
             F._pack_cache.clear()   # the captured packs live in the graph's private pool; do not reuse them eagerly
         else:
-            # the graph reads the cached pack tensors by address: pin them for the lifetime of this object
-            self._pinned_packs = [v[3] for v in F._pack_cache.values()]
+            # the graph reads the cached pack tensors by address: pin them for the lifetime of this object, and remember
+            # each weight's version so an in-place load (``load_state_dict``) between replays is noticed
+            self._pinned_packs = [(v[0], key[1], v[3]) for key, v in F._pack_cache.items()]
+            self._pack_versions = [(ref, ref()._version) for ref, _, _ in self._pinned_packs if ref() is not None]
+
+    def refresh_packs(self):
+        """Recompute the pinned bf16 weight packs IN PLACE from the current fp32 weights.  Needed after the weights
+        were overwritten behind FusedAdam's back (``model.load_state_dict`` of a checkpoint, a broadcast): the captured
+        kernels read the packs by address and only the captured Adam update rewrites them.  ``__call__`` does this
+        automatically when a weight's version counter moved."""
+        if not self.keep_packs:
+            return
+        from . import kernels as K
+        with torch.no_grad():
+            for ref, up, packs in self._pinned_packs:
+                w = ref()
+                if w is None:
+                    continue
+                new = K.pack_upconv3_weights(w.detach().contiguous()) if up else K.pack_conv3_weights(w.detach().contiguous())
+                for dst, src in zip(packs, new):
+                    dst.copy_(src)
+        self._pack_versions = [(ref, ref()._version) for ref, _, _ in self._pinned_packs if ref() is not None]
 
     def __call__(self, real_batch: torch.Tensor, noise_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Copies the batch into the captured input buffers (device or pinned-host source) and replays.
         The returned dict holds the captured loss tensors: values are overwritten by the next call."""
         self.real.copy_(real_batch, non_blocking=True)
         self.noise.copy_(noise_batch, non_blocking=True)
+        if self.keep_packs and any(ref() is not None and ref()._version != v for ref, v in self._pack_versions):
+            self.refresh_packs()
         for opt in (self.opt_e, self.opt_d):
             if hasattr(opt, "sync_lr"):
                 opt.sync_lr()          # LR-scheduler changes reach the device scalar the captured step reads

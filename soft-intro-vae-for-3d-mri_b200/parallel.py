@@ -172,6 +172,7 @@ class FlatGradReducer:
         self.used: List[torch.nn.Parameter] = []
 
     def _build(self):
+        self.flat = None
         self.used = [p for p in self.params if p.grad is not None]
         if not self.used:
             return
@@ -185,9 +186,25 @@ class FlatGradReducer:
                 p.grad = v
                 o += p.numel()
 
+    def bound(self) -> bool:
+        """True while every ``.grad`` of the group still aliases its slot of the flat buffer.  ``Module.to()`` round
+        trips (the trainer's per-epoch checkpoint through the CPU, utils/my_trainer.py:476-480) and
+        ``zero_grad(set_to_none=True)`` re-allocate gradient storage and silently break the aliasing."""
+        if self.flat is None:
+            return False
+        base, esz, o = self.flat.data_ptr(), self.flat.element_size(), 0
+        for p in self.used:
+            g = p.grad
+            if g is None or g.device != self.flat.device or g.data_ptr() != base + o * esz:
+                return False
+            o += p.numel()
+        return True
+
     def finish(self):
         """Call between ``loss.backward()`` and ``optimizer.step()``."""
-        if self.flat is None:
+        if not self.bound():
+            # first call, or the views were lost: gather the current gradients into a fresh flat buffer and re-bind
+            # (a CUDA graph captured over the old addresses is invalid anyway once the parameters have moved)
             self._build()
         if self.flat is None or self.world == 1:
             return

@@ -69,6 +69,12 @@ class StepHyper:
     scale: Optional[float] = None       # my_trainer.py:194; None -> 8 / voxels-per-volume of the batch
 
 
+def _dist_rank() -> int:
+    """Rank of this process in the default torch.distributed group (0 when not initialised)."""
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def _set_requires_grad(module: nn.Module, flag: bool):
     for p in module.parameters():
         p.requires_grad = flag
@@ -210,9 +216,11 @@ def train_soft_intro_vae(model, train_loader, val_loader, epochs, lr=0.001, devi
     hot path, and are not reproduced; the csv header, per-epoch checkpoint and loss text dumps are.
     """
     seed = 77
-    os.makedirs(os.path.join(path, "prams"), exist_ok=True)
-    with open(path + "train_result.csv", "w") as f:
-        csv.writer(f).writerow(["epoch", "train_lossE", "train_lossD", "val_lossE", "val_lossD"])
+    rank = _dist_rank()
+    if rank == 0:                                                     # one writer per job (ranks share ``path``)
+        os.makedirs(os.path.join(path, "prams"), exist_ok=True)
+        with open(path + "train_result.csv", "w") as f:
+            csv.writer(f).writerow(["epoch", "train_lossE", "train_lossD", "val_lossE", "val_lossD"])
     random.seed(seed)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -231,6 +239,13 @@ def train_soft_intro_vae(model, train_loader, val_loader, epochs, lr=0.001, devi
     hp = StepHyper(beta_rec, beta_neg, beta_kl, 1e-8, None)
     model.apply(init_weights_he)                                    # after the optional load (Q6)
     red_e, red_d = reducers if reducers is not None else (None, None)
+    if rank != 0:
+        # identical initialisation on every rank (seed 77 above), then rank-distinct latent noise, eps and dropout
+        # streams -- DataParallel replicas see different samples AND different noise (main_DataParallel.py:609)
+        torch.manual_seed(seed + rank)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed(seed + rank)
+        F.manual_seed(seed + rank)
 
     train_lossE_list, train_lossD_list, val_lossE_list, val_lossD_list = [], [], [], []
     train_lossE = train_lossD = val_lossE = val_lossD = 0.0         # never reset per epoch (Q10)
@@ -275,22 +290,24 @@ def train_soft_intro_vae(model, train_loader, val_loader, epochs, lr=0.001, devi
         rec_errs.append(float(np.mean(ep["loss_rec"])) if ep["loss_rec"] else 0.0)
 
         # per-epoch checkpoint through the CPU, then back (:476-480; re-allocates parameter storage, Q11)
-        torch.save(model.to("cpu").state_dict(), path + f"prams/S-IntroVAE_3898_epoch{epoch}.pth")
-        model = model.to(device)
+        if rank == 0:
+            torch.save(model.to("cpu").state_dict(), path + f"prams/S-IntroVAE_3898_epoch{epoch}.pth")
+            model = model.to(device)
         print(f"Epoch[{epoch + 1}/{epochs}] train_lossE:{train_lossE:.3f}  train_lossD:{train_lossD:.3f}  "
               f"val_lossE:{val_lossE:.3f}  val_lossD:{val_lossD:.3f}  total:{(time.time() - start) / 60:.0f}min")
         train_lossE_list.append(train_lossE)                         # appended twice (Q10)
         train_lossD_list.append(train_lossD)
         val_lossE_list.append(val_lossE)
         val_lossD_list.append(val_lossD)
-        with open(path + "/loss.txt", "w") as f:
-            for name, lst in (("train_lossE", train_lossE_list), ("val_lossE", val_lossE_list),
-                              ("train_lossD", train_lossD_list), ("val_lossD", val_lossD_list)):
-                f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
-        with open(path + "/kl_losses.txt", "w") as f:
-            for name, lst in (("kls_real", kls_real), ("kls_fake", kls_fake), ("kls_rec", kls_rec),
-                              ("rec_errs", rec_errs)):
-                f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
+        if rank == 0:
+            with open(path + "/loss.txt", "w") as f:
+                for name, lst in (("train_lossE", train_lossE_list), ("val_lossE", val_lossE_list),
+                                  ("train_lossD", train_lossD_list), ("val_lossD", val_lossD_list)):
+                    f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
+            with open(path + "/kl_losses.txt", "w") as f:
+                for name, lst in (("kls_real", kls_real), ("kls_fake", kls_fake), ("kls_rec", kls_rec),
+                                  ("rec_errs", rec_errs)):
+                    f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
         e_scheduler.step()
         d_scheduler.step()
     print("Finished S-IntroVAE Traininig !!")

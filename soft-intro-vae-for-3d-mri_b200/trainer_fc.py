@@ -25,7 +25,8 @@ import torch.optim as optim
 
 from . import functional as F
 from .optim import FusedAdam
-from .trainer import (StepHyper, calc_kl, calc_reconstruction_loss, init_weights_he, soft_intro_train_step)  # noqa: F401
+from .trainer import (StepHyper, _dist_rank, calc_kl, calc_reconstruction_loss, init_weights_he,  # noqa: F401
+                      soft_intro_train_step)
 
 SCALE = 8.0 / (80 * 96 * 80)          # trainer_fc.py:179
 
@@ -70,9 +71,11 @@ def train_soft_intro_vae(model=None, train_loader=None, val_loader=None, epochs=
     """Same signature and return value as utils/trainer_fc.py:128-454 (``reducers`` is the only addition: an optional
     ``(reducer_e, reducer_d)`` pair for one-process-per-GPU data parallelism, see parallel.py)."""
     seed = 77
-    os.makedirs(os.path.join(path, "prams"), exist_ok=True)
-    with open(path + "train_result.csv", "w") as f:
-        csv.writer(f).writerow(["epoch", "train_lossE", "train_lossD", "val_lossE", "val_lossD"])
+    rank = _dist_rank()
+    if rank == 0:                                                     # one writer per job (ranks share ``path``)
+        os.makedirs(os.path.join(path, "prams"), exist_ok=True)
+        with open(path + "train_result.csv", "w") as f:
+            csv.writer(f).writerow(["epoch", "train_lossE", "train_lossD", "val_lossE", "val_lossD"])
     random.seed(seed)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -90,6 +93,13 @@ def train_soft_intro_vae(model=None, train_loader=None, val_loader=None, epochs=
     hp = StepHyper(beta_rec, beta_neg, beta_kl, 1e-8, SCALE)
     model.apply(init_weights_he)                                      # after the optional load (:189)
     red_e, red_d = reducers if reducers is not None else (None, None)
+    if rank != 0:
+        # identical initialisation on every rank (seed 77 above), then rank-distinct latent noise, eps and dropout
+        # streams -- DataParallel replicas see different samples AND different noise (main_DataParallel.py:609)
+        torch.manual_seed(seed + rank)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed(seed + rank)
+        F.manual_seed(seed + rank)
 
     train_lossE_list, train_lossD_list, val_lossE_list, val_lossD_list = [], [], [], []
     train_lossE = train_lossD = val_lossE = val_lossD = 0.0           # never reset per epoch (:192)
@@ -128,22 +138,24 @@ def train_soft_intro_vae(model=None, train_loader=None, val_loader=None, epochs=
         for lst, key in ((kls_real, "kl_real"), (kls_fake, "fake_kl"), (kls_rec, "rec_kl"), (rec_errs, "loss_rec")):
             lst.append(float(np.mean(ep[key])) if ep[key] else 0.0)
 
-        torch.save(model.to("cpu").state_dict(), path + f"prams/S-IntroVAE_4184_epoch{epoch}.pth")   # :418-421
-        model.to(device)
+        if rank == 0:
+            torch.save(model.to("cpu").state_dict(), path + f"prams/S-IntroVAE_4184_epoch{epoch}.pth")   # :418-421
+            model.to(device)
         print(f"Epoch [{epoch + 1}/{epochs}]  train_lossE:{train_lossE:.3f}  train_lossD:{train_lossD:.3f}  "
               f"val_lossE:{val_lossE:.3f}  val_lossD:{val_lossD:.3f}  total:{(time.time() - start) / 60:.1f}min")
         train_lossE_list.append(train_lossE)                           # appended twice (:431-434)
         train_lossD_list.append(train_lossD)
         val_lossE_list.append(val_lossE)
         val_lossD_list.append(val_lossD)
-        with open(path + "/loss.txt", "w") as f:
-            for name, lst in (("train_lossE", train_lossE_list), ("val_lossE", val_lossE_list),
-                              ("train_lossD", train_lossD_list), ("val_lossD", val_lossD_list)):
-                f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
-        with open(path + "/kl_losses.txt", "w") as f:
-            for name, lst in (("kls_real", kls_real), ("kls_fake", kls_fake), ("kls_rec", kls_rec),
-                              ("rec_errs", rec_errs)):
-                f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
+        if rank == 0:
+            with open(path + "/loss.txt", "w") as f:
+                for name, lst in (("train_lossE", train_lossE_list), ("val_lossE", val_lossE_list),
+                                  ("train_lossD", train_lossD_list), ("val_lossD", val_lossD_list)):
+                    f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
+            with open(path + "/kl_losses.txt", "w") as f:
+                for name, lst in (("kls_real", kls_real), ("kls_fake", kls_fake), ("kls_rec", kls_rec),
+                                  ("rec_errs", rec_errs)):
+                    f.write(name + ":" + ",".join(f"{x:.6f}" for x in lst) + "\n")
     e_scheduler.step()                                                 # once, after the loop (:447-448)
     d_scheduler.step()
     print("Finished S-IntroVAE Traininig !!")

@@ -51,9 +51,11 @@ def synthetic_volumes(n, vol, gen):
 
 
 def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setting=((64, 1, 2), (128, 1, 2), (256, 2, 2)),
-        lr=2e-4, seed=77, device="cuda", verbose=False, control=False, fc=None):
+        lr=2e-4, seed=77, device="cuda", verbose=False, control=False, fc=None, perturb=None):
     """``fc`` = dict(chans=(c1,c2,c3,c4), z_ch=..., grid=(gd,gh,gw)) selects the FC-latent variant (models/mymodel.py +
-    utils/trainer_fc.py: vector noise, no dropout, scale fixed at 8/(80*96*80)); ``vol`` must then be 16 * grid."""
+    utils/trainer_fc.py: vector noise, no dropout, scale fixed at 8/(80*96*80)); ``vol`` must then be 16 * grid.
+    ``perturb`` = (seed, rel): every arm starts from the SAME initial weights multiplied by (1 + rel * N(0,1)) --
+    replicas for tools/curve_ensemble.py, which measures how far trajectories of ONE arithmetic spread."""
     import sivae_b200
     from sivae_b200 import functional as F, trainer as T
     from oracle import sivae_oracle as O
@@ -75,6 +77,11 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
     net = (sivae_b200.mymodel.SoftIntroVAE(*fc["chans"], fc["z_ch"], latent_grid=tuple(fc["grid"])) if fc is not None
            else sivae_b200.SoftIntroVAE(in_ch, bs))
     net.apply(T.init_weights_he)
+    if perturb is not None:
+        pg = torch.Generator().manual_seed(int(perturb[0]))
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.mul_(1.0 + float(perturb[1]) * torch.randn(p_.shape, generator=pg))
     net.to(dev).train()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}          # oracle's private copy
     enc_names, dec_names, _ = O.split_state(sd)
@@ -204,7 +211,12 @@ def main():
     ap.add_argument("--control", action="store_true", help="also train the oracle under bf16 autocast")
     ap.add_argument("--fc", type=int, nargs=5, default=None, metavar=("C1", "C2", "C3", "C4", "Z"),
                     help="FC-latent variant mymodel.SoftIntroVAE(C1,C2,C3,C4,Z); the latent grid is vol/16")
+    ap.add_argument("--env", nargs="*", default=[], metavar="K=V",
+                    help="libsivae kernel-family toggles for this run (e.g. SIVAE_CONV_KD=0), for bisecting")
     a = ap.parse_args()
+    for kv in a.env:
+        k_, v_ = kv.split("=", 1)
+        os.environ[k_] = v_
     fc = None
     if a.fc is not None:
         fc = dict(chans=tuple(a.fc[:4]), z_ch=a.fc[4], grid=tuple(v // 16 for v in a.vol))

@@ -288,3 +288,206 @@ def test_fused_adam_graph_matches_torch_adam_graph():
     for va, vb in zip(a[1:], b[1:]):
         for i, (x, y) in enumerate(zip(va, vb)):
             assert x == pytest.approx(y, rel=1e-1 if i == 3 else 2e-2), (a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config 1: vaemodel.ResNetVAE + lossf.normal_loss (vae_main.py:180,205)
+# ---------------------------------------------------------------------------------------------------------------
+def test_plain_vae_step_vs_golden_gpu(golden_dir):
+    """vaemodel.ResNetVAE(4, 4 stages) + lossf.normal_loss through the CUDA path vs the fixture generated from the
+    unmodified reference (tests/golden/vae_small.pt: models/vaemodel.py:215-230 forward, models/lossf.py:20-24).  The
+    widths 4/8 exercise the zero-pad-to-64 path end to end.  The net is tiny and ill-conditioned (BatchNorm over 4
+    values per channel at the 1x2x1 latent), so gradients are compared by direction."""
+    g = _load(golden_dir, "vae_small.pt")
+    st = g["step"]
+    net = sivae_b200.vaemodel.ResNetVAE(g["in_ch"], g["block_setting"])
+    assert list(net.state_dict().keys()) == list(g["sd0"].keys())
+    net.load_state_dict(g["sd0"])
+    net.to(DEV).train()
+    x = g["x"].to(DEV)
+    F.noise_state.eps_feed = iter([st["eps"].to(DEV)])
+    x_re, mu, lv = net(x)
+    loss, mse, kld = sivae_b200.lossf.normal_loss(x_re, mu, lv, x, 1.0, 1.0)
+    loss.backward()
+    F.noise_state.eps_feed = None
+    assert x_re.shape == st["x_re"].shape and mu.shape == st["mu"].shape
+    assert float(loss) == pytest.approx(st["terms"]["loss"], rel=2e-2)
+    assert float(mse) == pytest.approx(st["terms"]["mse"], rel=2e-2)
+    assert float(kld) == pytest.approx(st["terms"]["kld"], rel=0.25, abs=0.3)       # 4 latent values per sample
+    assert _cos(x_re, st["x_re"].to(DEV)) > 0.99
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(grads) == set(st["grads"])
+    cos = {k: _cos(grads[k], ref.to(DEV)) for k, ref in st["grads"].items()
+           if not k.endswith("blocks.0.0.bias") and k != "decoder.blocks.0.0.weight" and ref.numel() >= 16}
+    worst = min((v, k) for k, v in cos.items())
+    print("plain VAE golden: worst grad cosine", worst, " mean", sum(cos.values()) / len(cos))
+    assert sum(cos.values()) / len(cos) > 0.9 and worst[0] > 0.5, worst
+    sd = net.state_dict()
+    for k, v in st["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert float((sd[k].cpu() - v).abs().max()) <= 0.05 * float(v.abs().max()) + 2e-3, k
+
+
+def test_config1_plain_vae_step_vs_oracle():
+    """BASELINE configs[0] as stated: vaemodel.ResNetVAE(12,[[12,1,2],[24,1,2],[32,2,2],[48,2,2]]) (vae_main.py:180)
+    on 2 x 1x80x96x80 volumes, one lossf.normal_loss(mse_w=1, kl_w=1) step (vae_main.py:205, my_trainer.py:588-594),
+    CUDA path vs the fp32 oracle on the same device; the oracle under torch.autocast(bfloat16) is the control.
+    Loss terms: north_star's 1e-3 on loss / mse (first-pass terms); the KL of the 150-element latent and the
+    gradients are bounded relative to the control."""
+    bs = [[12, 1, 2], [24, 1, 2], [32, 2, 2], [48, 2, 2]]
+    torch.manual_seed(77)
+    net = sivae_b200.vaemodel.ResNetVAE(12, bs)
+    net.apply(T.init_weights_he_relu)
+    net.to(DEV).train()
+    cfg = O.NetCfg.plain_vae(12, bs)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    gen = torch.Generator(device=DEV).manual_seed(4242)
+    x = torch.rand(2, 1, 80, 96, 80, device=DEV, generator=gen)
+    eps = torch.randn(2, 1, 5, 6, 5, device=DEV, generator=gen)
+    ref_terms, ref_grads, ref_x = O.plain_vae_step_grads({k: v.clone() for k, v in sd.items()}, cfg, x, eps, 1.0, 1.0)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        amp_terms, amp_grads, _ = O.plain_vae_step_grads({k: v.clone() for k, v in sd.items()}, cfg, x, eps, 1.0, 1.0)
+    F.noise_state.eps_feed = iter([eps])
+    x_re, mu, lv = net(x)
+    loss, mse, kld = sivae_b200.lossf.normal_loss(x_re, mu, lv, x, 1.0, 1.0)
+    loss.backward()
+    F.noise_state.eps_feed = None
+    got = dict(loss=float(loss), mse=float(mse), kld=float(kld))
+    for k in got:
+        rel = abs(got[k] - ref_terms[k]) / abs(ref_terms[k])
+        rel_amp = abs(amp_terms[k] - ref_terms[k]) / abs(ref_terms[k])
+        print(f"  {k:5s} cuda {got[k]:12.6g} oracle {ref_terms[k]:12.6g} rel {rel:.2e} (amp rel {rel_amp:.2e})")
+        tol = 1e-3 if k != "kld" else max(1e-3, 2.0 * rel_amp) + 2e-3
+        assert rel <= tol, (k, got[k], ref_terms[k], rel_amp)
+    assert _cos(x_re, ref_x) > 0.9995
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(grads) == set(ref_grads)
+    rows = []
+    for k, ref in ref_grads.items():
+        if k.endswith("blocks.0.0.bias") or k == "decoder.blocks.0.0.weight" or ref.numel() < 16:
+            continue
+        rows.append((_cos(grads[k], ref), _cos(amp_grads[k].float(), ref), k))
+    worst = min(rows)
+    print("config 1: worst grad cosine (ours, control, name):", worst,
+          " mean ours", sum(r[0] for r in rows) / len(rows), " mean control", sum(r[1] for r in rows) / len(rows))
+    for c, c_amp, k in rows:
+        assert c > min(0.98, c_amp - 0.03), (k, c, c_amp)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the configuration bench.py measures: batch 8 through GraphedTrainStep + FusedAdam (z-1200main.py:190 bs=8)
+# ---------------------------------------------------------------------------------------------------------------
+def test_bench_config_graph_step_vs_oracle():
+    """Two E+D iterations of the headline net at the BENCH configuration -- batch 8 x 80x96x80 (z-1200main.py:190),
+    whole-step CUDA graph (graph.GraphedTrainStep) + optim.FusedAdam -- vs the fp32 oracle + torch.optim.Adam on the
+    same device with identical weights, batch, latent noise, eps and dropout keep-masks (the graph reads the fed masks /
+    eps from fixed buffers that are rewritten before every replay).  First-pass loss terms must meet north_star's 1e-3;
+    chained terms (second-pass reconstructions, KLs of re-encoded images) are bounded by the oracle under
+    torch.autocast(bfloat16) (the control); BatchNorm statistics are over 8 volumes on both sides."""
+    import itertools
+    B, D, H, W = 8, 80, 96, 80
+    bs = [[64, 1, 2], [128, 1, 2], [256, 2, 2]]
+    torch.manual_seed(77)
+    net = sivae_b200.SoftIntroVAE(64, bs)
+    net.apply(T.init_weights_he)
+    net.to(DEV).train()
+    cfg = O.NetCfg.soft_intro(64, bs)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    lat = (B, 1, D // 8, H // 8, W // 8)
+    gen = torch.Generator(device=DEV).manual_seed(2024)
+
+    def draw():
+        real = torch.rand(B, 1, D, H, W, device=DEV, generator=gen)
+        noise = torch.randn(lat, device=DEV, generator=gen)
+        eps = [torch.randn(lat, device=DEV, generator=gen) for _ in range(5)]
+        masks = []
+        for ch in "dedededddeedd":
+            if ch == "e":
+                masks.append(torch.rand(B, 64, D, H, W, device=DEV, generator=gen) >= 0.35)
+            else:
+                masks.append(torch.rand(B, 256, D // 8, H // 8, W // 8, device=DEV, generator=gen) >= 0.25)
+                masks.append(torch.rand(B, 1, D, H, W, device=DEV, generator=gen) >= 0.35)
+        return real, noise, eps, masks
+
+    steps = [draw() for _ in range(2)]
+    # fixed feed buffers (the captured kernels read them by address)
+    real_b, noise_b = steps[0][0].clone(), steps[0][1].clone()
+    eps_b = [e.clone() for e in steps[0][2]]
+    mask_b = _gpu_masks(steps[0][3])
+    opt_e = sivae_b200.FusedAdam(net.encoder.parameters(), lr=2e-4)
+    opt_d = sivae_b200.FusedAdam(net.decoder.parameters(), lr=2e-4)
+    F.dropout_state.mask_feed = itertools.cycle(mask_b)
+    F.noise_state.eps_feed = itertools.cycle(eps_b)
+    step = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real_b, noise_b, warmup=1)
+    F.dropout_state.mask_feed = None
+    F.noise_state.eps_feed = None
+    # the warm-up trained: back to the initial weights / buffers / Adam state (in place -- the graph holds addresses)
+    net.load_state_dict(sd0)
+    for opt in (opt_e, opt_d):
+        for st in opt.state.values():
+            st["exp_avg"].zero_()
+            st["exp_avg_sq"].zero_()
+        for gs in opt._gs.values():
+            gs["step"].zero_()
+    # oracle + control
+    enc_names, dec_names, _ = O.split_state(sd0)
+
+    def make_arm():
+        sd = {k: v.detach().clone() for k, v in sd0.items()}
+        for k in enc_names + dec_names:
+            sd[k] = torch.nn.Parameter(sd[k])
+        opt = {"E": torch.optim.Adam([sd[k] for k in enc_names], lr=2e-4),
+               "D": torch.optim.Adam([sd[k] for k in dec_names], lr=2e-4)}
+
+        def upd(names, grads, phase):
+            for k in names:
+                g_ = grads.get(k)
+                sd[k].grad = None if g_ is None else g_.float()
+            opt[phase].step()
+        return sd, upd
+
+    sd_o, upd_o = make_arm()
+    sd_c, upd_c = make_arm()
+    first = ("lossE", "lossD", "loss_rec", "loss_rec_d")
+    chained = ("kl_real", "rec_kl", "fake_kl", "loss_rec_rec_d", "loss_fake_rec_d")
+    for i, (real, noise, eps, masks) in enumerate(steps):
+        real_b.copy_(real)
+        noise_b.copy_(noise)
+        for dst, src in zip(eps_b, eps):
+            dst.copy_(src)
+        for dst, src in zip(mask_b, _gpu_masks(masks)):
+            dst.copy_(src)
+        out = step(real_b, noise_b)
+        got = {k: float(v) for k, v in out.items()}
+        om = [m.float() for m in masks]
+        ref, _, _ = O.soft_intro_step_grads(sd_o, cfg, real, noise, eps, om, O.StepHyper(), apply_update=upd_o)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            amp, _, _ = O.soft_intro_step_grads(sd_c, cfg, real, noise, eps, om, O.StepHyper(), apply_update=upd_c)
+        del om
+        for k in first + chained:
+            rel = abs(got[k] - ref[k]) / abs(ref[k])
+            rel_amp = abs(amp[k] - ref[k]) / abs(ref[k])
+            print(f"  step {i} {k:16s} graph {got[k]:14.6g} oracle {ref[k]:14.6g} rel {rel:.2e} (amp rel {rel_amp:.2e})")
+            if i == 0 and k in first:
+                assert rel <= 1e-3, (i, k, got[k], ref[k])                  # north_star
+            elif i == 0:
+                assert rel <= max(2.0 * rel_amp, 1e-3) + 2e-3, (i, k, got[k], ref[k], rel_amp)
+            else:
+                # after one Adam update (+-lr on every weight, kl_real x 1e2..1e4) roundings are amplified on both arms
+                assert rel <= max(3.0 * rel_amp, 2e-2) + (0.5 if "kl" in k else 0.0), (i, k, got[k], ref[k], rel_amp)
+    # after two updates: the replicas of the weights moved the same way
+    agree, agree_c = [], []
+    for k, p in net.named_parameters():
+        if p.dim() == 5 and p.shape[-1] == 3 and k in sd_o and (sd_o[k] - sd0[k]).abs().max() > 0:
+            d_ours, d_ref, d_amp = (p.detach() - sd0[k]), (sd_o[k].detach() - sd0[k]), (sd_c[k].detach() - sd0[k])
+            agree.append(_cos(d_ours, d_ref))
+            agree_c.append(_cos(d_amp, d_ref))
+    print(f"weight-update cosine vs fp32 after 2 steps: ours mean {sum(agree) / len(agree):.4f} min {min(agree):.4f}; "
+          f"control mean {sum(agree_c) / len(agree_c):.4f} min {min(agree_c):.4f}")
+    assert sum(agree) / len(agree) > sum(agree_c) / len(agree_c) - 0.05
+    sdn = net.state_dict()
+    assert int(sdn["encoder.blocks.0.1.num_batches_tracked"]) == 10 and int(sdn["decoder.blocks.0.1.num_batches_tracked"]) == 16
+    for k in ("encoder.blocks.1.0.block.1.running_var", "decoder.blocks.4.0.block.5.running_mean"):
+        assert float((sdn[k] - sd_o[k]).abs().max()) <= 0.03 * float(sd_o[k].abs().max()) + 1e-3, k

@@ -76,6 +76,55 @@ def test_stale_upconv_packs_are_dropped_cpu_emulated():
         assert not torch.equal(F._packed(w, True)[0], up[0])
 
 
+def _resume(device):
+    """state_dict -> fresh optimiser -> load_state_dict continues the trajectory of an uninterrupted torch.optim.Adam
+    (the shared device step counter and lr are persisted and re-bound), and a parameter whose first gradient arrives
+    after the group's first step is refused (one bias-correction counter per group)."""
+    torch.manual_seed(0)
+    ps = [torch.randn(n, device=device, requires_grad=True) for n in (5, 33)]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    opt, ref = sivae_b200.FusedAdam(ps, lr=1e-3), torch.optim.Adam(qs, lr=1e-3)
+
+    def one(o, r, step):
+        g = torch.Generator(device="cpu").manual_seed(step)
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, generator=g).to(device)
+            p.grad, q.grad = gr.clone(), gr.clone()
+        o.step()
+        r.step()
+
+    for step in range(3):
+        one(opt, ref, step)
+    sd = opt.state_dict()
+    opt2 = sivae_b200.FusedAdam(ps, lr=5e-2)                      # lr comes from the checkpoint, not the ctor
+    opt2.load_state_dict(sd)
+    assert opt2.state[ps[0]]["step"] is opt2.state[ps[1]]["step"] and int(opt2.state[ps[0]]["step"]) == 3
+    for step in range(3, 6):
+        one(opt2, ref, step)
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=2e-6, atol=1e-8)
+    assert int(opt2.state[ps[0]]["step"]) == 6
+    late = torch.randn(4, device=device, requires_grad=True)
+    opt3 = sivae_b200.FusedAdam([ps[0], late], lr=1e-3)
+    ps[0].grad = torch.ones_like(ps[0])
+    opt3.step()
+    late.grad = torch.ones_like(late)
+    with pytest.raises(RuntimeError, match="first gradient after"):
+        opt3.step()
+
+
+def test_fused_adam_resume_cpu_emulated():
+    with emulated_kernels():
+        _resume("cpu")
+
+
+@pytest.mark.gpu
+def test_fused_adam_resume_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    _resume("cuda")
+
+
 @pytest.mark.gpu
 def test_fused_adam_matches_torch_gpu():
     if not torch.cuda.is_available():

@@ -120,7 +120,15 @@ def _flat_worker(rank, world, port, q):
     params = list(enc.parameters()) + list(unused.parameters())
     opt = torch.optim.Adam(params, lr=1e-2)
     red = P.FlatGradReducer(params)
-    for step in range(3):
+    for step in range(4):
+        if step == 2:
+            # the trainer's per-epoch checkpoint moves the module through another device/dtype and back
+            # (utils/my_trainer.py:476-480): gradient storage is re-allocated and the flat views are lost;
+            # finish() must notice and re-bind, or the replicas silently stop exchanging gradients
+            flat_before = red.flat
+            enc.to(torch.float64)
+            enc.to(torch.float32)
+            assert not red.bound()
         torch.manual_seed(100 + 10 * step + rank)
         x = torch.randn(7, 6)
         T._zero_grad(opt, red)
@@ -135,6 +143,9 @@ def _flat_worker(rank, world, port, q):
         # the gradients stay views of the flat exchange buffer across zero_grad / backward
         assert all(p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
                    for p in enc.parameters())
+        assert red.bound()
+        if step == 2:
+            assert red.flat is not flat_before
         opt.step()
     q.put((rank, torch.cat([p.detach().flatten() for p in enc.parameters()]).tolist()))
     dist.destroy_process_group()
