@@ -155,12 +155,15 @@ int sivae_bn_train_act_fwd(const void* y_bf16, const void* res_bf16, void* out_b
                            void* workspace, size_t workspace_bytes, void* stream);
 /* out = resample( dropout( act( y*scale[c]+shift[c] (+ res) ) ) )
  *   act(t) = t>0 ? t : slope*t        (slope 0.2 = LeakyReLU(0.2), slope 0 = ReLU)
- *   dropout: keep-mask (uint8 NDHWC, 0/1) if mask != NULL, else Philox(seed) if p > 0, else none;
- *            kept values are scaled by 1/(1-p).
+ *   dropout: mask != NULL, seed == 0: caller-provided keep-mask (uint8 NDHWC, 0/1), read;
+ *            mask != NULL, seed != 0, p > 0 (resample = none only): KEEP-BIT STORE -- the kernel draws Philox(seed) and
+ *              WRITES its decisions to mask as uint8 [N*D*H*W*C/8], bit k of byte i = element 8i+k kept;
+ *              sivae_bn_act_bwd with the same (mask, seed, p) reads them instead of regenerating Philox;
+ *            mask == NULL: Philox(seed) if p > 0, else none.   Kept values are scaled by 1/(1-p).
  * y, res: [N][D][H][W][C] bf16; out: [N][D'][H'][W'][C] with D' = D/2, D or 2D per `resample`. */
 int sivae_bn_act_fwd(const void* y_bf16, const float* scale, const float* shift, const void* res_bf16,
                      void* out_bf16, int N, int D, int H, int W, int C, float slope, int resample,
-                     const uint8_t* mask, float p, unsigned long long seed, void* stream);
+                     uint8_t* mask, float p, unsigned long long seed, void* stream);
 
 /* Backward of sivae_bn_train_coeffs + sivae_bn_act_fwd given g = dLoss/d(out) (bf16, out's shape):
  *   dconv = gradient w.r.t. y (bf16), dres = gradient w.r.t. res (bf16, may be NULL),

@@ -153,9 +153,24 @@ def bn_train_coeffs(y, gamma, beta, running_mean, running_var, num_batches_track
     return mean, invstd, scale, shift
 
 
-def _keep_scale(y, mask, p):
+def _unpack_keep_bits(bits, shape):
+    """uint8 [numel/8] (bit k of byte i = element 8i+k kept) -> bool tensor of ``shape``."""
+    k = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    return ((bits.reshape(-1, 1) >> k) & 1).bool().reshape(shape)
+
+
+def _keep_scale(y, mask, p, keep_bits=None, draw=False):
+    """Keep-scale of a dropout call.  ``mask``: explicit byte keep-mask.  ``keep_bits``: the keep-bit store -- the forward
+    (``draw=True``) draws the decisions and writes them there (here from torch's generator: the Philox stream itself is
+    only checked statistically), the backward reads them back."""
     if mask is not None:
         return mask.float() * (1.0 / (1.0 - p))
+    if keep_bits is not None and p > 0.0:
+        if draw:
+            keep = torch.rand(y.shape, device=y.device) >= p
+            k = torch.arange(8, device=y.device)
+            keep_bits.copy_((keep.reshape(-1, 8).long() << k).sum(1).to(torch.uint8))
+        return _unpack_keep_bits(keep_bits, y.shape).float() * (1.0 / (1.0 - p))
     if p > 0.0:
         raise NotImplementedError("Philox dropout is only checked statistically; pass an explicit mask")
     return None
@@ -177,12 +192,12 @@ def _resample_T(g, resample):  # transpose of _resample; g fp32 in output space
     return g
 
 
-def bn_act_fwd(y, scale, shift, res, slope, resample, mask=None, p=0.0, seed=0):
+def bn_act_fwd(y, scale, shift, res, slope, resample, mask=None, p=0.0, seed=0, keep_bits=None):
     t = y.float() * scale + shift
     if res is not None:
         t = t + res.float()
     a = torch.where(t > 0, t, slope * t)
-    ks = _keep_scale(y, mask, p)
+    ks = _keep_scale(y, mask, p, keep_bits, draw=True)
     if ks is not None:
         a = a * ks
     return _resample(a, resample).contiguous().to(y.dtype)
@@ -197,14 +212,14 @@ def bn_train_act_fwd(y, res, gamma, beta, running_mean, running_var, num_batches
 
 
 def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope, resample, mask=None, p=0.0, seed=0,
-               need_dres=False, need_affine=True):
+               need_dres=False, need_affine=True, keep_bits=None):
     c = y.shape[-1]
     xh = (y.float() - mean) * invstd
     t = xh * gamma + beta
     if res is not None:
         t = t + res.float()
     gp = _resample_T(g.float(), resample)
-    ks = _keep_scale(y, mask, p)
+    ks = _keep_scale(y, mask, p, keep_bits)
     if ks is not None:
         gp = gp * ks
     dt = gp * torch.where(t > 0, torch.ones_like(t), torch.full_like(t, slope))

@@ -235,7 +235,7 @@ int sivae_bn_train_coeffs(const void* y, long long nvox, int C, const float* gam
                          shift, ws, ws_bytes, ST(stream));
 }
 int sivae_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* res, void* out, int N, int D,
-                     int H, int W, int C, float slope, int resample, const uint8_t* mask, float p,
+                     int H, int W, int C, float slope, int resample, uint8_t* mask, float p,
                      unsigned long long seed, void* stream) {
   return bn_act_fwd(y, scale, shift, res, out, N, D, H, W, C, slope, resample, mask, p, seed, ST(stream));
 }

@@ -60,6 +60,26 @@ __device__ __forceinline__ void drop8(const uint8_t* mask, float p, unsigned lon
   }
 }
 
+// Keep-bit store (dropout of the encoder stem, models/models.py:95): the forward pass draws the Philox decisions of the 8
+// elements [8i, 8i+8) ONCE and stores them as byte i (bit k = element 8i+k kept); both backward passes read that byte
+// instead of re-running Philox4x32-10 (which, not HBM, bounded them: 2.3 vs 3.9 TB/s).  1 bit per element = 1/16 of the
+// bf16 tensor.  Same decisions as drop8 / philox_keep for the same (seed, element).
+__device__ __forceinline__ uint32_t philox_keep_byte(float p, unsigned long long seed, unsigned long long item) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)item, (uint32_t)(item >> 32), 0u, 0u), key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const uint32_t thr = drop_threshold(p);
+  uint32_t byte = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) byte |= ((((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) >= thr) ? 1u : 0u) << k;
+  return byte;
+}
+__device__ __forceinline__ void keep_scale_from_byte(uint32_t byte, float p, float (&ks)[8]) {
+  const float inv = 1.f / (1.f - p);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ks[k] = ((byte >> k) & 1u) ? inv : 0.f;
+}
+
 // Block-level reduction of per-thread (s1[8], s2[8]) for threads sharing a channel chunk; result to
 // partial[(blockIdx.x*2 + {0,1})*C + c].
 __device__ __forceinline__ void block_reduce_channels(const float (&s1)[8], const float (&s2)[8], int C, int cpc,
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ out, int N, int D, int H, int W,
                                                          int C, float slope, const uint8_t* __restrict__ mask, float p,
-                                                         const SeedRef sref) {
+                                                         const SeedRef sref, uint8_t* __restrict__ keep_bits) {
   const unsigned long long seed = resolve_seed(sref);
   const int cpc = C >> 3;
   const long long nvox_in = (long long)N * D * H * W;
@@ -244,7 +264,13 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
           }
-          drop8(mask, p, seed, e0, ks);
+          if (keep_bits != nullptr) {
+            const uint32_t byte = philox_keep_byte(p, seed, i);
+            keep_bits[i] = (uint8_t)byte;
+            keep_scale_from_byte(byte, p, ks);
+          } else {
+            drop8(mask, p, seed, e0, ks);
+          }
 #pragma unroll
           for (int k = 0; k < 8; ++k) a[k] = (f[k] > 0.f ? f[k] : slope * f[k]) * ks[k];
           st8(out + e0, a);
@@ -508,13 +534,15 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat1
 // Folded per-channel constants keep the register count low enough for 4 voxels (128 B) in flight per thread at
 // >= 2 CTAs/SM, which is what the HBM latency-bandwidth product needs (~64 KB in flight per SM).
 //   t = y*S + T (S = gamma*invstd, T = beta - mean*S);  xhat = y*invstd + M2 (M2 = -mean*invstd);  dt = g * act'(t)
-template <bool DROP>
+// DROP: 0 = no dropout, 1 = Philox regenerated in the kernel, 2 = keep-bit store written by the forward pass
+template <int DROP>
 __global__ void __launch_bounds__(kBnThreads, 2)
 bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                            const float* __restrict__ mean, const float* __restrict__ invstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, long long nvox, int C,
-                           float slope, float p, const SeedRef sref, float* __restrict__ partial) {
-  const unsigned long long seed = DROP ? resolve_seed(sref) : 0ull;
+                           float slope, float p, const SeedRef sref, const uint8_t* __restrict__ keep_bits,
+                           float* __restrict__ partial) {
+  const unsigned long long seed = DROP == 1 ? resolve_seed(sref) : 0ull;
   const int cpc = C >> 3;
   const int chunk = threadIdx.x % cpc;
   const int lanes_v = kBnThreads / cpc;
@@ -533,6 +561,7 @@ bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloa
   const unsigned stride = gridDim.x * lanes_v, nv = (unsigned)nvox;
   for (unsigned v0 = blockIdx.x * lanes_v + threadIdx.x / cpc; v0 < nv; v0 += stride * 4) {
     uint4 ry[4], rg[4];
+    uint32_t kb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const unsigned v = v0 + u * stride;
@@ -540,6 +569,7 @@ bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloa
         const size_t e0 = (size_t)v * C + chunk * 8;
         ry[u] = *reinterpret_cast<const uint4*>(y + e0);
         rg[u] = *reinterpret_cast<const uint4*>(g + e0);
+        if (DROP == 2) kb[u] = keep_bits[(size_t)v * cpc + chunk];
       }
     }
 #pragma unroll
@@ -548,9 +578,10 @@ bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloa
         float f[8], gp[8];
         unpack8(ry[u], f);
         unpack8(rg[u], gp);
-        if (DROP) {
+        if (DROP != 0) {
           float ks[8];
-          drop8(nullptr, p, seed, (long long)((size_t)(v0 + u * stride) * C + chunk * 8), ks);
+          if (DROP == 2) keep_scale_from_byte(kb[u], p, ks);
+          else drop8(nullptr, p, seed, (long long)((size_t)(v0 + u * stride) * C + chunk * 8), ks);
 #pragma unroll
           for (int k = 0; k < 8; ++k) gp[k] *= ks[k];
         }
@@ -568,14 +599,14 @@ bn_bwd_reduce_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloa
 }
 
 // dconv = A*dt + y*U + V with A = gamma*invstd, U = -A*invstd*c2, V = A*(mean*invstd*c2 - c1)
-template <bool DROP>
+template <int DROP>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ coef, __nv_bfloat16* __restrict__ dconv, long long items, int C,
-                          float slope, float p, const SeedRef sref) {
-  const unsigned long long seed = DROP ? resolve_seed(sref) : 0ull;
+                          float slope, float p, const SeedRef sref, const uint8_t* __restrict__ keep_bits) {
+  const unsigned long long seed = DROP == 1 ? resolve_seed(sref) : 0ull;
   const int cpc = C >> 3;
   const int chunk = (int)(threadIdx.x % cpc);
   float S[8], T[8], A[8], U[8], V[8];
@@ -595,12 +626,14 @@ bn_bwd_apply_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat
   const unsigned stride = gridDim.x * blockDim.x, nitems = (unsigned)items;
   for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nitems; i0 += stride * 4) {
     uint4 ry[4], rg[4];
+    uint32_t kb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const unsigned i = i0 + u * stride;
       if (i < nitems) {
         ry[u] = *reinterpret_cast<const uint4*>(y + (size_t)i * 8);
         rg[u] = *reinterpret_cast<const uint4*>(g + (size_t)i * 8);
+        if (DROP == 2) kb[u] = keep_bits[i];
       }
     }
 #pragma unroll
@@ -610,9 +643,10 @@ bn_bwd_apply_plain_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat
         float f[8], gp[8], o[8];
         unpack8(ry[u], f);
         unpack8(rg[u], gp);
-        if (DROP) {
+        if (DROP != 0) {
           float ks[8];
-          drop8(nullptr, p, seed, (long long)((size_t)i * 8), ks);
+          if (DROP == 2) keep_scale_from_byte(kb[u], p, ks);
+          else drop8(nullptr, p, seed, (long long)((size_t)i * 8), ks);
 #pragma unroll
           for (int k = 0; k < 8; ++k) gp[k] *= ks[k];
         }
@@ -1111,12 +1145,20 @@ int bn_act_fwd(const void* y, const float* scale, const float* shift, const void
   const int blocks = grid_for(items, 256);
   const __nv_bfloat16 *yy = (const __nv_bfloat16*)y, *rr = (const __nv_bfloat16*)res;
   __nv_bfloat16* oo = (__nv_bfloat16*)out;
+  // `mask` with seed == 0: caller-provided byte keep-mask (read).  `mask` with seed != 0 and p > 0: keep-bit STORE --
+  // the kernel draws the Philox decisions and writes one bit per element for the backward passes (see philox_keep_byte)
+  uint8_t* keep_bits = nullptr;
+  if (mask != nullptr && seed != 0ull && p > 0.f) {
+    SIVAE_CHECK(resample == SIVAE_RESAMPLE_NONE, "bn_act_fwd: the keep-bit store needs resample = none");
+    keep_bits = const_cast<uint8_t*>(mask);
+    mask = nullptr;
+  }
   if (resample == 0)
-    bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
+    bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed), keep_bits);
   else if (resample == 1)
-    bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
+    bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed), nullptr);
   else
-    bn_act_fwd_kernel<2><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed));
+    bn_act_fwd_kernel<2><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed), nullptr);
   SIVAE_LAUNCH_OK("bn_act_fwd_kernel");
   return 0;
 }
@@ -1139,18 +1181,25 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
     return launch_small_cluster(bn_small_bwd_kernel, "bn_small_bwd_kernel", st, (const __nv_bfloat16*)g,
                                 (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, mean, invstd, gamma, beta,
                                 (__nv_bfloat16*)dconv, (__nv_bfloat16*)dres, dgamma, dbeta, nvox, C, slope);
-  const bool plain = resample == SIVAE_RESAMPLE_NONE && res == nullptr && mask == nullptr && dres == nullptr;
+  // `mask` with seed != 0 and p > 0 is the keep-bit store written by bn_act_fwd (1 bit per element)
+  const uint8_t* keep_bits = (mask != nullptr && seed != 0ull && p > 0.f) ? mask : nullptr;
+  SIVAE_CHECK(keep_bits == nullptr || (resample == SIVAE_RESAMPLE_NONE && res == nullptr && dres == nullptr),
+              "bn_act_bwd: the keep-bit store needs resample = none and no residual");
+  const bool plain = resample == SIVAE_RESAMPLE_NONE && res == nullptr && (mask == nullptr || keep_bits != nullptr) &&
+                     dres == nullptr;
   if (plain) {
     const SeedRef sr = make_seed_ref(seed);
     const long long items = nvox * (C / 8);
     const int ablk = grid_for(items, 256 * 4);
-    if (p > 0.f) bn_bwd_reduce_plain_kernel<true><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, partial);
-    else bn_bwd_reduce_plain_kernel<false><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, partial);
+    if (keep_bits) bn_bwd_reduce_plain_kernel<2><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, keep_bits, partial);
+    else if (p > 0.f) bn_bwd_reduce_plain_kernel<1><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, nullptr, partial);
+    else bn_bwd_reduce_plain_kernel<0><<<blocks, kBnThreads, 0, st>>>(gg, yy, mean, invstd, gamma, beta, nvox, C, slope, p, sr, nullptr, partial);
     SIVAE_LAUNCH_OK("bn_bwd_reduce_plain_kernel");
     bn_bwd_finalize_kernel<<<cdiv(C, 8), kFinThreads, 0, st>>>(partial, blocks, C, nvox, coef, dgamma, dbeta);
     SIVAE_LAUNCH_OK("bn_bwd_finalize_kernel");
-    if (p > 0.f) bn_bwd_apply_plain_kernel<true><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr);
-    else bn_bwd_apply_plain_kernel<false><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr);
+    if (keep_bits) bn_bwd_apply_plain_kernel<2><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr, keep_bits);
+    else if (p > 0.f) bn_bwd_apply_plain_kernel<1><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr, nullptr);
+    else bn_bwd_apply_plain_kernel<0><<<ablk, 256, 0, st>>>(gg, yy, mean, invstd, gamma, beta, coef, (__nv_bfloat16*)dconv, items, C, slope, p, sr, nullptr);
     SIVAE_LAUNCH_OK("bn_bwd_apply_plain_kernel");
     return 0;
   }

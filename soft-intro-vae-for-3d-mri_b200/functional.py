@@ -201,25 +201,29 @@ class _StemBnAct(torch.autograd.Function):
         else:
             y = K.c1_to_cn(x1, weight, bias)
             mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
-        mask, seed = (None, 0)
+        mask, seed, bits = None, 0, None
         p_eff = p if bn.training else 0.0
         if p_eff > 0.0:
             mask, seed = dropout_state.next()
-        out = K.bn_act_fwd(y, scale, shift, None, slope, K.RESAMPLE_NONE, mask, p_eff, seed)
-        ctx.save_for_backward(x1, y, mean, invstd, gamma, beta, weight, mask)
+            if mask is None:
+                # in-kernel Philox dropout: the forward kernel stores its keep decisions (1 bit per element) so the two
+                # backward passes read 1/16 of a tensor instead of re-running Philox4x32-10
+                bits = torch.empty(y.numel() // 8, dtype=torch.uint8, device=y.device)
+        out = K.bn_act_fwd(y, scale, shift, None, slope, K.RESAMPLE_NONE, mask, p_eff, seed, keep_bits=bits)
+        ctx.save_for_backward(x1, y, mean, invstd, gamma, beta, weight, mask, bits)
         ctx.cfg = (slope, p_eff, seed, bn.training)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x1, y, mean, invstd, gamma, beta, weight, mask = ctx.saved_tensors
+        x1, y, mean, invstd, gamma, beta, weight, mask, bits = ctx.saved_tensors
         slope, p, seed, training = ctx.cfg
         if not training:
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference hot path")
         need_x, need_w, need_bias, need_g, need_b = ctx.needs_input_grad[:5]
         dconv, _, dgamma, dbeta = K.bn_act_bwd(g.contiguous(), y, None, mean, invstd, gamma, beta, slope,
                                                K.RESAMPLE_NONE, mask, p, seed, need_dres=False,
-                                               need_affine=bool(need_g or need_b))
+                                               need_affine=bool(need_g or need_b), keep_bits=bits)
         dw = dbias = dx = None
         if need_w or need_bias:
             dw, dbias, _ = K.wgrad_c1(dconv, x1, weight.shape[1], flip=False)

@@ -421,19 +421,34 @@ def _resampled_shape(shape, resample):
     return (n, d, h, w, c)
 
 
-def bn_act_fwd(y, scale, shift, res, slope: float, resample: int, mask=None, p: float = 0.0, seed: int = 0):
-    """out = resample(dropout(act(y*scale+shift (+res))))."""
+def _mask_args(y, mask, keep_bits, p, seed):
+    """-> (pointer, seed) of the C ABI's dual-use ``mask`` argument: a caller-provided byte keep-mask travels with
+    seed 0; the keep-bit store (uint8 [numel/8], written by the forward kernel from Philox(seed), read by backward)
+    travels with the non-zero seed of its dropout call."""
+    if mask is not None:
+        _req(mask, torch.uint8, "mask")
+        assert mask.shape == y.shape and keep_bits is None
+        return _p(mask), 0
+    if keep_bits is not None and p > 0.0:
+        _req(keep_bits, torch.uint8, "keep_bits")
+        assert keep_bits.numel() * 8 == y.numel() and seed != 0
+        return _p(keep_bits), seed
+    return None, seed
+
+
+def bn_act_fwd(y, scale, shift, res, slope: float, resample: int, mask=None, p: float = 0.0, seed: int = 0,
+               keep_bits=None):
+    """out = resample(dropout(act(y*scale+shift (+res)))).  ``keep_bits`` (uint8 [numel/8], resample = none): the kernel
+    stores its Philox keep decisions there, one bit per element, for ``bn_act_bwd``."""
     _req(y, torch.bfloat16, "y")
     n, d, h, w, c = y.shape
     if res is not None:
         _req(res, torch.bfloat16, "res")
         assert res.shape == y.shape
-    if mask is not None:
-        _req(mask, torch.uint8, "mask")
-        assert mask.shape == y.shape
+    mptr, seed = _mask_args(y, mask, keep_bits, p, seed)
     out = torch.empty(_resampled_shape(y.shape, resample), dtype=torch.bfloat16, device=y.device)
     _check(_L().sivae_bn_act_fwd(_p(y), _p(scale), _p(shift), _p(res), _p(out), n, d, h, w, c, slope, resample,
-                                 _p(mask), p, seed, _stream(y)), "sivae_bn_act_fwd")
+                                 mptr, p, seed, _stream(y)), "sivae_bn_act_fwd")
     return out
 
 
@@ -463,11 +478,12 @@ def bn_train_act_fwd(y, res, gamma, beta, running_mean, running_var, num_batches
 
 
 def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int, mask=None, p: float = 0.0,
-               seed: int = 0, need_dres: bool = False, need_affine: bool = True):
+               seed: int = 0, need_dres: bool = False, need_affine: bool = True, keep_bits=None):
     """-> (dconv bf16 like y, dres bf16 or None, dgamma fp32 [C] or None, dbeta fp32 [C] or None)."""
     _req(g, torch.bfloat16, "g")
     _req(y, torch.bfloat16, "y")
     n, d, h, w, c = y.shape
+    mptr, seed = _mask_args(y, mask, keep_bits, p, seed)
     assert tuple(g.shape) == _resampled_shape(y.shape, resample), (g.shape, y.shape, resample)
     lib = _L()
     ws = _workspace(y.device, lib.sivae_bn_workspace_bytes(c), "bn")
@@ -476,7 +492,7 @@ def bn_act_bwd(g, y, res, mean, invstd, gamma, beta, slope: float, resample: int
     aff = torch.empty(2, c, dtype=torch.float32, device=y.device) if need_affine else None
     _check(lib.sivae_bn_act_bwd(_p(g), _p(y), _p(res), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dconv), _p(dres),
                                 _p(aff[0]) if need_affine else None, _p(aff[1]) if need_affine else None,
-                                n, d, h, w, c, slope, resample, _p(mask), p, seed, _p(ws), ws.numel(), _stream(y)),
+                                n, d, h, w, c, slope, resample, mptr, p, seed, _p(ws), ws.numel(), _stream(y)),
            "sivae_bn_act_bwd")
     return dconv, dres, (aff[0] if need_affine else None), (aff[1] if need_affine else None)
 

@@ -127,6 +127,33 @@ def test_philox_dropout_is_consistent_and_calibrated():
     assert_f32_close(db2, db1, "dbeta", 1e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8, 64), (1, 5, 7, 3, 128), (3, 2, 2, 2, 256)])
+def test_dropout_keep_bit_store_equals_philox_regeneration(shape):
+    """The keep-bit store (forward writes 1 bit per element, backward reads it) must reproduce bit for bit what the
+    Philox-regenerating kernels compute for the same seed: same forward output, same dconv / dgamma / dbeta; the
+    stored bits are exactly the non-zero pattern of the forward output, and the kernel specification fed with the
+    decoded bits as an explicit mask agrees."""
+    C, p, seed = shape[-1], 0.35, 0xC0FFEE
+    y, g = bf(*shape), bf(*shape)
+    gam, bet = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    mean, invstd, scale, shift = S.bn_train_coeffs(y, gam, bet, None, None, None, 0.1, 1e-5)
+    bits = torch.zeros(y.numel() // 8, dtype=torch.uint8, device=DEV)
+    a_ref = K.bn_act_fwd(y, scale, shift, None, 0.2, 0, None, p, seed)
+    a = K.bn_act_fwd(y, scale, shift, None, 0.2, 0, None, p, seed, keep_bits=bits)
+    assert torch.equal(a, a_ref)
+    keep = S._unpack_keep_bits(bits, y.shape)
+    t = y.float() * scale + shift
+    assert torch.equal(keep | (t == 0), (a != 0) | (t == 0))
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.05
+    d_ref, _, dg_ref, db_ref = K.bn_act_bwd(g, y, None, mean, invstd, gam, bet, 0.2, 0, None, p, seed)
+    d, _, dg, db = K.bn_act_bwd(g, y, None, mean, invstd, gam, bet, 0.2, 0, None, p, seed, keep_bits=bits)
+    assert torch.equal(d, d_ref) and torch.equal(dg, dg_ref) and torch.equal(db, db_ref)
+    exp = S.bn_act_bwd(g, y, None, mean, invstd, gam, bet, 0.2, 0, keep.to(torch.uint8), p, 0)
+    assert_bf16_close(d, exp[0], "dconv vs spec", slack=0.02 * float(exp[0].float().abs().mean()) + 1e-6)
+    assert_f32_close(dg, exp[2], "dgamma", 1e-3)
+    assert_f32_close(db, exp[3], "dbeta", 1e-3)
+
+
 # ------------------------------------------------------------------------------------------- thin convs
 @pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (256, 1)])
 @pytest.mark.parametrize("flip", [False, True])
