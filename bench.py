@@ -33,12 +33,24 @@ VOL = (80, 96, 80)
 LOCAL_BATCH = 8
 GFLOP_PER_VOLUME_STEP = 7270.4       # 32 network passes x 227.2 GFLOP (SURVEY.md section 8d / BASELINE.md section 2)
 METRIC = "train volumes/sec (Soft-IntroVAE z=1200, 80x96x80)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on its top shape
-# (conv3_kd3_kernel, 64->64 @ 8x80x96x80; algorithmic 2 x 629.1 MB), from the ncu --set full capture summarised in
-# profiles/r01c_ncu_hot_kernels.md
-TRAFFIC_TOP_SHAPE_BYTES = 629615000 + 592356352
-TRAFFIC_NOTE = ("per launch of the top shape (64->64 @ 8x80x96x80), ncu --set full capture in "
-                "profiles/r01c_ncu_hot_kernels.md; algorithmic bytes 1.258e9")
+# roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on its top shape,
+# conv3_kd3_kernel 64->64 @ 8x80x96x80, algorithmic 2 x 629.1 MB) is READ from the committed summary of the ncu
+# --set full capture of the current kernel (tools/gpu/ncu_profile.sh writes it); absent file -> null.
+TOP_KERNEL_PROFILE = os.path.join(ROOT, "profiles", "top_kernel_ncu.json")
+HW_FLOP_FACTOR = {"conv3_igemm": 1.0, "conv3_wgrad": 1.0, "upconv3_fprop": 8.0 / 27.0, "upconv3_dgrad": 8.0 / 27.0,
+                  "upconv3_wgrad": 8.0 / 27.0}     # executed / reference-equivalent MACs (Upsample folded: 27 -> 8 taps)
+
+
+def _top_kernel_profile():
+    """-> (traffic bytes per launch or None, note)."""
+    if not os.path.isfile(TOP_KERNEL_PROFILE):
+        return None, "no ncu capture of this build committed (profiles/top_kernel_ncu.json absent)"
+    with open(TOP_KERNEL_PROFILE) as f:
+        d = json.load(f)
+    note = (f"ncu --set full, {d.get('kernel')} {d.get('shape')}, launch {d.get('duration_us')} us, tensor pipe "
+            f"{d.get('tensor_pipe_active_pct')} % active, source commit {d.get('commit')}; algorithmic bytes 1.258e9; "
+            f"profiles/{d.get('summary')}")
+    return d.get("dram_bytes_per_launch"), note
 
 
 def _peaks():
@@ -200,6 +212,38 @@ def fc_gflop_per_volume_step(chans, z_ch, grid):
     return (13 * enc + 19 * dec) / 1e9
 
 
+def measure_l_shape(dev, steps=3, vol=(160, 192, 160), batch=2):
+    """volumes/s of the headline net on the L-shape (160x192x160, same fully-convolutional net, latent
+    20x24x20 = 9600), inputs resident in HBM, whole-step CUDA graph + FusedAdam, CUDA-event timing."""
+    import sivae_b200
+    from sivae_b200 import trainer as T
+    torch.manual_seed(77)
+    net = sivae_b200.SoftIntroVAE(IN_CH, BLOCK_SETTING)
+    net.apply(T.init_weights_he)
+    net.to(dev).train()
+    opt_e = sivae_b200.FusedAdam(net.encoder.parameters(), lr=2e-4)
+    opt_d = sivae_b200.FusedAdam(net.decoder.parameters(), lr=2e-4)
+    d, h, w = vol
+    real = torch.rand(batch, 1, d, h, w, device=dev)
+    noise = torch.randn(batch, 1, d // 8, h // 8, w // 8, device=dev)
+    g = sivae_b200.graph.GraphedTrainStep(net, opt_e, opt_d, real, noise, T.StepHyper(), warmup=2)
+    for _ in range(2):
+        g(real, noise)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = g(real, noise)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gflop = GFLOP_PER_VOLUME_STEP * (d * h * w) / float(VOL[0] * VOL[1] * VOL[2])
+    return {"workload": f"same net, {d}x{h}x{w} ({d * h * w} voxels, latent {d // 8}x{h // 8}x{w // 8}), local batch {batch}",
+            "value": batch / (ms / 1e3), "unit": "volumes/s", "ms_per_step": ms, "steps": steps,
+            "gflop_per_volume_step": gflop, "whole_step_tflops": batch / (ms / 1e3) * gflop / 1e3,
+            "lossE": float(out["lossE"])}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import sivae_b200
@@ -215,6 +259,11 @@ def run_ours(args):
     if sampler:
         sampler.start()                                     # early: nvidia-smi takes ~1 s to deliver its first sample
     B = args.batch
+    if args.global_batch:
+        # BASELINE configs[3] as stated (main_DataParallel.py:609: global batch 64 over 2/4/8 GPUs): strong scaling
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
     D, H, W = args.vol
     fc = args.workload == "fc600"
     if fc and tuple(args.vol) != VOL:
@@ -336,6 +385,16 @@ def run_ours(args):
     ms_e2e, res = timed(step_e2e, args.steps)
     if not (lossE == lossE and lossD == lossD):
         raise SystemExit("NaN loss in the benchmark step")
+    params_identical = None
+    if world > 1:
+        # replicas must hold bit-identical parameters after the run (identical init + averaged gradients + the same
+        # update): fp64 checksums (sum, sum of squares) of every parameter, max over ranks == min over ranks
+        chk = torch.stack([torch.stack([p_.detach().double().sum(), p_.detach().double().pow(2).sum()])
+                           for p_ in net.parameters()]).flatten()
+        mx, mn = chk.clone(), chk.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        params_identical = bool(torch.equal(mx, mn)) and bool(torch.isfinite(chk).all())
 
     if rank != 0:
         if world > 1:
@@ -352,12 +411,22 @@ def run_ours(args):
     achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
     top_shape = max(dom["by_shape"].items(), key=lambda kv: kv[1]["ms"]) if dom["by_shape"] else None
     wg = ksum.get("conv3_wgrad", dict(launches=0, ms=0.0, work=0.0))
+    # every tensor-core 3x3x3 conv kernel of the step together, in EXECUTED (hardware) FLOPs: tensor-pipe utilisation
+    hw_flop = sum(ksum[k]["work"] * f for k, f in HW_FLOP_FACTOR.items() if k in ksum)
+    hw_ms = sum(ksum[k]["ms"] for k in HW_FLOP_FACTOR if k in ksum)
+    hw_tflops = hw_flop / (hw_ms * 1e-3) / 1e12 if hw_ms > 0 else 0.0
+    traffic, traffic_note = _top_kernel_profile()
     roofline = {"bound": "tensor",
                 "kernel": "3x3x3 conv fprop/dgrad on tcgen05 (conv3_kd3_kernel + conv3_igemm_kernel, all layer shapes)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
-                "traffic": TRAFFIC_TOP_SHAPE_BYTES if tuple(args.vol) == VOL and B == LOCAL_BATCH else None,
-                "traffic_note": TRAFFIC_NOTE,
+                "traffic": traffic if tuple(args.vol) == VOL and B == LOCAL_BATCH and not fc else None,
+                "traffic_note": traffic_note,
+                # flat per-kernel figures (dominant kernel on its top shape; all tensor-core conv kernels together)
+                "top_ms": top_shape[1]["ms"] / top_shape[1]["launches"] if top_shape else None,
+                "top_tflops": top_shape[1]["work"] / (top_shape[1]["ms"] * 1e-3) / 1e12 if top_shape else None,
+                "top_frac": (top_shape[1]["work"] / (top_shape[1]["ms"] * 1e-3) / 1e12 / peak_tf) if top_shape else None,
+                "hw_tflops": hw_tflops, "all_tc_conv_frac": hw_tflops / peak_tf, "all_tc_conv_ms": hw_ms,
                 "launches": dom["launches"],
                 "share_of_step": dom["ms"] / (ms / args.steps if graphed is not None else ms) if ms else None,
                 "top_shape": ({"NDHWCiCo": list(top_shape[0]),
@@ -386,6 +455,21 @@ def run_ours(args):
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
                                       "d2h_bytes_per_step": int(res.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roofline, "loss": {"lossE": lossE, "lossD": lossD}}
+    if world > 1:
+        line["params_identical"] = params_identical
+    if args.global_batch:
+        line["scaling"] = "strong"
+        line["config"]["global_batch_mode"] = f"--global-batch {args.global_batch}: local batch {B} on {world} ranks"
+    if world == 1 and not fc and not args.no_lshape and tuple(args.vol) == VOL:
+        # second, clearly named entry: the "~5 M voxel" point of BASELINE.json's metric -- the same net on the original
+        # 160x192x160 resolution (4,915,200 voxels, latent 20x24x20), batch 2, same whole-step graph + FusedAdam
+        del graphed
+        net = opt_e = opt_d = None
+        torch.cuda.empty_cache()
+        try:
+            line["l_shape"] = measure_l_shape(dev, steps=min(args.steps, 5))
+        except Exception as ex:  # noqa: BLE001
+            line["l_shape"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     if fc:
         line["roofline"]["traffic"] = None
         line["roofline"]["note"] = ("channel counts below 64 run zero-padded to 64 (tcgen05 tile width): the 32-channel "
@@ -420,6 +504,10 @@ def main():
     ap.add_argument("--vol", type=int, nargs=3, default=list(VOL), metavar=("D", "H", "W"),
                     help="volume extents (headline 80 96 80; 160 192 160 = the ~5M-voxel L-shape, use --batch 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lshape", action="store_true", help="skip the second (160x192x160, batch 2) measurement")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch split over the ranks (BASELINE configs[3]: 64 -> local 32/16/8 at 2/4/8 "
+                         "GPUs, strong scaling); default 0 = fixed local batch (--batch), weak scaling")
     ap.add_argument("--workload", default="z1200", choices=["z1200", "fc600"],
                     help="z1200: the headline conv-latent net (BASELINE config 3); fc600: the FC-latent variant "
                          "mymodel.SoftIntroVAE(32,64,128,256,600) of 600z_main.py (BASELINE config 2, batch 4)")

@@ -363,19 +363,6 @@ int sivae_flat_to_ndhwc(const float* src, void* dst, int B, int S, int C, int Cp
 int sivae_add_act_fwd(const void* a, const void* b, void* out, long long n, float slope, void* stream);
 int sivae_add_act_bwd(const void* g, const void* out, void* dz, long long n, float slope, void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * EXPERIMENTAL (default off in the Python host: SIVAE_SPLITK=1 enables it; not yet validated on hardware, see the
- * header of the kernel in csrc/conv3_tc.cu): sivae_conv3_igemm with a caller-owned workspace.  For shapes with fewer
- * voxel tiles than two waves of CTAs (latent-resolution layers) the 27 taps are split over up to 9 CTAs per tile, the
- * fp32 partial accumulators go to the workspace and a reduce kernel writes the bf16 output; every other shape, or a
- * workspace smaller than sivae_conv3_igemm_splitk_workspace_bytes(...) (0 = no split for this shape), runs
- * sivae_conv3_igemm unchanged.  Same operands and result as sivae_conv3_igemm (nn.Conv3d k=3 p=1 forward / data
- * gradient, models/models.py:17,21,55,59).
- * ---------------------------------------------------------------------------------------------- */
-size_t sivae_conv3_igemm_splitk_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
-int sivae_conv3_igemm_ws(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
-                         void* workspace, size_t workspace_bytes, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ requires grad (the trainer freezes encoder / decoder per phase, utils/my_trainer
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Optional
 
@@ -21,6 +22,7 @@ import torch
 
 from . import kernels as K
 
+KEEP_BITS = os.environ.get("SIVAE_KEEP_BITS", "1") != "0"   # 0: regenerate Philox in both backward passes (A/B switch)
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
 
@@ -205,7 +207,7 @@ class _StemBnAct(torch.autograd.Function):
         p_eff = p if bn.training else 0.0
         if p_eff > 0.0:
             mask, seed = dropout_state.next()
-            if mask is None:
+            if mask is None and KEEP_BITS:
                 # in-kernel Philox dropout: the forward kernel stores its keep decisions (1 bit per element) so the two
                 # backward passes read 1/16 of a tensor instead of re-running Philox4x32-10
                 bits = torch.empty(y.numel() // 8, dtype=torch.uint8, device=y.device)

@@ -82,8 +82,6 @@ _SIGNATURES = {
     "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
     "sivae_affine_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "sivae_conv3_igemm_splitk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "sivae_conv3_igemm_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "sivae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
@@ -254,15 +252,6 @@ def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
     y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
     flops = 2.0 * 27 * ci * co * n * d * h * w
     lib = _L()
-    if os.environ.get("SIVAE_SPLITK") == "1":
-        # EXPERIMENTAL (see include/sivae.h): split-K over the taps for shapes with too few voxel tiles to fill the GPU
-        nbytes = lib.sivae_conv3_igemm_splitk_workspace_bytes(n, d, h, w, ci, co)
-        if nbytes > 0:
-            ws = _workspace(x.device, nbytes, "splitk")
-            _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
-                   lambda: _check(lib.sivae_conv3_igemm_ws(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _p(ws), ws.numel(),
-                                                           _stream(x)), "sivae_conv3_igemm_ws"))
-            return y
     _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
            lambda: _check(lib.sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
                           "sivae_conv3_igemm"))
@@ -799,7 +788,7 @@ def cn_to_c1(x, w, bias, flip: bool = False, act: int = 0, mask=None, p: float =
     if w.shape[1] == 27 and c % 64 == 0:
         # 3x3x3: implicit GEMM on tcgen05 (N=16 tile, fp32 column-0 epilogue); weights are rounded to bf16
         ws = _workspace(x.device, lib.sivae_conv3_to1_workspace_bytes(c), "to1")
-        flops = 2.0 * 27 * c * 16 * n * d * h * ww
+        flops = 2.0 * 27 * c * 1 * n * d * h * ww          # reference-equivalent: Cout = 1 (the kernel pads N to 16 / 64 columns)
         _timed("conv3_to1", (flops, (n, d, h, ww, c, 1)),
                lambda: _check(lib.sivae_conv3_to1(_p(x), _p(w), _p(bias), _p(y), n, d, h, ww, c, int(flip), act,
                                                   _p(mask), p, seed, _p(ws), ws.numel(), _stream(x)),

@@ -90,3 +90,24 @@ def test_clock_sampler_window():
     s2.lines += [busy]
     out2 = s2.stop()
     assert out2["samples"] == 5 and out2["window"].startswith("warm-up")
+
+
+def test_top_kernel_profile_is_read_from_profiles(tmp_path, monkeypatch):
+    """roofline.traffic is not a constant in bench.py: it comes from the committed ncu summary of the current kernel
+    (profiles/top_kernel_ncu.json), and is null when no capture is committed."""
+    monkeypatch.setattr(bench, "TOP_KERNEL_PROFILE", str(tmp_path / "absent.json"))
+    traffic, note = bench._top_kernel_profile()
+    assert traffic is None and "absent" in note
+    p = tmp_path / "top_kernel_ncu.json"
+    p.write_text(json.dumps({"kernel": "conv3_kd3_kernel", "shape": "64->64 @ 8x80x96x80", "duration_us": 800.0,
+                             "tensor_pipe_active_pct": 70.0, "dram_bytes_per_launch": 1.23e9, "commit": "abc1234",
+                             "summary": "r02_ncu_top_kernel.md"}))
+    monkeypatch.setattr(bench, "TOP_KERNEL_PROFILE", str(p))
+    traffic, note = bench._top_kernel_profile()
+    assert traffic == 1.23e9 and "abc1234" in note and "r02_ncu_top_kernel.md" in note
+
+
+def test_hw_flop_factors():
+    # Upsample(2) folded into the convolution executes 8 of the 27 reference taps per output voxel
+    assert bench.HW_FLOP_FACTOR["upconv3_fprop"] == pytest.approx(8 / 27)
+    assert bench.HW_FLOP_FACTOR["conv3_igemm"] == 1.0

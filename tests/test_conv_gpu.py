@@ -42,16 +42,11 @@ CONV_MODES = {"auto": {}, "kd_force": {"SIVAE_CONV_KD": "force"}, "tapwise": {"S
               "n256_ring3": {"SIVAE_CONV_KD": "0", "SIVAE_N256": "1"}}
 
 
-if os.environ.get("SIVAE_TEST_SPLITK") == "1":
-    # EXPERIMENTAL split-K path (csrc/conv3_tc.cu, conv3_igemm_splitk_kernel): written after the round's GPU budget was
-    # spent, so its parity runs are opt-in until it has been through a GPU box once
-    CONV_MODES["splitk"] = {"SIVAE_CONV_KD": "0", "SIVAE_SPLITK": "1"}
-
 
 @pytest.fixture(params=list(CONV_MODES))
 def kwmode(request):
     import os
-    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW", "SIVAE_DEEP_RING", "SIVAE_N256", "SIVAE_SPLITK")
+    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW", "SIVAE_DEEP_RING", "SIVAE_N256")
     old = {k: os.environ.get(k) for k in keys}
     for k in keys:
         os.environ.pop(k, None)

@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 VAR=$1; A=$2; B=$3; EXTRA=$4
 for i in 1 2; do
   for v in "$A" "$B"; do
-    env $VAR=$v timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline $EXTRA 2>/dev/null | \
+    env $VAR=$v timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-lshape $EXTRA 2>/dev/null | \
       python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$VAR=$v', round(d['ms_per_step'],2), 'ms', round(d['value'],1), 'vol/s', d['gpu_launches'], 'launches')"
   done
 done

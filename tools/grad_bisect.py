@@ -65,6 +65,8 @@ def main():
     ap.add_argument("--worst", type=int, default=12)
     ap.add_argument("--all", action="store_true", help="print every parameter")
     ap.add_argument("--device", default="cuda")
+    ap.add_argument("--follow", default="oracle", choices=["oracle", "ours"],
+                    help="whose Adam trajectory supplies the weights at which the gradients are compared")
     a = ap.parse_args()
 
     import sivae_b200
@@ -121,6 +123,11 @@ def main():
 
     hp, ohp = T.StepHyper(), O.StepHyper()
     last = max(a.at)
+    tnet = topt = None
+    if a.follow == "ours":
+        import copy
+        tnet = copy.deepcopy(net)
+        topt = (torch.optim.Adam(tnet.encoder.parameters(), lr=2e-4), torch.optim.Adam(tnet.decoder.parameters(), lr=2e-4))
     for step in range(last + 1):
         real = data[(step % a.n_batches) * batch:(step % a.n_batches + 1) * batch]
         noise = torch.randn(lat, device=dev, generator=g)
@@ -128,7 +135,7 @@ def main():
         masks = draw_masks()
         omasks = [m.float() for m in masks]
         if step in a.at:
-            snap = {k: v.detach().clone() for k, v in sd.items()}
+            snap = {k: v.detach().clone() for k, v in (tnet.state_dict() if tnet is not None else sd).items()}
             t0, gE0, gD0 = O.soft_intro_step_grads({k: v.clone() for k, v in snap.items()}, cfg, real, noise, eps,
                                                    omasks, ohp)
             ref = {**gE0, **gD0}
@@ -180,7 +187,15 @@ def main():
                     print(f"   {r['name']:45s} cos {r['cos']:.5f}  |g|/|g0| {r['ratio']:.4f}  proj {r['proj']:.4f}  "
                           f"sign {r['sign']:.4f}")
             sys.stdout.flush()
-        if step < last:
+        if step < last and tnet is not None:
+            F.dropout_state.mask_feed = iter(to_feed(masks))
+            F.noise_state.eps_feed = iter(eps)
+            try:
+                T.soft_intro_train_step(tnet, real, noise, topt[0], topt[1], hp)
+            finally:
+                F.dropout_state.mask_feed = None
+                F.noise_state.eps_feed = None
+        elif step < last:
             O.soft_intro_step_grads(sd, cfg, real, noise, eps, omasks, ohp, apply_update=apply_update)
 
 
