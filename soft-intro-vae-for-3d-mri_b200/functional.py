@@ -14,6 +14,7 @@ requires grad (the trainer freezes encoder / decoder per phase, utils/my_trainer
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import weakref
 from typing import Optional
@@ -77,20 +78,85 @@ def begin_step(device):
 
 
 class BnState:
-    """Non-differentiable BatchNorm state handed to the fused units."""
+    """Non-differentiable BatchNorm state handed to the fused units.  ``defer`` = the holder's (running_mean,
+    running_var, num_batches_tracked) when this call must NOT touch them itself (it runs on a side stream next to
+    another pass through the same layer, see ``deferred_bn``): the kernels then get NULL buffers and the batch
+    statistics are logged for ``apply_deferred_bn``."""
 
-    __slots__ = ("running_mean", "running_var", "num_batches_tracked", "training", "momentum", "eps")
+    __slots__ = ("running_mean", "running_var", "num_batches_tracked", "training", "momentum", "eps", "defer")
 
-    def __init__(self, running_mean, running_var, num_batches_tracked, training, momentum=BN_MOMENTUM, eps=BN_EPS):
+    def __init__(self, running_mean, running_var, num_batches_tracked, training, momentum=BN_MOMENTUM, eps=BN_EPS,
+                 defer=None):
         self.running_mean, self.running_var, self.num_batches_tracked = running_mean, running_var, num_batches_tracked
-        self.training, self.momentum, self.eps = training, momentum, eps
+        self.training, self.momentum, self.eps, self.defer = training, momentum, eps, defer
+
+
+# ----------------------------------------------------------------------------------------------
+# two independent passes on two streams (trainer._fork_join): the side branch defers its BatchNorm running-statistic
+# updates, so that two passes through the same layer never race on the buffers and the updates compose in the
+# reference's call order (running <- 0.9 running + 0.1 batch is order dependent; SURVEY Q15)
+# ----------------------------------------------------------------------------------------------
+class _BnDefer:
+    def __init__(self):
+        self.records = None      # list while a side branch is being issued, else None
+
+
+bn_defer = _BnDefer()
+
+
+@contextlib.contextmanager
+def deferred_bn():
+    """Inside: train-mode BatchNorm calls leave the running statistics alone and log (buffers, mean, invstd, n, momentum,
+    eps) instead.  -> the log, to be passed to ``apply_deferred_bn`` after the streams have joined."""
+    prev, bn_defer.records = bn_defer.records, []
+    try:
+        yield bn_defer.records
+    finally:
+        bn_defer.records = prev
+
+
+def _note_bn(bn: BnState, mean, invstd, nvox: int):
+    if bn.defer is not None and bn.training:
+        bn_defer.records.append((bn.defer, mean, invstd, int(nvox), float(bn.momentum), float(bn.eps)))
+
+
+def apply_deferred_bn(records):
+    """running_mean <- (1-m) running_mean + m mean;  running_var <- (1-m) running_var + m var n/(n-1) with the biased batch
+    variance var = 1/invstd^2 - eps;  num_batches_tracked += 1 -- in log order, a handful of multi-tensor launches per
+    wave (wave k = the k-th pass through each layer in the log)."""
+    if not records:
+        return
+    waves, count = [], {}
+    for r in records:
+        k = count.get(id(r[0][0]), 0)
+        count[id(r[0][0])] = k + 1
+        if k == len(waves):
+            waves.append([])
+        waves[k].append(r)
+    with torch.no_grad():
+        for wave in waves:
+            for m in sorted({r[4] for r in wave}):
+                rs = [r for r in wave if r[4] == m]
+                var = torch._foreach_pow([r[2] for r in rs], -2.0)
+                torch._foreach_sub_(var, [r[5] for r in rs])
+                torch._foreach_mul_(var, [m * (r[3] / (r[3] - 1.0) if r[3] > 1 else 1.0) for r in rs])
+                rms, rvs = [r[0][0] for r in rs], [r[0][1] for r in rs]
+                torch._foreach_mul_(rms, 1.0 - m)
+                torch._foreach_add_(rms, [r[1] for r in rs], alpha=m)
+                torch._foreach_mul_(rvs, 1.0 - m)
+                torch._foreach_add_(rvs, var)
+            nbts = [r[0][2] for r in wave if r[0][2] is not None]
+            if nbts:
+                torch._foreach_add_(nbts, 1)
 
 
 def _bn_coeffs(y, gamma, beta, bn: BnState):
     """-> (mean, invstd, scale, shift).  Train: batch statistics (+ running-stat update).  Eval: running stats."""
     if bn.training:
-        return K.bn_train_coeffs(y, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+        coef = K.bn_train_coeffs(y, gamma, beta, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                  bn.momentum, bn.eps)
+        _note_bn(bn, coef[0], coef[1], y.numel() // y.shape[-1])
+        return coef
     invstd = torch.rsqrt(bn.running_var + bn.eps)
     scale = gamma * invstd
     return bn.running_mean, invstd, scale, beta - bn.running_mean * scale
@@ -152,6 +218,7 @@ class _ConvBnAct(torch.autograd.Function):
             y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
             out, mean, invstd = K.bn_train_act_fwd(y, res, gamma, beta, bn.running_mean, bn.running_var,
                                                    bn.num_batches_tracked, bn.momentum, bn.eps, slope)
+            _note_bn(bn, mean, invstd, y.numel() // y.shape[-1])
             ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
             ctx.cfg = (slope, resample, bn.training, pre_up)
             return out
@@ -160,6 +227,7 @@ class _ConvBnAct(torch.autograd.Function):
             conv_bn = K.upconv3_fprop_bn if pre_up else K.conv3_igemm_bn
             y, mean, invstd, scale, shift = conv_bn(x, wf, gamma, beta, bn.running_mean, bn.running_var,
                                                     bn.num_batches_tracked, bn.momentum, bn.eps)
+            _note_bn(bn, mean, invstd, y.numel() // y.shape[-1])
         else:
             y = K.upconv3_fprop(x, wf) if pre_up else K.conv3_igemm(x, wf)
             mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)
@@ -200,6 +268,7 @@ class _StemBnAct(torch.autograd.Function):
         if bn.training:
             y, mean, invstd, scale, shift = K.c1_to_cn_bn(x1, weight, bias, gamma, beta, bn.running_mean, bn.running_var,
                                                           bn.num_batches_tracked, bn.momentum, bn.eps)
+            _note_bn(bn, mean, invstd, y.numel() // y.shape[-1])
         else:
             y = K.c1_to_cn(x1, weight, bias)
             mean, invstd, scale, shift = _bn_coeffs(y, gamma, beta, bn)

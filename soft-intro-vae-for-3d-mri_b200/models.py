@@ -60,6 +60,12 @@ class _BnBinding:
     def state(self) -> F.BnState:
         bn = self.bn
         mom = 0.1 if bn.momentum is None else bn.momentum
+        if F.bn_defer.records is not None and bn.training:
+            # side-stream pass (trainer._fork_join): the running statistics are updated after the streams have joined
+            if self.c != self.cp:
+                raise RuntimeError("two-stream execution needs channel counts that are multiples of 64")
+            return F.BnState(None, None, None, True, mom, bn.eps,
+                             defer=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         if self.c == self.cp:
             return F.BnState(bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.training, mom, bn.eps)
         rm = _pad_dim(bn.running_mean, 0, self.cp)
@@ -132,6 +138,12 @@ class BuildingBlock(nn.Module):
 
     def _projection(self, channel_in, channel_out):
         return nn.Conv3d(channel_in, channel_out, kernel_size=1, stride=1, padding=0)
+
+    def prepack(self):
+        """Make sure the bf16 weight packs of both convolutions exist (on the CURRENT stream) -- called before two passes
+        through this block are issued on two streams, so neither of them launches a pack kernel the other one needs."""
+        F._packed(_conv3_weight(self.block[0]), False)
+        F._packed(_conv3_weight(self.block[4]), self.stride == 2 and self._upsample)
 
     def forward(self, x):
         """x, result: NDHWC activations (bf16 on the CUDA path)."""
@@ -388,6 +400,15 @@ class SoftIntroVAE(nn.Module):
         super().__init__()
         self.encoder = VAEResNetEncoder(in_ch=in_ch, block_setting=block_setting)
         self.decoder = ResNetDecoder(self.encoder)
+
+    def two_stream_ok(self) -> bool:
+        """Independent passes may run on two CUDA streams (trainer._fork_join) when no layer needs channel padding."""
+        return all(m.num_features % CH_ALIGN == 0 for m in self.modules() if isinstance(m, nn.BatchNorm3d))
+
+    def prepack(self):
+        for m in self.modules():
+            if isinstance(m, BuildingBlock):
+                m.prepack()
 
     def reparameterize(self, mu, logvar, val_flag=False):
         # train: eps ~ N(0,1) from torch's generator (randn_like); validation: the constant 0.1 (SURVEY Q9)

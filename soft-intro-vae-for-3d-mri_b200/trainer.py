@@ -80,6 +80,56 @@ def _set_requires_grad(module: nn.Module, flag: bool):
         p.requires_grad = flag
 
 
+# Two-stream issue of the independent passes of an iteration (SIVAE_TWO_STREAMS=1; default off until measured): of the 13
+# forward passes of utils/my_trainer.py:248-311 these pairs do not depend on each other --
+#   E phase: decode(noise) | encode(real) -> z -> decode(z);   forward(rec.detach()) | forward(fake.detach())
+#   D phase: decode(noise) | decode(z);   encode(rec) | encode(fake);   decode(z_rec) | decode(z_fake)
+# -- and the latent-resolution layers (80-160 CTAs of serial K chains, dozens of 5-10 us BatchNorm launches) leave most
+# of the GPU idle.  The second pass of a pair is issued on a side stream; autograd replays each pass's backward on the
+# stream its forward ran on, so the backward passes overlap the same way; inside a CUDA-graph capture the pairs become
+# parallel branches.  Python still issues the passes in the reference's order, so dropout keys, fed masks and eps
+# draws are unchanged, and the side pass defers its BatchNorm running-statistic updates until the streams have joined
+# (functional.deferred_bn), which keeps them race-free and in the reference's order.
+TWO_STREAMS = os.environ.get("SIVAE_TWO_STREAMS", "0") == "1"
+_side_streams = {}
+
+
+def _fork_join(model, device, fn_a, fn_b):
+    """-> (fn_a(), fn_b()), with fn_b on a side stream when two-stream issue is on and the model allows it."""
+    ok = TWO_STREAMS and device.type == "cuda" and hasattr(model, "two_stream_ok")
+    if ok:
+        if not hasattr(model, "_two_stream_ok"):
+            model._two_stream_ok = bool(model.two_stream_ok())
+        ok = model._two_stream_ok
+    if not ok:
+        return fn_a(), fn_b()
+    model.prepack()                       # no pack kernel may be launched inside one branch and read by the other
+    cur = torch.cuda.current_stream(device)
+    side = _side_streams.get(device)
+    if side is None:
+        side = _side_streams[device] = torch.cuda.Stream(device)
+    side.wait_stream(cur)
+    ra = fn_a()
+    with torch.cuda.stream(side), F.deferred_bn() as log:
+        rb = fn_b()
+    cur.wait_stream(side)
+    # tensors of the side branch that outlive the join (its results, its autograd graph) are only freed after the
+    # backward of this phase, i.e. after every reader on either stream has been issued and joined
+    F.apply_deferred_bn(log)
+    return ra, rb
+
+
+def _encode_sample_decode(model, x):
+    mu, logvar = model.encode(x)
+    z = model.reparameterize(mu, logvar)
+    return mu, logvar, z, model.decode(z)
+
+
+def _encode_sample(model, x):
+    mu, logvar = model.encode(x)
+    return mu, logvar, model.reparameterize(mu, logvar)
+
+
 def _zero_grad(optimizer, reducer):
     # a FlatGradReducer keeps ``.grad`` as views of its flat exchange buffer: clear in place, do not drop them
     optimizer.zero_grad(set_to_none=not getattr(reducer, "needs_persistent_grads", False))
@@ -95,12 +145,11 @@ def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional
     F.begin_step(real_batch.device)          # new dropout epoch (device-side counter; CUDA-graph safe)
     _set_requires_grad(model.encoder, True)
     _set_requires_grad(model.decoder, False)
-    fake = model.decode(noise_batch)
-    real_mu, real_logvar = model.encode(real_batch)
-    z = model.reparameterize(real_mu, real_logvar)
-    rec = model.decode(z)
-    rec_mu, rec_logvar, z_rec, rec_rec = model.forward(rec.detach())
-    fake_mu, fake_logvar, z_fake, rec_fake = model.forward(fake.detach())
+    dev = real_batch.device
+    fake, (real_mu, real_logvar, z, rec) = _fork_join(
+        model, dev, lambda: model.decode(noise_batch), lambda: _encode_sample_decode(model, real_batch))
+    (rec_mu, rec_logvar, z_rec, rec_rec), (fake_mu, fake_logvar, z_fake, rec_fake) = _fork_join(
+        model, dev, lambda: model.forward(rec.detach()), lambda: model.forward(fake.detach()))
     # per-sample vectors (the mse / kl kernels), then the whole :260-284 assembly in one fused kernel
     r_real = F.mse_persample(real_batch, rec)
     k_real = F.kl_persample(real_mu, real_logvar)
@@ -125,14 +174,11 @@ def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optio
     beta_rec, beta_kl, gamma_r = hp.beta_rec, hp.beta_kl, hp.gamma_r
     _set_requires_grad(model.encoder, False)
     _set_requires_grad(model.decoder, True)
-    fake = model.decode(noise_batch)
-    rec = model.decode(z.detach())
-    rec_mu, rec_logvar = model.encode(rec)
-    z_rec = model.reparameterize(rec_mu, rec_logvar)
-    fake_mu, fake_logvar = model.encode(fake)
-    z_fake = model.reparameterize(fake_mu, fake_logvar)
-    rec_rec = model.decode(z_rec.detach())
-    rec_fake = model.decode(z_fake.detach())
+    dev = real_batch.device
+    fake, rec = _fork_join(model, dev, lambda: model.decode(noise_batch), lambda: model.decode(z.detach()))
+    (rec_mu, rec_logvar, z_rec), (fake_mu, fake_logvar, z_fake) = _fork_join(
+        model, dev, lambda: _encode_sample(model, rec), lambda: _encode_sample(model, fake))
+    rec_rec, rec_fake = _fork_join(model, dev, lambda: model.decode(z_rec.detach()), lambda: model.decode(z_fake.detach()))
     r_real = F.mse_persample(real_batch, rec)
     r_rec_rec = F.mse_persample(rec.detach(), rec_rec)
     r_fake_rec = F.mse_persample(fake.detach(), rec_fake)

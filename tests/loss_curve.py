@@ -51,11 +51,17 @@ def synthetic_volumes(n, vol, gen):
 
 
 def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setting=((64, 1, 2), (128, 1, 2), (256, 2, 2)),
-        lr=2e-4, seed=77, device="cuda", verbose=False, control=False, fc=None, perturb=None):
+        lr=2e-4, seed=77, device="cuda", verbose=False, control=False, fc=None, perturb=None, warm_start=0):
     """``fc`` = dict(chans=(c1,c2,c3,c4), z_ch=..., grid=(gd,gh,gw)) selects the FC-latent variant (models/mymodel.py +
     utils/trainer_fc.py: vector noise, no dropout, scale fixed at 8/(80*96*80)); ``vol`` must then be 16 * grid.
     ``perturb`` = (seed, rel): every arm starts from the SAME initial weights multiplied by (1 + rel * N(0,1)) --
-    replicas for tools/curve_ensemble.py, which measures how far trajectories of ONE arithmetic spread."""
+    replicas for tools/curve_ensemble.py, which measures how far trajectories of ONE arithmetic spread.
+    ``warm_start`` = N: the fp32 oracle alone trains N steps first; every arm then continues from ITS weights, BatchNorm
+    buffers and Adam moments (exp_avg, exp_avg_sq, step) for ``steps`` recorded steps.  From a cold start the recipe's
+    step-1 transient (kl_real jumps from 6e2 to ~1e9 = sum of exp(logvar), set by the few largest logvar elements) is
+    amplified chaotically by any rounding, and its gradient spike stays in Adam's second moment (beta2 = 0.999) for the
+    whole run, so 200-step curves mostly measure that one spike (profiles/r02_ensemble_*.md); behind the transient the
+    curves measure the arithmetic of the training dynamics."""
     import sivae_b200
     from sivae_b200 import functional as F, trainer as T
     from oracle import sivae_oracle as O
@@ -149,11 +155,34 @@ def run(steps=200, vol=(16, 24, 16), batch=2, n_batches=4, in_ch=64, block_setti
     curves = {"ours": {k: [] for k in TERMS}, "oracle": {k: [] for k in TERMS}}
     if control:
         curves["control"] = {k: [] for k in TERMS}
-    for step in range(steps):
+    def adopt(opt_dst, params_dst, opt_src, params_src):
+        """Give ``opt_dst`` (over ``params_dst``) deep copies of the Adam state ``opt_src`` holds for ``params_src``."""
+        for pd, ps in zip(params_dst, params_src):
+            st = opt_src.state.get(ps)
+            if st:
+                opt_dst.state[pd] = {k_: (v_.detach().clone() if torch.is_tensor(v_) else v_) for k_, v_ in st.items()}
+
+    for step in range(-warm_start, steps):
         real = data[(step % n_batches) * batch:(step % n_batches + 1) * batch]
         noise = torch.randn(lat, device=dev, generator=g)
         eps = [torch.randn(lat, device=dev, generator=g) for _ in range(5)]
         masks = draw_masks()
+        if step < 0:                                                        # warm start: the fp32 oracle alone
+            omasks = None if fc is not None else [m.float() for m in masks]
+            O.soft_intro_step_grads(sd, cfg, real, noise, eps, omasks, ohp, apply_update=apply_update)
+            if step == -1:
+                with torch.no_grad():
+                    net.load_state_dict({k: v.detach() for k, v in sd.items()})
+                named = dict(net.named_parameters())
+                adopt(opt_e, [named[k] for k in enc_names], o_opt["E"], [sd[k] for k in enc_names])
+                adopt(opt_d, [named[k] for k in dec_names], o_opt["D"], [sd[k] for k in dec_names])
+                if control:
+                    with torch.no_grad():
+                        for k in sd_c:
+                            sd_c[k].copy_(sd[k])
+                    adopt(c_opt["E"], [sd_c[k] for k in enc_names], o_opt["E"], [sd[k] for k in enc_names])
+                    adopt(c_opt["D"], [sd_c[k] for k in dec_names], o_opt["D"], [sd[k] for k in dec_names])
+            continue
         # ---- ours
         F.dropout_state.mask_feed = iter(to_feed(masks))
         F.noise_state.eps_feed = iter(eps)
@@ -211,6 +240,8 @@ def main():
     ap.add_argument("--control", action="store_true", help="also train the oracle under bf16 autocast")
     ap.add_argument("--fc", type=int, nargs=5, default=None, metavar=("C1", "C2", "C3", "C4", "Z"),
                     help="FC-latent variant mymodel.SoftIntroVAE(C1,C2,C3,C4,Z); the latent grid is vol/16")
+    ap.add_argument("--warm-start", type=int, default=0,
+                    help="the fp32 oracle alone trains this many steps first; every arm continues from its state")
     ap.add_argument("--env", nargs="*", default=[], metavar="K=V",
                     help="libsivae kernel-family toggles for this run (e.g. SIVAE_CONV_KD=0), for bisecting")
     a = ap.parse_args()
@@ -220,11 +251,14 @@ def main():
     fc = None
     if a.fc is not None:
         fc = dict(chans=tuple(a.fc[:4]), z_ch=a.fc[4], grid=tuple(v // 16 for v in a.vol))
-    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True, control=a.control, fc=fc)
+    curves = run(a.steps, tuple(a.vol), a.batch, a.n_batches, verbose=True, control=a.control, fc=fc,
+                 warm_start=a.warm_start)
     dev = deviations(curves)
     netname = f"mymodel.SoftIntroVAE{tuple(a.fc)} (FC-latent variant)" if a.fc is not None else "headline net"
     lines = [f"# Loss-curve parity, {a.steps} steps, {netname}, volumes {a.vol}, batch {a.batch}, "
-             f"{a.n_batches} synthetic batches cycled, identical init / noise / eps / dropout masks", "",
+             f"{a.n_batches} synthetic batches cycled, identical init / noise / eps / dropout masks"
+             + (f", warm start: every arm continues the fp32 oracle's state after {a.warm_start} steps" if a.warm_start
+                else ""), "",
              "ours = libsivae.so (bf16 activations) ; oracle = torch fp32 restatement of the reference on the same GPU", "",
              "| term | oracle first | oracle last | ours last | rel.dev median | p90 | max | 10-step-mean max |",
              "|---|---:|---:|---:|---:|---:|---:|---:|"]

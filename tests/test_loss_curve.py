@@ -21,6 +21,41 @@ def test_loss_curve_wiring_cpu():
         assert v["max"] < 2e-3, (k, v)
 
 
+def test_loss_curve_warm_start_wiring_cpu():
+    """Warm start (tests/loss_curve.py ``warm_start``): after N oracle-only steps every arm adopts the oracle's weights,
+    BatchNorm buffers and Adam moments; the module shells on the fp32 kernel specification must then continue the
+    oracle's trajectory to round-off -- which also pins the Adam-state hand-over itself."""
+    with emulated_kernels():
+        c = L.run(steps=3, vol=(8, 8, 8), batch=2, n_batches=2, in_ch=4, block_setting=((4, 1, 2), (8, 1, 2), (8, 2, 2)),
+                  device="cpu", warm_start=3)
+    for k, v in L.deviations(c).items():
+        assert v["max"] < 2e-3, (k, v)
+
+
+def _assert_tracks_like_control(c, first_tol):
+    ours, ctrl = L.deviations(c, "ours"), L.deviations(c, "control")
+    for k in ours:
+        print(f"{k:12s} ours median {ours[k]['median']:.3g} smooth_max {ours[k]['smooth_max']:.3g}   "
+              f"control median {ctrl[k]['median']:.3g} smooth_max {ctrl[k]['smooth_max']:.3g}")
+    for k in ours:
+        assert ours[k]["median"] <= 1.5 * ctrl[k]["median"] + 0.03, (k, ours[k], ctrl[k])
+        assert ours[k]["smooth_max"] <= 1.5 * ctrl[k]["smooth_max"] + 0.10, (k, ours[k], ctrl[k])
+    for k in ("lossE", "loss_rec", "kl_real"):
+        assert ours[k]["first"] < first_tol, (k, ours[k])
+
+
+@pytest.mark.gpu
+def test_loss_curve_200_steps_40x48x40_warm_gpu():
+    """200 Adam steps of the headline net on 40x48x40 volumes, batch 4, continuing the fp32 oracle's state after its
+    first 20 steps (see ``warm_start`` in tests/loss_curve.py: a cold start at this size measures the chaotic step-1
+    transient, profiles/r02_ensemble_40x48x40.md).  Same criterion as the 16x24x16 test: ours no further from the fp32
+    trajectory than the oracle under torch.autocast(bfloat16)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    c = L.run(steps=200, vol=(40, 48, 40), batch=4, n_batches=4, control=True, warm_start=20)
+    _assert_tracks_like_control(c, 5e-3)
+
+
 @pytest.mark.gpu
 def test_loss_curve_200_steps_gpu():
     """200 Adam steps of the headline net on 16x24x16 volumes: ours (CUDA kernels, bf16 activations) and a control

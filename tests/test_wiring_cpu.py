@@ -253,3 +253,43 @@ def test_fc_eval_forward_matches_oracle_small_grid():
     torch.testing.assert_close(mu, mu_r, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(lv, lv_r, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(x_re, x_r, rtol=1e-4, atol=1e-5)
+
+
+def test_deferred_bn_updates_match_direct():
+    """trainer._fork_join issues the second pass of an independent pair on a side stream with its BatchNorm
+    running-statistic updates deferred (functional.deferred_bn / apply_deferred_bn).  Two passes through the same
+    layers, deferred and applied afterwards, must leave exactly the buffers that two direct passes leave
+    (running <- 0.9 running + 0.1 batch composes in call order; num_batches_tracked += 2)."""
+    torch.manual_seed(5)
+    bs = [[64, 1, 2], [64, 1, 2], [64, 2, 2]]
+    a = sivae_b200.SoftIntroVAE(64, bs)
+    a.apply(T.init_weights_he)
+    b = sivae_b200.SoftIntroVAE(64, bs)
+    b.load_state_dict(a.state_dict())
+    a.train(), b.train()
+    assert a.two_stream_ok()
+    x1, x2 = torch.rand(2, 1, 8, 8, 8), torch.rand(2, 1, 8, 8, 8) * 3.0
+    F.noise_state.eps_feed = iter([torch.zeros(2, 1, 1, 1, 1)] * 4)
+    for m in list(a.modules()) + list(b.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0                                              # the kernel specification takes explicit masks only
+    try:
+        with emulated_kernels(), torch.no_grad():
+            ra = [a.forward(x1)[3], a.forward(x2)[3]]
+            with F.deferred_bn() as log:
+                rb = [b.forward(x1)[3], b.forward(x2)[3]]
+            assert len(log) == 2 * 18                              # 18 BatchNorm layers, two passes
+            # nothing was touched while deferred
+            assert int(b.state_dict()["encoder.blocks.0.1.num_batches_tracked"]) == 0
+            F.apply_deferred_bn(log)
+    finally:
+        F.noise_state.eps_feed = None
+    for u, v in zip(ra, rb):
+        torch.testing.assert_close(u, v, rtol=0, atol=0)           # train-mode outputs do not depend on the buffers
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) and int(sa[k]) in (0, 2), k
+        elif "running" in k:
+            torch.testing.assert_close(sb[k], sa[k], rtol=2e-5, atol=1e-6, msg=k)
+    assert not sivae_b200.SoftIntroVAE(4, [[4, 1, 2], [8, 1, 2], [8, 2, 2]]).two_stream_ok()   # padded widths: no

@@ -29,19 +29,22 @@ def main():
     ap.add_argument("--rel", type=float, default=1e-6)
     ap.add_argument("--out", default=None)
     ap.add_argument("--env", nargs="*", default=[])
+    ap.add_argument("--warm-start", type=int, default=0)
     a = ap.parse_args()
     for kv in a.env:
         k_, v_ = kv.split("=", 1)
         os.environ[k_] = v_
     runs = []
     for r in range(a.replicas):
-        c = L.run(a.steps, tuple(a.vol), a.batch, 4, control=True, perturb=None if r == 0 else (1000 + r, a.rel))
+        c = L.run(a.steps, tuple(a.vol), a.batch, 4, control=True, perturb=None if r == 0 else (1000 + r, a.rel),
+                  warm_start=a.warm_start)
         runs.append(c)
         print(f"replica {r}: loss_rec@last  fp32 {c['oracle']['loss_rec'][-1]:.6g}  control {c['control']['loss_rec'][-1]:.6g}"
               f"  ours {c['ours']['loss_rec'][-1]:.6g}", flush=True)
     marks = [s for s in (0, 1, 5, 10, 25, 50, 100, 150, a.steps - 1) if s < a.steps]
     lines = [f"# Replica ensemble, {a.replicas} replicas (initial weights x (1 + {a.rel:g} N(0,1)), replica 0 unperturbed), "
-             f"{a.steps} steps, volumes {a.vol}, batch {a.batch}" + (f", env {a.env}" if a.env else ""), ""]
+             f"{a.steps} steps, volumes {a.vol}, batch {a.batch}" + (f", env {a.env}" if a.env else "")
+             + (f", warm start {a.warm_start} fp32 steps" if a.warm_start else ""), ""]
     for term in ("loss_rec", "kl_real", "lossE", "lossD"):
         lines += [f"## {term}: 10-step mean around the step, per arm: mean over replicas [min .. max]", "",
                   "| step | fp32 | control | ours |", "|---:|---|---|---|"]
