@@ -150,6 +150,73 @@ def apply_deferred_bn(records):
                 torch._foreach_add_(nbts, 1)
 
 
+# ----------------------------------------------------------------------------------------------
+# weight gradients on their own stream (SIVAE_WGRAD_STREAM=1; default off until measured)
+# ----------------------------------------------------------------------------------------------
+class _WgradSideStream:
+    """Backward's critical path is the chain  BN-backward -> dgrad -> BN-backward -> ...  (memory-bound passes alternating
+    with tensor-bound ones); the weight gradient of a layer depends only on that layer's ``dconv`` and nothing waits
+    for it until the optimiser.  Inside ``with wgrad_side_stream(device):`` the 3x3x3 weight-gradient kernels are
+    therefore issued on a second stream, where they overlap the BatchNorm passes of the layers further down, and their
+    results are accumulated THERE (several passes share a weight) and handed to ``param.grad`` when the block exits,
+    after the streams have joined.  autograd sees no gradient for those weights (``None``), so this path is not used
+    together with gradient hooks (parallel.GradReducer); parallel.FlatGradReducer's persistent ``.grad`` views work."""
+
+    def __init__(self):
+        self.active = False
+        self.streams = {}
+        self.stream = None
+        self.pending = {}       # id(param) -> [param, fp32 sum of its weight gradients (lives on the side stream)]
+        self.keep = []          # operands of in-flight kernels: freed only after the join
+
+    def launch(self, param, fn, operands):
+        cur = torch.cuda.current_stream(param.device)
+        self.stream.wait_stream(cur)                    # dconv is complete
+        with torch.cuda.stream(self.stream):
+            dw = fn()
+            ent = self.pending.get(id(param))
+            if ent is None:
+                self.pending[id(param)] = [param, dw]
+            else:
+                ent[1].add_(dw)
+        self.keep.append(operands)
+
+    def flush(self, device):
+        if not self.pending:
+            return
+        torch.cuda.current_stream(device).wait_stream(self.stream)
+        with torch.no_grad():
+            for param, buf in self.pending.values():
+                buf = buf.reshape(param.shape)
+                if param.grad is None:
+                    param.grad = buf
+                else:
+                    param.grad.add_(buf)
+        self.pending, self.keep = {}, []
+
+
+wgrad_side = _WgradSideStream()
+WGRAD_STREAM = os.environ.get("SIVAE_WGRAD_STREAM", "0") == "1"
+
+
+@contextlib.contextmanager
+def wgrad_side_stream(device, enabled=True):
+    """Wrap ``loss.backward()``: 3x3x3 weight gradients of parameters passed unpadded run on a side stream."""
+    device = torch.device(device)
+    if not (enabled and device.type == "cuda"):
+        yield
+        return
+    st = wgrad_side.streams.get(device)
+    if st is None:
+        st = wgrad_side.streams[device] = torch.cuda.Stream(device)
+    wgrad_side.stream, wgrad_side.active = st, True
+    try:
+        yield
+    finally:
+        wgrad_side.active = False
+        wgrad_side.flush(device)
+
+
 def _bn_coeffs(y, gamma, beta, bn: BnState):
     """-> (mean, invstd, scale, shift).  Train: batch statistics (+ running-stat update).  Eval: running stats."""
     if bn.training:
@@ -221,6 +288,7 @@ class _ConvBnAct(torch.autograd.Function):
             _note_bn(bn, mean, invstd, y.numel() // y.shape[-1])
             ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
             ctx.cfg = (slope, resample, bn.training, pre_up)
+            ctx.wparam = weight if isinstance(weight, torch.nn.Parameter) else None
             return out
         if bn.training:
             # convolution + batch statistics in one C-ABI call (the sums come out of the conv epilogue)
@@ -235,6 +303,7 @@ class _ConvBnAct(torch.autograd.Function):
         # x is only needed for the weight gradient: frozen-parameter passes (dgrad-only) do not keep it
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, res, mean, invstd, gamma, beta, wd)
         ctx.cfg = (slope, resample, bn.training, pre_up)
+        ctx.wparam = weight if isinstance(weight, torch.nn.Parameter) else None
         return out
 
     @staticmethod
@@ -251,7 +320,12 @@ class _ConvBnAct(torch.autograd.Function):
         if need_x:
             dx = K.upconv3_dgrad(dconv, wd) if pre_up else K.conv3_igemm(dconv, wd)
         if need_w:
-            dw = K.upconv3_wgrad(x, dconv) if pre_up else K.conv3_wgrad(x, dconv)
+            if wgrad_side.active and ctx.wparam is not None and dconv.is_cuda:
+                # on the weight-gradient stream; accumulated there and handed to .grad at the join (dw stays None here)
+                wgrad_side.launch(ctx.wparam, (lambda: K.upconv3_wgrad(x, dconv)) if pre_up
+                                  else (lambda: K.conv3_wgrad(x, dconv)), (x, dconv))
+            else:
+                dw = K.upconv3_wgrad(x, dconv) if pre_up else K.conv3_wgrad(x, dconv)
         return dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), dres, None, None, None, None
 
 

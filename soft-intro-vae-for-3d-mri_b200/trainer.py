@@ -119,6 +119,12 @@ def _fork_join(model, device, fn_a, fn_b):
     return ra, rb
 
 
+def _wgrad_stream_ok(reducer) -> bool:
+    # the side-stream weight gradients bypass autograd's accumulation: fine without a reducer and with FlatGradReducer
+    # (persistent .grad views), not with the hook-driven GradReducer
+    return F.WGRAD_STREAM and (reducer is None or getattr(reducer, "needs_persistent_grads", False))
+
+
 def _encode_sample_decode(model, x):
     mu, logvar = model.encode(x)
     z = model.reparameterize(mu, logvar)
@@ -160,7 +166,8 @@ def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional
     lossE, loss_rec, lossE_real_kl, exp_elbo_fake, exp_elbo_rec = F.intro_loss_e(
         r_real, k_real, r_fake, k_fake, r_rec, k_rec, scale, beta_rec, beta_kl, beta_neg)
     _zero_grad(optimizer_e, reducer_e)
-    lossE.backward()
+    with F.wgrad_side_stream(dev, _wgrad_stream_ok(reducer_e)):
+        lossE.backward()
     out = dict(lossE=lossE.detach(), loss_rec=loss_rec.detach(), kl_real=lossE_real_kl.detach(),
                exp_elbo_fake=exp_elbo_fake.detach(), exp_elbo_rec=exp_elbo_rec.detach())
     return out, z.detach()
@@ -187,7 +194,8 @@ def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optio
     lossD, loss_rec, rec_kl, fake_kl, loss_rec_rec, loss_fake_rec = F.intro_loss_d(
         r_real, k_rec, k_fake, r_rec_rec, r_fake_rec, scale, beta_rec, beta_kl, gamma_r)
     _zero_grad(optimizer_d, reducer_d)
-    lossD.backward()
+    with F.wgrad_side_stream(dev, _wgrad_stream_ok(reducer_d)):
+        lossD.backward()
     return dict(lossD=lossD.detach(), loss_rec_d=loss_rec.detach(), rec_kl=rec_kl.detach(), fake_kl=fake_kl.detach(),
                 loss_rec_rec_d=loss_rec_rec.detach(), loss_fake_rec_d=loss_fake_rec.detach())
 

@@ -509,7 +509,7 @@ def test_bench_config_graph_step_vs_oracle():
 # ---------------------------------------------------------------------------------------------------------------
 # two-stream issue of independent passes (trainer._fork_join, SIVAE_TWO_STREAMS)
 # ---------------------------------------------------------------------------------------------------------------
-def _one_step_terms_and_grads(two_streams: bool, graphed: bool):
+def _one_step_terms_and_grads(two_streams: bool, graphed: bool, wgrad_stream: bool = False):
     torch.manual_seed(21)
     F.manual_seed(21)
     net = sivae_b200.SoftIntroVAE(64, [[64, 1, 2], [128, 1, 2], [256, 2, 2]]).to(DEV)
@@ -519,8 +519,8 @@ def _one_step_terms_and_grads(two_streams: bool, graphed: bool):
     real = torch.rand(2, 1, 32, 48, 32, device=DEV, generator=g)
     noise = torch.randn(2, 1, 4, 6, 4, device=DEV, generator=g)
     torch.cuda.manual_seed(77)
-    old = T.TWO_STREAMS
-    T.TWO_STREAMS = two_streams
+    old, old_w = T.TWO_STREAMS, F.WGRAD_STREAM
+    T.TWO_STREAMS, F.WGRAD_STREAM = two_streams, wgrad_stream
     try:
         if graphed:
             oe, od = sivae_b200.FusedAdam(net.encoder.parameters(), lr=2e-4), sivae_b200.FusedAdam(net.decoder.parameters(), lr=2e-4)
@@ -535,7 +535,7 @@ def _one_step_terms_and_grads(two_streams: bool, graphed: bool):
             t = T.soft_intro_train_step(net, real, noise, oe, od)
             terms = {k: float(v) for k, v in t.items()}
     finally:
-        T.TWO_STREAMS = old
+        T.TWO_STREAMS, F.WGRAD_STREAM = old, old_w
     torch.cuda.synchronize()
     grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
     return terms, grads, {k: v.detach().clone() for k, v in net.state_dict().items()}
@@ -571,3 +571,23 @@ def test_two_stream_step_equals_single_stream_graphed():
             assert torch.equal(s1[k], s2[k]), k
         else:
             assert int(s1[k]) == int(s2[k]), k
+
+
+@pytest.mark.parametrize("two_streams", [False, True])
+def test_wgrad_side_stream_equals_autograd_accumulation(two_streams):
+    """functional.wgrad_side_stream: the 3x3x3 weight gradients run on their own stream and are summed there over the
+    passes that share a weight; loss terms and every gradient must be bit-identical to autograd's own accumulation
+    (same kernels, same summation order), eagerly and inside the whole-step graph, alone and combined with the
+    two-stream issue of independent passes."""
+    t1, g1, _ = _one_step_terms_and_grads(False, False)
+    t2, g2, _ = _one_step_terms_and_grads(two_streams, False, wgrad_stream=True)
+    assert t1 == t2
+    assert set(g1) == set(g2)
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+    t3, _, s3 = _one_step_terms_and_grads(False, True)
+    t4, _, s4 = _one_step_terms_and_grads(two_streams, True, wgrad_stream=True)
+    assert t3 == t4, (t3, t4)
+    for k in s3:
+        if "running" not in k and not k.endswith("num_batches_tracked"):
+            assert torch.equal(s3[k], s4[k]), k
