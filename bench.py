@@ -255,7 +255,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     K.device_check()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not args.no_clocks else None
     if sampler:
         sampler.start()                                     # early: nvidia-smi takes ~1 s to deliver its first sample
     B = args.batch
@@ -504,6 +504,7 @@ def main():
     ap.add_argument("--vol", type=int, nargs=3, default=list(VOL), metavar=("D", "H", "W"),
                     help="volume extents (headline 80 96 80; 160 192 160 = the ~5M-voxel L-shape, use --batch 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="no nvidia-smi clock sampler child (runs under ncu)")
     ap.add_argument("--no-lshape", action="store_true", help="skip the second (160x192x160, batch 2) measurement")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="fixed GLOBAL batch split over the ranks (BASELINE configs[3]: 64 -> local 32/16/8 at 2/4/8 "

@@ -1,26 +1,20 @@
 #!/bin/bash
 # Profiles for profiles/ (one GPU; each ncu pass only after the same command exited 0 without ncu):
 #   1. launch list of one eager training step (per-kernel shares, tools/launch_summary.py reads it)
-#   2. ncu --set full of the hot kernels (tools/ncu_targets.py launches each once)
-#   3. ncu --set full of the Linear-head kernels of the FC-latent variant (tools/ncu_linear.py)
+#   2. ncu --set full of the hot kernels (tools/ncu_targets.py launches each once) -> tools/ncu_summarize.py (run in the
+#      authoring container on the pulled .ncu-rep) writes profiles/<round>_ncu_hot_kernels.md + profiles/top_kernel_ncu.json
+# bench.py runs with --no-clocks here: the nvidia-smi sampler child is what made the round-1 launch-list pass hang under ncu.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-# NOTE (end of round 1): in the final state the launch-list pass below did not finish within 8 minutes (it took ~3
-# before; cause not yet investigated -- candidates: the clock sampler's nvidia-smi child now starts before the model
-# is built and ncu follows child processes; add --target-processes application-only when retrying).  Give this
-# script a generous gpurun --timeout and run it when at least 15 GPU-minutes are left.
+BENCH="python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-graph --no-clocks --no-lshape"
 echo "== ncu launch list"
-timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-graph > gpurun_out/bench_plain.log 2>&1 && \
-timeout 900 ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -s 3100 -c 1700 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-graph > gpurun_out/ncu_launch.log 2>&1
+timeout 300 $BENCH > gpurun_out/bench_plain.log 2>&1 && \
+timeout 900 ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1700 --csv --log-file gpurun_out/launches.csv \
+    $BENCH > gpurun_out/ncu_launch.log 2>&1
 echo "rc=$?"; wc -l gpurun_out/launches.csv
 echo "== ncu full, hot kernels"
 timeout 300 python tools/ncu_targets.py > gpurun_out/ncu_targets_plain.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'conv3_kd3|conv3_wgrad_kw64|upconv3_fused|upconv3_wgrad_tall|conv3_to1_halo|c1_to_c64_tc_kernel' -s 7 -c 7 \
+timeout 1500 ncu --target-processes application-only --set full --clock-control none --import-source on \
+    -k regex:'conv3_kd3|conv3_wgrad_kw64|upconv3_fused|upconv3_wgrad_tall|conv3_to1_halo|c1_to_c64_tc_kernel|conv3_igemm_kernel' -s 8 -c 8 \
     -o gpurun_out/hot -f python tools/ncu_targets.py > gpurun_out/ncu_targets.log 2>&1
 echo "rc=$?"; tail -2 gpurun_out/ncu_targets.log
-echo "== ncu full, Linear heads"
-timeout 200 python tools/ncu_linear.py && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"linear_(fwd|dgrad|wgrad)_kernel" -s 6 -c 6 \
-  -o gpurun_out/linear -f python tools/ncu_linear.py > gpurun_out/ncu_linear.log 2>&1
-echo "rc=$?"; tail -2 gpurun_out/ncu_linear.log
