@@ -240,6 +240,11 @@ int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n
  * eps == NULL -> the scalar eps_const is used (validation path, eps = 0.1). */
 int sivae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float eps_const,
                       float* z, long long n, void* stream);
+/* The sampler of the training path (models/models.py:265-266, eps = torch.randn_like(std)): eps ~ N(0,1) is drawn IN the
+ * kernel (Philox4x32-10 keyed by `seed` and the registered dropout epoch counter -> a captured graph draws fresh noise on
+ * every replay; Box-Muller), written to eps_out [n] for sivae_reparam_bwd, and z = mu + eps*exp(0.5*logvar) as above. */
+int sivae_reparam_draw_fwd(const float* mu, const float* logvar, float* eps_out, float* z, long long n,
+                           unsigned long long seed, void* stream);
 /* dmu (+)= dz ; dlogvar (+)= dz*eps*0.5*exp(0.5*logvar).  accumulate=1 adds into dmu/dlogvar. */
 int sivae_reparam_bwd(const float* dz, const float* logvar, const float* eps, float eps_const,
                       float* dmu, float* dlogvar, long long n, int accumulate, void* stream);

@@ -285,6 +285,12 @@ def reparam_fwd(mu, logvar, eps):
     return mu + eps * torch.exp(0.5 * logvar)
 
 
+def reparam_draw_fwd(mu, logvar, seed):
+    """eps ~ N(0,1) (here from torch's generator: the Philox stream itself is only checked statistically) -> (z, eps)."""
+    eps = torch.randn_like(mu)
+    return reparam_fwd(mu, logvar, eps), eps
+
+
 def reparam_bwd(dz, logvar, eps):
     return dz.clone(), dz * eps * torch.exp(0.5 * logvar) * 0.5
 

@@ -96,6 +96,7 @@ int wgrad_c1(const void*, const float*, float*, float*, float*, int, int, int, i
 int relu_drop_bwd(const float*, const float*, float*, long long, float, cudaStream_t);
 int reparam_fwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
 int reparam_bwd(const float*, const float*, const float*, float, float*, float*, long long, int, cudaStream_t);
+int reparam_draw_fwd(const float*, const float*, float*, float*, long long, unsigned long long, cudaStream_t);
 int kl_persample_fwd(const float*, const float*, float*, int, long long, cudaStream_t);
 int kl_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, int, cudaStream_t);
 size_t mse_workspace_bytes(int, long long);
@@ -265,6 +266,10 @@ int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n
 int sivae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float eps_const, float* z, long long n,
                       void* stream) {
   return reparam_fwd(mu, logvar, eps, eps_const, z, n, ST(stream));
+}
+int sivae_reparam_draw_fwd(const float* mu, const float* logvar, float* eps_out, float* z, long long n,
+                           unsigned long long seed, void* stream) {
+  return reparam_draw_fwd(mu, logvar, eps_out, z, n, seed, ST(stream));
 }
 int sivae_reparam_bwd(const float* dz, const float* logvar, const float* eps, float eps_const, float* dmu,
                       float* dlogvar, long long n, int accumulate, void* stream) {

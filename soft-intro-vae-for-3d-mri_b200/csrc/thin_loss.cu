@@ -389,6 +389,36 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __
     z[i] = __fadd_rn(mu[i], t);                               // mu + eps*std    three rounded ops, as torch)
   }
 }
+// Sampler of the reparameterisation (models/models.py:265-266: eps = torch.randn_like(std)): eps ~ N(0,1) drawn in the
+// kernel from Philox4x32-10 (one block = 4 uniforms = 2 Box-Muller pairs = 4 normals for elements 4i..4i+3), written
+// out for the backward pass, and z = mu + eps*exp(0.5*logvar) with the same three separately rounded operations.
+__global__ void reparam_draw_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                        float* __restrict__ eps_out, float* __restrict__ z, long long n,
+                                        const SeedRef sref) {
+  const unsigned long long seed = resolve_seed(sref);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const long long quads = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 0x5EED0001u, 0u), key);
+    // uniforms in (0,1): (x + 0.5) * 2^-32, so the logarithm stays finite
+    const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+    const float r0 = sqrtf(-2.f * logf(fminf(u0, 0.99999994f))), r1 = sqrtf(-2.f * logf(fminf(u2, 0.99999994f)));
+    const float e[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = q * 4 + k;
+      if (i < n) {
+        const float std = expf(__fmul_rn(0.5f, lv[i]));
+        eps_out[i] = e[k];
+        z[i] = __fadd_rn(mu[i], __fmul_rn(e[k], std));
+      }
+    }
+  }
+}
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ lv,
                                    const float* __restrict__ eps, float eps_c, float* dmu, float* dlv, long long n,
                                    int accumulate) {
@@ -578,6 +608,14 @@ int reparam_fwd(const float* mu, const float* lv, const float* eps, float eps_c,
   SIVAE_CHECK(n > 0, "reparam_fwd: empty tensor");
   reparam_fwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, eps, eps_c, z, n);
   SIVAE_LAUNCH_OK("reparam_fwd_kernel");
+  return 0;
+}
+int reparam_draw_fwd(const float* mu, const float* lv, float* eps_out, float* z, long long n, unsigned long long seed,
+                     cudaStream_t st) {
+  SIVAE_CHECK(n > 0, "reparam_draw_fwd: empty tensor");
+  SIVAE_CHECK(eps_out != nullptr, "reparam_draw_fwd: eps_out is required (the backward pass reads it)");
+  reparam_draw_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(mu, lv, eps_out, z, n, make_seed_ref(seed));
+  SIVAE_LAUNCH_OK("reparam_draw_fwd_kernel");
   return 0;
 }
 int reparam_bwd(const float* dz, const float* lv, const float* eps, float eps_c, float* dmu, float* dlv, long long n,

@@ -53,6 +53,7 @@ class _DropoutState:
     def begin_step(self, device):
         """Call once at the start of every training step (graph-capturable)."""
         self.call = 0
+        noise_state.call = 0
         device = torch.device(device)
         if device.type != "cuda":
             return
@@ -69,6 +70,8 @@ def manual_seed(seed: int):
     """Re-key the in-kernel Philox dropout streams (independent of torch's generator)."""
     dropout_state.base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     dropout_state.call = 0
+    noise_state.base_seed = (int(seed) * 0x9E3779B97F4A7C15 + 0x0E95) & 0xFFFFFFFFFFFFFFFF
+    noise_state.call = 0
     if dropout_state.epoch is not None:
         dropout_state.epoch.zero_()
 
@@ -448,7 +451,12 @@ class _Reparam(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, logvar, eps):
         mu, logvar = mu.contiguous(), logvar.contiguous()
-        z = K.reparam_fwd(mu, logvar, eps)
+        if eps is None:
+            # training path: eps ~ N(0,1) drawn inside the kernel (its Philox key = this call's seed + the device-side
+            # epoch counter), returned for the backward pass
+            z, eps = K.reparam_draw_fwd(mu, logvar, noise_state.next_seed())
+        else:
+            z = K.reparam_fwd(mu, logvar, eps)
         if isinstance(eps, torch.Tensor):
             ctx.save_for_backward(logvar, eps)
             ctx.eps_const = None
@@ -468,8 +476,9 @@ class _Reparam(torch.autograd.Function):
         return dmu, dlv, None
 
 
-def reparameterize(mu, logvar, eps):
-    """z = mu + eps*exp(0.5*logvar); eps is a tensor (train) or a python float (validation, 0.1)."""
+def reparameterize(mu, logvar, eps=None):
+    """z = mu + eps*exp(0.5*logvar); eps is a tensor (injected, parity tests), a python float (validation, 0.1) or None:
+    drawn ~ N(0,1) inside the kernel (the training path)."""
     return _Reparam.apply(mu, logvar, eps)
 
 
@@ -673,18 +682,29 @@ def add_act(a, b, slope: float):
 
 
 # ----------------------------------------------------------------------------------------------
-# reparameterisation noise: torch's generator by default (randn_like, as the reference), or an
+# reparameterisation noise: drawn inside the kernel by default (functional.manual_seed keys it), or an
 # injected sequence of eps tensors for parity tests
 # ----------------------------------------------------------------------------------------------
 class _NoiseState:
+    """``eps_feed``: optional iterator of injected eps tensors (parity tests).  Otherwise every reparameterisation call of
+    a step gets its own Philox key (base seed, call index; the kernels mix in the device-side epoch counter that
+    ``begin_step`` advances, exactly as for dropout), so a captured CUDA graph draws fresh noise on every replay."""
+
     def __init__(self):
         self.eps_feed = None
+        self.base_seed = 0x0E9500E95
+        self.call = 0
+
+    def next_seed(self) -> int:
+        self.call += 1
+        return ((self.base_seed * 0xD6E8FEB86659FD93 + self.call * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF) | 1
 
 
 noise_state = _NoiseState()
 
 
-def draw_eps(like: torch.Tensor) -> torch.Tensor:
+def draw_eps(like: torch.Tensor):
+    """-> the injected eps tensor of this call, or None (= the kernel draws it; on CPU tensors: torch.randn_like)."""
     if noise_state.eps_feed is not None:
         return next(noise_state.eps_feed).to(like.device, like.dtype).reshape(like.shape)
-    return torch.randn_like(like)
+    return None

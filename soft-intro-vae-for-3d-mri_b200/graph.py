@@ -9,7 +9,7 @@ replays it per step with a single launch.  What makes the capture valid:
   * torch allocates all intermediates from the graph's private pool, so replayed addresses (and the TMA tensor
     maps encoded from them at capture time) stay valid;
   * dropout masks are keyed by a device-side epoch counter advanced inside the graph (functional.begin_step);
-  * reparameterisation noise comes from torch's graph-safe Philox generator (``randn_like``);
+  * reparameterisation noise is drawn inside ``sivae_reparam_draw_fwd`` from Philox keyed by the same device-side counter;
   * weight re-packing (fp32 -> bf16 tap-major) is part of the captured stream, after each optimiser step.
 """
 from __future__ import annotations

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "sivae_relu_drop_bwd": (_i, [_vp, _vp, _vp, _ll, _f, _vp]),
     "sivae_reparam_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _ll, _vp]),
     "sivae_reparam_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
+    "sivae_reparam_draw_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _u64, _vp]),
     "sivae_kl_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "sivae_kl_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "sivae_mse_workspace_bytes": (_sz, [_i, _ll]),
@@ -841,6 +842,18 @@ def reparam_fwd(mu, logvar, eps):
     _check(_L().sivae_reparam_fwd(_p(mu), _p(logvar), _p(et), 0.0 if et is not None else float(eps), _p(z),
                                   mu.numel(), _stream(mu)), "sivae_reparam_fwd")
     return z
+
+
+def reparam_draw_fwd(mu, logvar, seed: int):
+    """Training-path sampler: eps ~ N(0,1) drawn in the kernel (Philox keyed by ``seed`` and the device epoch counter).
+    -> (z, eps)."""
+    _req(mu, torch.float32, "mu")
+    _req(logvar, torch.float32, "logvar")
+    assert mu.shape == logvar.shape
+    z, eps = torch.empty_like(mu), torch.empty_like(mu)
+    _check(_L().sivae_reparam_draw_fwd(_p(mu), _p(logvar), _p(eps), _p(z), mu.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                       _stream(mu)), "sivae_reparam_draw_fwd")
+    return z, eps
 
 
 def reparam_bwd(dz, logvar, eps):

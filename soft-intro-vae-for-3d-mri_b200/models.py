@@ -411,7 +411,7 @@ class SoftIntroVAE(nn.Module):
                 m.prepack()
 
     def reparameterize(self, mu, logvar, val_flag=False):
-        # train: eps ~ N(0,1) from torch's generator (randn_like); validation: the constant 0.1
+        # train: eps ~ N(0,1) drawn inside the reparameterisation kernel (or injected); validation: the constant 0.1 (Q9)
         eps = F.draw_eps(mu) if val_flag is False else 0.1
         return F.reparameterize(mu, logvar, eps)
 

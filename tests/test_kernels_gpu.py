@@ -244,6 +244,31 @@ def test_reparam_bit_exact_and_backward():
     assert_f32_close(dlv, rlv, "dlogvar", 1e-6)
 
 
+def test_reparam_sampler_statistics_and_determinism():
+    """sivae_reparam_draw_fwd: eps ~ N(0,1) drawn in the kernel (Philox + Box-Muller).  Same seed -> same draw, other seed
+    -> another; moments of 4M draws within sampling error; z obeys the bit-exact reparameterisation rule given the
+    returned eps; odd lengths (tail of the 4-element Philox block) are covered."""
+    n = 1 << 22
+    mu = torch.randn(n, device=DEV)
+    lv = torch.randn(n, device=DEV) * 0.5
+    z1, e1 = K.reparam_draw_fwd(mu, lv, 12345)
+    z2, e2 = K.reparam_draw_fwd(mu, lv, 12345)
+    z3, e3 = K.reparam_draw_fwd(mu, lv, 54321)
+    assert torch.equal(e1, e2) and torch.equal(z1, z2) and not torch.equal(e1, e3)
+    assert torch.isfinite(e1).all()
+    m, v = float(e1.mean()), float(e1.var())
+    skew, kurt = float((e1 ** 3).mean()), float((e1 ** 4).mean())
+    assert abs(m) < 3e-3 and abs(v - 1) < 5e-3 and abs(skew) < 1e-2 and abs(kurt - 3) < 3e-2, (m, v, skew, kurt)
+    assert float(e1.abs().max()) > 4.5                              # tails are there (P(|x| > 4.5) * 4M = 28)
+    assert abs(float((e1[0::4] * e1[1::4]).mean())) < 3e-3          # the two outputs of a Box-Muller pair are uncorrelated
+    assert abs(float((e1[:-1] * e1[1:]).mean())) < 3e-3
+    assert torch.equal(z1, K.reparam_fwd(mu, lv, e1))               # same three rounded operations as the injected path
+    for odd in (1, 3, 5, 1201):
+        zo, eo = K.reparam_draw_fwd(mu[:odd].contiguous(), lv[:odd].contiguous(), 777)
+        assert zo.shape == (odd,) and torch.isfinite(eo).all()
+        assert torch.equal(eo, K.reparam_draw_fwd(mu[:1201].contiguous(), lv[:1201].contiguous(), 777)[1][:odd])
+
+
 @pytest.mark.parametrize("B,n", [(8, 1200), (3, 7), (1, 9600)])
 def test_kl(B, n):
     mu, lv = torch.randn(B, n, device=DEV), torch.randn(B, n, device=DEV) * 0.5
