@@ -172,16 +172,22 @@ class _WgradSideStream:
         self.pending = {}       # id(param) -> [param, fp32 sum of its weight gradients (lives on the side stream)]
         self.keep = []          # operands of in-flight kernels: freed only after the join
 
-    def launch(self, param, fn, operands):
-        cur = torch.cuda.current_stream(param.device)
+    def launch(self, params, fn, operands):
+        """``fn()`` -> one gradient per entry of ``params`` (a Parameter, or a tuple of them), computed on the side stream."""
+        single = not isinstance(params, (tuple, list))
+        plist = [params] if single else list(params)
+        cur = torch.cuda.current_stream(plist[0].device)
         self.stream.wait_stream(cur)                    # dconv is complete
         with torch.cuda.stream(self.stream):
-            dw = fn()
-            ent = self.pending.get(id(param))
-            if ent is None:
-                self.pending[id(param)] = [param, dw]
-            else:
-                ent[1].add_(dw)
+            out = fn()
+            for param, dw in zip(plist, [out] if single else out):
+                if param is None or dw is None:
+                    continue
+                ent = self.pending.get(id(param))
+                if ent is None:
+                    self.pending[id(param)] = [param, dw]
+                else:
+                    ent[1].add_(dw.reshape(ent[1].shape))
         self.keep.append(operands)
 
     def flush(self, device):
@@ -196,6 +202,16 @@ class _WgradSideStream:
                 else:
                     param.grad.add_(buf)
         self.pending, self.keep = {}, []
+
+
+def _owning_param(t):
+    """The nn.Parameter ``t`` is, or is a plain view of (``conv.weight.reshape(C, 27)``); None for padded copies."""
+    if isinstance(t, torch.nn.Parameter):
+        return t
+    base = getattr(t, "_base", None)
+    if isinstance(base, torch.nn.Parameter) and base.numel() == t.numel():
+        return base
+    return None
 
 
 wgrad_side = _WgradSideStream()
@@ -360,6 +376,7 @@ class _StemBnAct(torch.autograd.Function):
         out = K.bn_act_fwd(y, scale, shift, None, slope, K.RESAMPLE_NONE, mask, p_eff, seed, keep_bits=bits)
         ctx.save_for_backward(x1, y, mean, invstd, gamma, beta, weight, mask, bits)
         ctx.cfg = (slope, p_eff, seed, bn.training)
+        ctx.wparams = (_owning_param(weight), _owning_param(bias))
         return out
 
     @staticmethod
@@ -374,7 +391,11 @@ class _StemBnAct(torch.autograd.Function):
                                                need_affine=bool(need_g or need_b), keep_bits=bits)
         dw = dbias = dx = None
         if need_w or need_bias:
-            dw, dbias, _ = K.wgrad_c1(dconv, x1, weight.shape[1], flip=False)
+            wp, bp = ctx.wparams
+            if wgrad_side.active and dconv.is_cuda and wp is not None and bp is not None and need_w and need_bias:
+                wgrad_side.launch((wp, bp), lambda: K.wgrad_c1(dconv, x1, weight.shape[1], flip=False)[:2], (dconv, x1))
+            else:
+                dw, dbias, _ = K.wgrad_c1(dconv, x1, weight.shape[1], flip=False)
         if need_x:
             dx = K.cn_to_c1(dconv, weight, None, flip=True, act=0)
         return (dx, dw if need_w else None, dbias if need_bias else None, dgamma if need_g else None,
@@ -397,6 +418,7 @@ class _TailReluDrop(torch.autograd.Function):
         out = K.cn_to_c1(a, weight, bias, flip=False, act=1, mask=mask, p=p_eff, seed=seed)
         ctx.save_for_backward(a, weight, out)
         ctx.p = p_eff
+        ctx.wparams = (_owning_param(weight), _owning_param(bias))
         return out
 
     @staticmethod
@@ -407,7 +429,14 @@ class _TailReluDrop(torch.autograd.Function):
         da = K.c1_to_cn(dy, weight, None, flip=True) if need_a else None
         dw = db = None
         if need_w or need_b:
-            dw, _, db = K.wgrad_c1(a, dy, weight.shape[1], flip=True)
+            wp, bp = ctx.wparams
+            if wgrad_side.active and dy.is_cuda and wp is not None and bp is not None and need_w and need_b:
+                def _tail_wgrad():
+                    dw_, _, db_ = K.wgrad_c1(a, dy, weight.shape[1], flip=True)
+                    return dw_, db_
+                wgrad_side.launch((wp, bp), _tail_wgrad, (a, dy))
+            else:
+                dw, _, db = K.wgrad_c1(a, dy, weight.shape[1], flip=True)
         return da, (dw if need_w else None), (db if need_b else None), None, None
 
 
