@@ -14,6 +14,7 @@ replays it per step with a single launch.  What makes the capture valid:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -49,6 +50,9 @@ class GraphedTrainStep:
         self.model, self.opt_e, self.opt_d, self.hp = model, optimizer_e, optimizer_d, hp or T.StepHyper()
         self.red_e, self.red_d = reducer_e, reducer_d
         self.split = reducer_e is not None or reducer_d is not None
+        # SIVAE_GRAPH_NCCL=1: capture the two all-reduces INSIDE one whole-step graph (on the update side stream, under
+        # the first decoder passes of the D phase) instead of issuing them between three graph replays
+        self.capture_nccl = self.split and os.environ.get("SIVAE_GRAPH_NCCL", "0") == "1"
         if self.split:
             for r in (reducer_e, reducer_d):
                 if r is None or not getattr(r, "needs_persistent_grads", False):
@@ -77,6 +81,13 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.out = T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp)
             self.graphs = [self.graph]
+        elif self.capture_nccl:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.out = T.soft_intro_train_step(model, self.real, self.noise, optimizer_e, optimizer_d, self.hp,
+                                                   reducer_e, reducer_d)
+            self.graphs = [self.graph]
+            self.split = False
         else:
             g0, g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g0, capture_error_mode="thread_local"):

@@ -125,6 +125,24 @@ def _wgrad_stream_ok(reducer) -> bool:
     return F.WGRAD_STREAM and (reducer is None or getattr(reducer, "needs_persistent_grads", False))
 
 
+def _run_concurrently(device, fn):
+    """Issue ``fn()`` on a dedicated side stream forked from the current one; -> a function that joins it back.
+    Used for the encoder's gradient exchange + Adam update, which nothing reads until the D phase encodes."""
+    if fn is None:
+        return lambda: None
+    if device.type != "cuda":
+        fn()
+        return lambda: None
+    cur = torch.cuda.current_stream(device)
+    st = _side_streams.get((device, "update"))
+    if st is None:
+        st = _side_streams[(device, "update")] = torch.cuda.Stream(device)
+    st.wait_stream(cur)
+    with torch.cuda.stream(st):
+        fn()
+    return lambda: torch.cuda.current_stream(device).wait_stream(st)
+
+
 def _encode_sample_decode(model, x):
     mu, logvar = model.encode(x)
     z = model.reparameterize(mu, logvar)
@@ -174,15 +192,20 @@ def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional
 
 
 def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optional[StepHyper] = None,
-                       reducer_d=None):
-    """Update-D half, utils/my_trainer.py:291-323, up to and including ``lossD.backward()``."""
+                       reducer_d=None, concurrent=None):
+    """Update-D half, utils/my_trainer.py:291-323, up to and including ``lossD.backward()``.  ``concurrent``: optional
+    callable issued on a side stream next to the first two decoder passes (they read neither encoder weights nor
+    encoder gradients: the caller passes the encoder's gradient exchange + optimiser step) and joined before the
+    first encoder pass."""
     hp = hp or StepHyper()
     scale = hp.scale if hp.scale is not None else 8.0 / float(real_batch[0].numel())
     beta_rec, beta_kl, gamma_r = hp.beta_rec, hp.beta_kl, hp.gamma_r
     _set_requires_grad(model.encoder, False)
     _set_requires_grad(model.decoder, True)
     dev = real_batch.device
+    join = _run_concurrently(dev, concurrent)
     fake, rec = _fork_join(model, dev, lambda: model.decode(noise_batch), lambda: model.decode(z.detach()))
+    join()
     (rec_mu, rec_logvar, z_rec), (fake_mu, fake_logvar, z_fake) = _fork_join(
         model, dev, lambda: _encode_sample(model, rec), lambda: _encode_sample(model, fake))
     rec_rec, rec_fake = _fork_join(model, dev, lambda: model.decode(z_rec.detach()), lambda: model.decode(z_fake.detach()))
@@ -209,10 +232,20 @@ def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer
     tensors.
     """
     out, z = soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp, reducer_e)
-    if reducer_e is not None:
-        reducer_e.finish()
-    optimizer_e.step()
-    out.update(soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp, reducer_d))
+
+    def update_e():
+        if reducer_e is not None:
+            reducer_e.finish()
+        optimizer_e.step()
+
+    if TWO_STREAMS and getattr(optimizer_e, "graph_safe", False) and real_batch.device.type == "cuda":
+        # the exchange + Adam(E) (which rewrites the encoder's weight packs in its own kernel) run under decode(noise) /
+        # decode(z) of the D phase (my_trainer.py:297-298).  Only with FusedAdam: a torch optimiser bumps the version
+        # counters on the host, and the re-pack kernels that triggers would race with its update kernels.
+        out.update(soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp, reducer_d, concurrent=update_e))
+    else:
+        update_e()
+        out.update(soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp, reducer_d))
     if reducer_d is not None:
         reducer_d.finish()
     optimizer_d.step()
