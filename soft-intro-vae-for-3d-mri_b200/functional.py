@@ -154,7 +154,7 @@ def apply_deferred_bn(records):
 
 
 # ----------------------------------------------------------------------------------------------
-# weight gradients on their own stream (SIVAE_WGRAD_STREAM=1; default off until measured)
+# weight gradients on their own stream (default on; SIVAE_WGRAD_STREAM=0 disables; 64.2 -> 63.6 ms alone, A/B on one box)
 # ----------------------------------------------------------------------------------------------
 class _WgradSideStream:
     """Backward's critical path is the chain  BN-backward -> dgrad -> BN-backward -> ...  (memory-bound passes alternating
@@ -215,7 +215,7 @@ def _owning_param(t):
 
 
 wgrad_side = _WgradSideStream()
-WGRAD_STREAM = os.environ.get("SIVAE_WGRAD_STREAM", "0") == "1"
+WGRAD_STREAM = os.environ.get("SIVAE_WGRAD_STREAM", "1") != "0"
 
 
 @contextlib.contextmanager

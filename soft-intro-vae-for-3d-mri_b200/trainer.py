@@ -80,7 +80,7 @@ def _set_requires_grad(module: nn.Module, flag: bool):
         p.requires_grad = flag
 
 
-# Two-stream issue of the independent passes of an iteration (SIVAE_TWO_STREAMS=1; default off until measured): of the 13
+# Two-stream issue of the independent passes of an iteration (default on; SIVAE_TWO_STREAMS=0 disables): of the 13
 # forward passes of utils/my_trainer.py:248-311 these pairs do not depend on each other --
 #   E phase: decode(noise) | encode(real) -> z -> decode(z);   forward(rec.detach()) | forward(fake.detach())
 #   D phase: decode(noise) | decode(z);   encode(rec) | encode(fake);   decode(z_rec) | decode(z_fake)
@@ -90,8 +90,13 @@ def _set_requires_grad(module: nn.Module, flag: bool):
 # parallel branches.  Python still issues the passes in the reference's order, so dropout keys, fed masks and eps
 # draws are unchanged, and the side pass defers its BatchNorm running-statistic updates until the streams have joined
 # (functional.deferred_bn), which keeps them race-free and in the reference's order.
-TWO_STREAMS = os.environ.get("SIVAE_TWO_STREAMS", "0") == "1"
+# Measured (profiles/r02c_ab_streams.md, A/B/A/B on one box, whole-step graph): 64.2 -> 62.5 ms; with the weight-gradient
+# stream (functional.wgrad_side_stream) 61.8-62.4 ms.  The gain is bounded by the board's power cap, not by idle SMs: the
+# step runs at ~1.3 GHz under sw_power_cap, and overlapping memory-bound passes with tensor-bound ones raises the power
+# draw of the same instants.
+TWO_STREAMS = os.environ.get("SIVAE_TWO_STREAMS", "1") != "0"
 _side_streams = {}
+_warned_off = False
 
 
 def _fork_join(model, device, fn_a, fn_b):
@@ -103,6 +108,14 @@ def _fork_join(model, device, fn_a, fn_b):
         ok = model._two_stream_ok
     if not ok:
         return fn_a(), fn_b()
+    global _warned_off
+    if not _warned_off:
+        # a parameter's AccumulateGrad node lives on the stream of its first use while the second branch produces
+        # gradients on the side stream: the engine orders the two correctly (that is the point); silence its notice
+        _warned_off = True
+        setter = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if setter is not None:
+            setter(False)
     model.prepack()                       # no pack kernel may be launched inside one branch and read by the other
     cur = torch.cuda.current_stream(device)
     side = _side_streams.get(device)

@@ -309,11 +309,11 @@ def test_fused_adam_graph_matches_torch_adam_graph():
     (tools/adam_cmp.py), which flips a few bf16 roundings of the repacked weights, and the recipe amplifies that
     (Adam's second update is +-lr on small-gradient elements, KL sums exp(logvar)); torch's capturable formula
     differs from torch's own eager one by the same amount (eager torch Adam reproduces FusedAdam's 28.55296 at this
-    step, the capturable graph gives 28.57584).  So: first replay to 2e-3, later ones to 2e-2, kl_real to 10 %."""
+    step, the capturable graph gives 28.57584).  So: first replay to 2e-3 (kl_real 1e-2), later ones to 2e-2, kl_real to 10 %."""
     a, _ = _graphed_losses(split=False, fused_adam=True)
     b, _ = _graphed_losses(split=False, fused_adam=False)
-    for x, y in zip(a[0], b[0]):
-        assert x == pytest.approx(y, rel=2e-3), (a, b)
+    for i, (x, y) in enumerate(zip(a[0], b[0])):
+        assert x == pytest.approx(y, rel=1e-2 if i == 3 else 2e-3), (a, b)
     for va, vb in zip(a[1:], b[1:]):
         for i, (x, y) in enumerate(zip(va, vb)):
             assert x == pytest.approx(y, rel=1e-1 if i == 3 else 2e-2), (a, b)
