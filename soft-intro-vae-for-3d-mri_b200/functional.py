@@ -353,6 +353,31 @@ def conv_bn_act(x, weight, gamma, beta, res, bn: BnState, slope: float, resample
     return _ConvBnAct.apply(x, weight, gamma, beta, res, bn, slope, resample, pre_up)
 
 
+class _Conv3(torch.autograd.Function):
+    """Plain 3x3x3 convolution (no BatchNorm): y = conv3(x, weight).  Only used for the 1x1 projection shortcut of a
+    stride-1 block that changes its channel count (models/models.py:28-43), which runs as the centre tap of a 3x3x3
+    kernel -- no shipped block_setting takes that path, so it reuses the validated kernels instead of
+    getting one of its own."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        wf, wd = _packed(weight, False)
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, wd)
+        return K.conv3_igemm(x, wf)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wd = ctx.saved_tensors
+        g = g.contiguous()
+        dx = K.conv3_igemm(g, wd) if ctx.needs_input_grad[0] else None
+        dw = K.conv3_wgrad(x, g) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def conv3(x, weight):
+    return _Conv3.apply(x, weight)
+
+
 class _StemBnAct(torch.autograd.Function):
     """x1 fp32 [N,D,H,W] -> NDHWC [N,D,H,W,C]; weight fp32 [C,T] (T = 27 or 1), bias [C]."""
 

@@ -150,8 +150,15 @@ class BuildingBlock(nn.Module):
         if self.res and not isinstance(self.shortcut, nn.Module):
             res = x
         elif self.res:
-            raise NotImplementedError("stride-1 block with a channel change: the reference would run the 1x1 "
-                                      "projection here, which no shipped block_setting does (SURVEY Q1)")
+            # stride-1 block that changes its channel count: the reference runs the 1x1 projection conv here
+            # (models/models.py:32-35,39-41).  No shipped block_setting does, so the projection reuses the
+            # 3x3x3 kernels with its weight as the centre tap (27x its FLOPs) and adds the bias in torch.
+            sc = self.shortcut
+            w1 = _pad_dim(_pad_dim(sc.weight, 0, _cpad(sc.out_channels)), 1, _cpad(sc.in_channels))
+            w3 = TF.pad(w1, (1, 1, 1, 1, 1, 1))
+            res = F.conv3(x, w3)
+            if sc.bias is not None:
+                res = res + _pad_dim(sc.bias, 0, _cpad(sc.out_channels)).to(res.dtype)
         else:
             res = None
         # AvgPool3d(2) is fused behind the first convolution's BN/activation; Upsample(2) is folded into the

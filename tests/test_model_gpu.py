@@ -619,3 +619,31 @@ def test_wgrad_side_stream_equals_autograd_accumulation(two_streams):
     for k in s3:
         if "running" not in k and not k.endswith("num_batches_tracked"):
             assert torch.equal(s3[k], s4[k]), k
+
+
+def test_stride1_block_with_projection_shortcut_gpu():
+    """BuildingBlock(64 -> 128, stride 1) on the CUDA path: the 1x1 projection shortcut of the reference
+    (models/models.py:28-43; unused by every shipped block_setting) vs the same block in torch fp32."""
+    import torch.nn.functional as TF
+    from sivae_b200.models import BuildingBlock
+    torch.manual_seed(9)
+    blk = BuildingBlock(64, 128, 1).to(DEV).train()
+    x = torch.randn(2, 8, 12, 10, 64, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    out = blk(x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    ps = {k: p.detach().clone().requires_grad_(True) for k, p in blk.named_parameters()}
+    xc = xr.permute(0, 4, 1, 2, 3)
+    h = TF.conv3d(xc, ps["block.0.weight"], None, 1, 1)
+    h = TF.leaky_relu(TF.batch_norm(h, None, None, ps["block.1.weight"], ps["block.1.bias"], True, 0.1, 1e-5), 0.2)
+    h = TF.conv3d(h, ps["block.4.weight"], None, 1, 1)
+    h = TF.batch_norm(h, None, None, ps["block.5.weight"], ps["block.5.bias"], True, 0.1, 1e-5)
+    ref = TF.leaky_relu(h + TF.conv3d(xc, ps["shortcut.weight"], ps["shortcut.bias"]), 0.2).permute(0, 2, 3, 4, 1)
+    ref.backward(g.float())
+    assert _cos(out, ref) > 0.9995
+    assert _cos(x.grad, xr.grad) > 0.999
+    for k, p in blk.named_parameters():
+        assert (p.grad is None) == (ps[k].grad is None), k
+        if p.grad is not None and p.numel() >= 16:
+            assert _cos(p.grad, ps[k].grad) > 0.995, (k, _cos(p.grad, ps[k].grad))

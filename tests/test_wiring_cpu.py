@@ -293,3 +293,41 @@ def test_deferred_bn_updates_match_direct():
         elif "running" in k:
             torch.testing.assert_close(sb[k], sa[k], rtol=2e-5, atol=1e-6, msg=k)
     assert not sivae_b200.SoftIntroVAE(4, [[4, 1, 2], [8, 1, 2], [8, 2, 2]]).two_stream_ok()   # padded widths: no
+
+
+def test_stride1_block_with_channel_change_runs_the_projection_shortcut():
+    """BuildingBlock(in != out, stride 1): the reference adds the 1x1 projection conv of the input to the block output
+    (models/models.py:28-43).  No shipped block_setting builds such a block, but a drop-in must not refuse
+    it: forward and every gradient against the same block written with torch.nn.functional."""
+    import torch.nn.functional as TF
+    from sivae_b200.models import BuildingBlock
+    torch.manual_seed(9)
+    blk = BuildingBlock(64, 128, 1)
+    blk.train()
+    with torch.no_grad():
+        for bn in (blk.block[1], blk.block[5]):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.2)
+    x = torch.randn(2, 4, 6, 5, 64)                                  # NDHWC
+    x.requires_grad_(True)
+    with emulated_kernels():
+        out = blk(x)
+        g = torch.randn_like(out)
+        out.backward(g)
+    got = {k: p.grad.clone() for k, p in blk.named_parameters() if p.grad is not None}
+    gx = x.grad.clone()
+    # the same block in torch
+    xr = x.detach().clone().requires_grad_(True)
+    ps = {k: p.detach().clone().requires_grad_(True) for k, p in blk.named_parameters()}
+    xc = xr.permute(0, 4, 1, 2, 3)
+    h = TF.conv3d(xc, ps["block.0.weight"], None, 1, 1)
+    h = TF.leaky_relu(TF.batch_norm(h, None, None, ps["block.1.weight"], ps["block.1.bias"], True, 0.1, 1e-5), 0.2)
+    h = TF.conv3d(h, ps["block.4.weight"], None, 1, 1)
+    h = TF.batch_norm(h, None, None, ps["block.5.weight"], ps["block.5.bias"], True, 0.1, 1e-5)
+    ref = TF.leaky_relu(h + TF.conv3d(xc, ps["shortcut.weight"], ps["shortcut.bias"]), 0.2).permute(0, 2, 3, 4, 1)
+    ref.backward(g)
+    torch.testing.assert_close(out.detach(), ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gx, xr.grad, rtol=1e-3, atol=1e-4)
+    assert set(got) == {k for k, p in ps.items() if p.grad is not None}
+    for k, v in got.items():
+        torch.testing.assert_close(v, ps[k].grad, rtol=2e-3, atol=1e-3 * float(ps[k].grad.abs().max()) + 1e-6, msg=k)
