@@ -490,6 +490,8 @@ def run_ours(args):
                                           f"torch-CPU/oneDNN on {threads} threads ({dt:.1f} s)"}
     print(json.dumps(line), flush=True)
     if world > 1:
+        graphed = None                      # graphs (and any collectives captured in them) go before the process group
+        torch.cuda.synchronize()
         dist.destroy_process_group()
     return 0
 
