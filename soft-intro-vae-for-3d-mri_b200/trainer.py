@@ -99,9 +99,11 @@ _side_streams = {}
 _warned_off = False
 
 
-def _fork_join(model, device, fn_a, fn_b):
-    """-> (fn_a(), fn_b()), with fn_b on a side stream when two-stream issue is on and the model allows it."""
-    ok = TWO_STREAMS and device.type == "cuda" and hasattr(model, "two_stream_ok")
+def _fork_join(model, device, fn_a, fn_b, allow=True):
+    """-> (fn_a(), fn_b()), with fn_b on a side stream when two-stream issue is on and the model allows it.  ``allow`` is
+    False with the hook-driven parallel.GradReducer: its buckets are filled from gradient hooks on whichever stream
+    the last gradient of a bucket arrives, which must then be the only one."""
+    ok = allow and TWO_STREAMS and device.type == "cuda" and hasattr(model, "two_stream_ok")
     if ok:
         if not hasattr(model, "_two_stream_ok"):
             model._two_stream_ok = bool(model.two_stream_ok())
@@ -132,10 +134,15 @@ def _fork_join(model, device, fn_a, fn_b):
     return ra, rb
 
 
+def _streams_ok(reducer) -> bool:
+    """Side streams in forward / backward are compatible with no reducer and with FlatGradReducer (persistent .grad
+    views, one exchange after backward), not with the hook-driven GradReducer."""
+    return reducer is None or getattr(reducer, "needs_persistent_grads", False)
+
+
 def _wgrad_stream_ok(reducer) -> bool:
-    # the side-stream weight gradients bypass autograd's accumulation: fine without a reducer and with FlatGradReducer
-    # (persistent .grad views), not with the hook-driven GradReducer
-    return F.WGRAD_STREAM and (reducer is None or getattr(reducer, "needs_persistent_grads", False))
+    # the side-stream weight gradients bypass autograd's accumulation (and with it the gradient hooks)
+    return F.WGRAD_STREAM and _streams_ok(reducer)
 
 
 def _run_concurrently(device, fn):
@@ -183,10 +190,11 @@ def soft_intro_phase_e(model, real_batch, noise_batch, optimizer_e, hp: Optional
     _set_requires_grad(model.encoder, True)
     _set_requires_grad(model.decoder, False)
     dev = real_batch.device
+    ok = _streams_ok(reducer_e)
     fake, (real_mu, real_logvar, z, rec) = _fork_join(
-        model, dev, lambda: model.decode(noise_batch), lambda: _encode_sample_decode(model, real_batch))
+        model, dev, lambda: model.decode(noise_batch), lambda: _encode_sample_decode(model, real_batch), ok)
     (rec_mu, rec_logvar, z_rec, rec_rec), (fake_mu, fake_logvar, z_fake, rec_fake) = _fork_join(
-        model, dev, lambda: model.forward(rec.detach()), lambda: model.forward(fake.detach()))
+        model, dev, lambda: model.forward(rec.detach()), lambda: model.forward(fake.detach()), ok)
     # per-sample vectors (the mse / kl kernels), then the whole :260-284 assembly in one fused kernel
     r_real = F.mse_persample(real_batch, rec)
     k_real = F.kl_persample(real_mu, real_logvar)
@@ -216,12 +224,14 @@ def soft_intro_phase_d(model, real_batch, noise_batch, z, optimizer_d, hp: Optio
     _set_requires_grad(model.encoder, False)
     _set_requires_grad(model.decoder, True)
     dev = real_batch.device
+    ok = _streams_ok(reducer_d)
     join = _run_concurrently(dev, concurrent)
-    fake, rec = _fork_join(model, dev, lambda: model.decode(noise_batch), lambda: model.decode(z.detach()))
+    fake, rec = _fork_join(model, dev, lambda: model.decode(noise_batch), lambda: model.decode(z.detach()), ok)
     join()
     (rec_mu, rec_logvar, z_rec), (fake_mu, fake_logvar, z_fake) = _fork_join(
-        model, dev, lambda: _encode_sample(model, rec), lambda: _encode_sample(model, fake))
-    rec_rec, rec_fake = _fork_join(model, dev, lambda: model.decode(z_rec.detach()), lambda: model.decode(z_fake.detach()))
+        model, dev, lambda: _encode_sample(model, rec), lambda: _encode_sample(model, fake), ok)
+    rec_rec, rec_fake = _fork_join(model, dev, lambda: model.decode(z_rec.detach()), lambda: model.decode(z_fake.detach()),
+                                   ok)
     r_real = F.mse_persample(real_batch, rec)
     r_rec_rec = F.mse_persample(rec.detach(), rec_rec)
     r_fake_rec = F.mse_persample(fake.detach(), rec_fake)
@@ -251,7 +261,8 @@ def soft_intro_train_step(model, real_batch, noise_batch, optimizer_e, optimizer
             reducer_e.finish()
         optimizer_e.step()
 
-    if TWO_STREAMS and getattr(optimizer_e, "graph_safe", False) and real_batch.device.type == "cuda":
+    if (TWO_STREAMS and getattr(optimizer_e, "graph_safe", False) and real_batch.device.type == "cuda"
+            and _streams_ok(reducer_e) and _streams_ok(reducer_d)):
         # the exchange + Adam(E) (which rewrites the encoder's weight packs in its own kernel) run under decode(noise) /
         # decode(z) of the D phase (my_trainer.py:297-298).  Only with FusedAdam: a torch optimiser bumps the version
         # counters on the host, and the re-pack kernels that triggers would race with its update kernels.
