@@ -364,10 +364,17 @@ def run_ours(args):
     if graphed is not None:
         # a replayed graph cannot carry per-kernel events: time the dominant kernels live in one eager step of
         # the same process on the same inputs (CUDA events on the launch stream), and count its launches
+        # ... on ONE stream: with the default two-stream issue a kernel's event bracket would also contain whatever the
+        # other stream ran meanwhile, and the roofline figure is about the kernel alone
         n0 = K.launch_count()
-        with K.KernelTimer() as kt:
-            step_eager()
-            torch.cuda.synchronize()
+        saved_streams = (T.TWO_STREAMS, F.WGRAD_STREAM)
+        T.TWO_STREAMS, F.WGRAD_STREAM = False, False
+        try:
+            with K.KernelTimer() as kt:
+                step_eager()
+                torch.cuda.synchronize()
+        finally:
+            T.TWO_STREAMS, F.WGRAD_STREAM = saved_streams
         launches = (K.launch_count() - n0) * args.steps
     ksum = kt.summary()
     if rank == 0 and args.kernel_table:
@@ -450,6 +457,8 @@ def run_ours(args):
                        "local_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set is tens of GB >> 126 MB L2 (inputs larger than L2)",
                        "gflop_per_volume_step": gflop_step, "cuda_graph": graphed is not None,
+                       "streams": {"independent_passes_on_two_streams": bool(T.TWO_STREAMS),
+                                   "weight_gradients_on_own_stream": bool(F.WGRAD_STREAM)},
                        "cuda_graph_note": graph_note},
             "clocks": clocks, "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": real_host.numel() * 4 + noise_host.numel() * 4,
