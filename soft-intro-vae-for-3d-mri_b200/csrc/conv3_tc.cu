@@ -2187,18 +2187,16 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
   if (threadIdx.x < 64) bias_s[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
   if (EPI != 0 && threadIdx.x >= 64 && threadIdx.x < 128) {
     const int c = threadIdx.x - 64;
-    // one 16-byte record {S, T, P, Q} per channel: a single broadcast LDS.128 per element in the epilogue (four
-    // LDS.32 made the shared-memory pipe, which the A-tile builders also live on, the bottleneck of the kernel)
     const float mu = __ldg(bn.mean + c), is = __ldg(bn.invstd + c), S = __ldg(bn.gamma + c) * is;
-    cst_s[4 * c] = S;
-    cst_s[4 * c + 1] = __ldg(bn.beta + c) - mu * S;
+    cst_s[c] = S;
+    cst_s[64 + c] = __ldg(bn.beta + c) - mu * S;
     if (EPI == 1) {
-      cst_s[4 * c + 2] = is;
-      cst_s[4 * c + 3] = -mu * is;
+      cst_s[128 + c] = is;
+      cst_s[192 + c] = -mu * is;
     } else {
       const float c1 = __ldg(bn.coef + c), c2 = __ldg(bn.coef + 64 + c);
-      cst_s[4 * c + 2] = -S * is * c2;
-      cst_s[4 * c + 3] = S * (mu * is * c2 - c1);
+      cst_s[128 + c] = -S * is * c2;
+      cst_s[192 + c] = S * (mu * is * c2 - c1);
     }
   }
   tc_fence_before();
@@ -2350,10 +2348,10 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int cl = c8 * 8 + e;                    // channel within the half
-              const float4 kc = lds128_f32(cst + (uint32_t)(hf * 32 + cl) * 16u);
+              const uint32_t ca = cst + (uint32_t)(hf * 32 + cl) * 4u;
               const float2 yy = unpack_bf16x2(yw[e >> 1]);
               const float yv = (e & 1) ? yy.y : yy.x;
-              const float S = kc.x, T = kc.y, P = kc.z, Q = kc.w;
+              const float S = lds_f32(ca), T = lds_f32(ca + 256u), P = lds_f32(ca + 512u), Q = lds_f32(ca + 768u);
               const float g = __uint_as_float(v[cl]);
               const float t = fmaf(yv, S, T);
               const float d = valid ? (t > 0.f ? g : g * slope) : 0.f;

@@ -239,7 +239,7 @@ def test_tail_dgrad_bn_bwd_fused(shape):
     mean, invstd, _, _ = S.bn_train_coeffs(y, gamma, beta, None, None, None, 0.1, 1e-5)
     got = K.tail_dgrad_bn_bwd(dy1, wt, y, mean, invstd, gamma, beta, 0.2)
     exp = S.tail_dgrad_bn_bwd(dy1, wt, y, mean, invstd, gamma, beta, 0.2)
-    slack = 0.02 * float(exp[0].float().abs().mean()) + 1e-5     # (1,1,1,1): dconv is 0 up to rounding on both sides
+    slack = 0.02 * float(exp[0].float().abs().mean()) + 1e-6
     assert_bf16_close(got[0], exp[0], "dconv", slack=slack)
     assert_f32_close(got[1], exp[1], "dgamma", 2e-3)
     assert_f32_close(got[2], exp[2], "dbeta", 2e-3)

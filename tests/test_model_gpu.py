@@ -669,7 +669,7 @@ def test_fused_decoder_end_matches_unfused():
             assert _cos(g0[k], g1[k]) > 0.9999, (k, _cos(g0[k], g1[k]))
     t2, _, s2 = run(False, True)
     t3, _, s3 = run(True, True)
-    for a, b in zip(t2, t3):                         # the eager warm-up step already trained with its own backward
+    assert t2[0] == t3[0]                            # first replay: same weights -> same forward
+    for a, b in zip(t2[1:], t3[1:]):
         for k in a:
-            if "exp_elbo" not in k:
-                assert a[k] == pytest.approx(b[k], rel=5e-2), (k, a[k], b[k])
+            assert a[k] == pytest.approx(b[k], rel=5e-2), (k, a[k], b[k])
