@@ -229,19 +229,6 @@ int sivae_wgrad_c64(const void* xc_bf16, const float* x1, float* dw, float* sum_
 /* backward of ReLU+Dropout on the decoder output: dy[i] = out[i] > 0 ? g[i]/(1-p) : 0 */
 int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n, float p, void* stream);
 
-/* Decoder end, backward (models/models.py:60 BatchNorm3d + LeakyReLU in front of :137 Conv3d(64,1,3)): the gradient
- * entering the BatchNorm is g = conv3^T(dy1; w) of the ONE-channel tail gradient dy1, so it is recomputed on tensor cores
- * in a reduce pass and an apply pass instead of being written and read twice:
- *   dconv = gamma*invstd*(dt - mean(dt) - xhat*mean(dt*xhat)),  dt = g * act'(BN(y)),  dgamma = sum(dt*xhat), dbeta = sum(dt)
- * = sivae_c1_to_cn(dy1, w, flip = 1) followed by sivae_bn_act_bwd(resample = none, no residual, no dropout), without the
- * 64-channel g.  dy1 fp32 [N][D][H][W]; w fp32 [64][27] (the tail weight as it lies in memory); y, dconv bf16
- * [N][D][H][W][64]; mean, invstd, gamma, beta fp32 [64]; dgamma, dbeta fp32 [64] or NULL.  C = 64 only. */
-size_t sivae_tail_dgrad_bn_bwd_workspace_bytes(void);
-int sivae_tail_dgrad_bn_bwd(const float* dy1, const float* w, const void* y_bf16, const float* mean, const float* invstd,
-                            const float* gamma, const float* beta, float slope, void* dconv_bf16, float* dgamma,
-                            float* dbeta, int N, int D, int H, int W, void* workspace, size_t workspace_bytes,
-                            void* stream);
-
 /* ------------------------------------------------------------------------------------------------
  * Latent / loss kernels (fp32, coalesced float4 + warp-shuffle reductions)
  *   reparameterize           models/models.py:263-271

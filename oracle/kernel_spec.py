@@ -285,21 +285,6 @@ def reparam_fwd(mu, logvar, eps):
     return mu + eps * torch.exp(0.5 * logvar)
 
 
-def tail_dgrad_bn_bwd(dy1, w, y, mean, invstd, gamma, beta, slope, need_affine=True):
-    """BatchNorm(train)+activation backward of g = conv3^T(dy1; w) (the tail convolution's input gradient), g kept in fp32."""
-    w5, k = _w5(w, True)
-    g = F.conv3d(dy1.float().unsqueeze(1), w5.unsqueeze(1), None, 1, k // 2).permute(0, 2, 3, 4, 1)
-    c = y.shape[-1]
-    xh = (y.float() - mean) * invstd
-    t = xh * gamma + beta
-    dt = g * torch.where(t > 0, torch.ones_like(t), torch.full_like(t, slope))
-    n = y.numel() // c
-    s1 = dt.reshape(-1, c).sum(0)
-    s2 = (dt * xh).reshape(-1, c).sum(0)
-    dconv = gamma * invstd * (dt - s1 / n - xh * (s2 / n))
-    return dconv.to(y.dtype), (s2 if need_affine else None), (s1 if need_affine else None)
-
-
 def reparam_draw_fwd(mu, logvar, seed):
     """eps ~ N(0,1) (here from torch's generator: the Philox stream itself is only checked statistically) -> (z, eps)."""
     eps = torch.randn_like(mu)

@@ -97,9 +97,6 @@ int relu_drop_bwd(const float*, const float*, float*, long long, float, cudaStre
 int reparam_fwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
 int reparam_bwd(const float*, const float*, const float*, float, float*, float*, long long, int, cudaStream_t);
 int reparam_draw_fwd(const float*, const float*, float*, float*, long long, unsigned long long, cudaStream_t);
-size_t tail_dgrad_bn_bwd_workspace_bytes();
-int tail_dgrad_bn_bwd(const float*, const float*, const void*, const float*, const float*, const float*, const float*, float,
-                      void*, float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 int kl_persample_fwd(const float*, const float*, float*, int, long long, cudaStream_t);
 int kl_persample_bwd(const float*, const float*, const float*, float*, float*, int, long long, int, cudaStream_t);
 size_t mse_workspace_bytes(int, long long);
@@ -269,13 +266,6 @@ int sivae_relu_drop_bwd(const float* g, const float* out, float* dy, long long n
 int sivae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float eps_const, float* z, long long n,
                       void* stream) {
   return reparam_fwd(mu, logvar, eps, eps_const, z, n, ST(stream));
-}
-size_t sivae_tail_dgrad_bn_bwd_workspace_bytes(void) { return tail_dgrad_bn_bwd_workspace_bytes(); }
-int sivae_tail_dgrad_bn_bwd(const float* dy1, const float* w, const void* y, const float* mean, const float* invstd,
-                            const float* gamma, const float* beta, float slope, void* dconv, float* dgamma, float* dbeta,
-                            int N, int D, int H, int W, void* ws, size_t ws_bytes, void* stream) {
-  return tail_dgrad_bn_bwd(dy1, w, y, mean, invstd, gamma, beta, slope, dconv, dgamma, dbeta, N, D, H, W, ws, ws_bytes,
-                           ST(stream));
 }
 int sivae_reparam_draw_fwd(const float* mu, const float* logvar, float* eps_out, float* z, long long n,
                            unsigned long long seed, void* stream) {

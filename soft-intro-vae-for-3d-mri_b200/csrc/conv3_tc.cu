@@ -2111,55 +2111,19 @@ __global__ void pack_to1_halo_weights_kernel(const float* __restrict__ w, int fl
 static constexpr int kC1ABytes = 2 * kTileBytes;          // two 64-wide K blocks of the 128-row A tile
 static constexpr int kC1BBytes = 2 * 64 * 128;            // [2 K blocks][64 channels][64]
 static constexpr int kC1Halo = (kHRows + 3) & ~3;         // floats per staged halo
-static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + kTileBytes + 2 * kC1Halo * 4 + 64 * 4 + 4 * 64 * 4 + 1024 + 256;
+static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + kTileBytes + 2 * kC1Halo * 4 + 64 * 4 + 1024 + 256;
 
-// EPI 1 / 2: train-mode BatchNorm backward fused behind the convolution.  The convolution output g[v][c] is then the
-// gradient arriving at LeakyReLU(BatchNorm(y)) -- decoder tail: g = conv3^T(dy) of the one-channel dy, i.e. this kernel
-// with flipped taps -- and is never written:
-//   dt = g * act'(y*S + T)            S = gamma*invstd, T = beta - mean*S           (models/models.py:60,137)
-//   EPI 1 (reduce): per-channel sums of dt and dt*xhat, xhat = y*invstd - mean*invstd, as partial rows for
-//                   bn_bwd_finalize (blk = CTA*4 + epilogue warp)
-//   EPI 2 (apply) : dconv = S*dt + y*U + V, U = -S*invstd*c2, V = S*(mean*invstd*c2 - c1), c1/c2 = the finalized means
-// y is read straight from global memory (128 contiguous bytes per voxel row); HBM traffic of the two passes: 2 reads of y
-// + 1 write of dconv, instead of write g + 2 x (read g, read y) + write dconv.
-struct C1BnBwd {
-  const __nv_bfloat16* y;
-  const float* mean;
-  const float* invstd;
-  const float* gamma;
-  const float* beta;
-  const float* coef;     // EPI 2: [2][64]
-  float slope;
-};
-
-// sum over the 32 lanes of v[l], delivered to lane l (31 shuffles; the array is consumed)
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool up = (lane & half) != 0;
-#pragma unroll
-    for (int k = 0; k < half; ++k) {
-      const float send = up ? v[k] : v[k + half];
-      const float keep = up ? v[k + half] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return v[0];
-}
-
-template <int EPI>
 __global__ void __launch_bounds__(288, 2)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
-                    int tiles_w, int tiles_h, int items, float* __restrict__ stats_partial, const C1BnBwd bn) {
+                    int tiles_w, int tiles_h, int items, float* __restrict__ stats_partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + 2 * kC1ABytes;
   uint8_t* smem_o = smem_b + kC1BBytes;
   float* xs = reinterpret_cast<float*>(smem_o + kTileBytes);       // [2][kC1Halo]
   float* bias_s = xs + 2 * kC1Halo;                                // [64]
-  float* cst_s = bias_s + 64;                                      // [4][64] per-channel constants of EPI 1 / 2
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(cst_s + 4 * 64);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint64_t* a_empty = a_full + 2;
   uint64_t* acc_full = a_empty + 2;
   uint64_t* acc_empty = acc_full + 2;
@@ -2185,20 +2149,6 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     tmem_alloc(tmem_ptr_smem, 128);
   }
   if (threadIdx.x < 64) bias_s[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
-  if (EPI != 0 && threadIdx.x >= 64 && threadIdx.x < 128) {
-    const int c = threadIdx.x - 64;
-    const float mu = __ldg(bn.mean + c), is = __ldg(bn.invstd + c), S = __ldg(bn.gamma + c) * is;
-    cst_s[c] = S;
-    cst_s[64 + c] = __ldg(bn.beta + c) - mu * S;
-    if (EPI == 1) {
-      cst_s[128 + c] = is;
-      cst_s[192 + c] = -mu * is;
-    } else {
-      const float c1 = __ldg(bn.coef + c), c2 = __ldg(bn.coef + 64 + c);
-      cst_s[128 + c] = -S * is * c2;
-      cst_s[192 + c] = S * (mu * is * c2 - c1);
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -2304,93 +2254,6 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     const uint32_t bias_addr = smem_u32(bias_s);
     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     uint32_t it = 0;
-    if constexpr (EPI != 0) {
-      // ===== BatchNorm backward behind the convolution (see C1BnBwd) =====
-      const uint32_t cst = smem_u32(cst_s);
-      const int ow = row % kHW, oh = row / kHW;
-      const float slope = bn.slope;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        int w0, h0, d0; long long n;
-        decode(item, w0, h0, d0, n);
-        const uint32_t s = it & 1;
-        const bool valid = (w0 + ow < W) && (h0 + oh < H);
-        const __nv_bfloat16* yrow = bn.y + ((((long long)n * D + d0) * H + (h0 + oh)) * W + (w0 + ow)) * 64;
-        uint4 ya[4], yb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                       // this row's 128 bytes of y: in flight while the MMAs finish
-          ya[j] = valid ? __ldg(reinterpret_cast<const uint4*>(yrow) + j) : make_uint4(0u, 0u, 0u, 0u);
-          yb[j] = valid ? __ldg(reinterpret_cast<const uint4*>(yrow) + 4 + j) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        mbar_wait(&acc_full[s], (it >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64u;
-        if (EPI == 2) {
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
-        const uint32_t tile_row = smem_u32(smem_o) + (uint32_t)row * 128u;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(hf * 32), v);
-          tmem_ld_wait();
-          if (hf == 1) {                                    // both halves are in registers: the accumulator stage is free
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[s]);
-          }
-          float dt[32], dx[32];
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const uint4 yr = hf == 0 ? ya[c8] : yb[c8];
-            const uint32_t yw[4] = {yr.x, yr.y, yr.z, yr.w};
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int cl = c8 * 8 + e;                    // channel within the half
-              const uint32_t ca = cst + (uint32_t)(hf * 32 + cl) * 4u;
-              const float2 yy = unpack_bf16x2(yw[e >> 1]);
-              const float yv = (e & 1) ? yy.y : yy.x;
-              const float S = lds_f32(ca), T = lds_f32(ca + 256u), P = lds_f32(ca + 512u), Q = lds_f32(ca + 768u);
-              const float g = __uint_as_float(v[cl]);
-              const float t = fmaf(yv, S, T);
-              const float d = valid ? (t > 0.f ? g : g * slope) : 0.f;
-              if (EPI == 1) {
-                dt[cl] = d;
-                dx[cl] = d * fmaf(yv, P, Q);                // xhat = y*invstd - mean*invstd
-              } else {
-                o[e] = fmaf(S, d, fmaf(yv, P, Q));          // dconv = S*dt + y*U + V
-              }
-            }
-            if (EPI == 2) {
-              uint4 pk;
-              pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-              pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-              sts128(tile_row + ((uint32_t)((hf * 4 + c8) ^ (row & 7)) << 4), pk);
-            }
-          }
-          if (EPI == 1) {
-            const float a = warp_transpose_sum32(dt, lane), b = warp_transpose_sum32(dx, lane);
-            if (hf == 0) { s1a += a; s2a += b; } else { s1b += a; s2b += b; }
-          }
-        }
-        if (EPI == 2) {
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (issuer) {
-            tma_store_5d(&tmC, smem_o, 0, w0, h0, d0, (int)n);
-            tma_store_commit();
-          }
-        }
-      }
-      if (EPI == 1) {
-        // partial[(blk * 2 + {0: sum dt, 1: sum dt*xhat}) * 64 + c]: lane l holds channel l (s*a) and 32 + l (s*b)
-        float* dst = stats_partial + (size_t)(blockIdx.x * 4 + (warp_id - 5)) * 2 * 64;
-        dst[lane] = s1a; dst[32 + lane] = s1b;
-        dst[64 + lane] = s2a; dst[96 + lane] = s2b;
-      }
-      if (EPI == 2 && issuer) tma_store_wait_read_all();
-    } else {
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       int w0, h0, d0; long long n;
       decode(item, w0, h0, d0, n);
@@ -2441,7 +2304,6 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
       *reinterpret_cast<float2*>(dst + 64 + 2 * lane) = make_float2(s2a, s2b);
     }
     if (issuer) tma_store_wait_read_all();
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -2485,78 +2347,18 @@ static int c1_to_c64_tc_impl(const float* x1, const float* w, const float* bias,
   SIVAE_CHECK(items < (1ll << 31), "c1_to_c64: too many tiles");
   static bool attr_set = false;
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
+    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
                    "cudaFuncSetAttribute(c1_to_c64_tc)"))
       return -1;
     attr_set = true;
   }
-  // two persistent CTAs per SM (103 KB of shared memory, 288 threads x <= 112 registers, 128 TMEM columns each): every
+  // two persistent CTAs per SM (102 KB of shared memory, 288 threads x <= 112 registers, 128 TMEM columns each): every
   // role is a single warp per scheduler, so a second CTA is what hides the LDS / ALU latencies of the builders
   const long long cap = 2ll * num_sms();
   const unsigned ctas = (unsigned)(items < cap ? items : cap);
-  c1_to_c64_tc_kernel<0><<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats,
-                                                      C1BnBwd{});
+  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
   if (stats != nullptr && stats_blocks != nullptr) *stats_blocks = (int)ctas * 4;
-  return 0;
-}
-
-int bn_bwd_finalize(const float* partial, int nblocks, int C, long long nvox, float* coef, float* dgamma, float* dbeta,
-                    cudaStream_t st);
-
-// workspace of tail_dgrad_bn_bwd: weight pack | partial sums (2 x 148 CTAs x 4 warps x 2 x 64) | coef [2][64]
-static constexpr size_t kTailBnPartialFloats = (size_t)2 * 148 * 4 * 2 * 64;
-size_t tail_dgrad_bn_bwd_workspace_bytes() {
-  return c1_to_c64_workspace_bytes() + (kTailBnPartialFloats + 128) * sizeof(float);
-}
-
-// dconv = BatchNorm3d(train)+LeakyReLU backward of g = conv3^T(dy1; w) -- the input gradient of the decoder tail
-// Conv3d(64,1,3) (models/models.py:137) pushed through the activation and BatchNorm in front of it (models.py:60) without
-// materialising g: pass 1 (EPI 1) reduces, bn_bwd_finalize, pass 2 (EPI 2) applies.  dy1 fp32 [N][D][H][W]; w fp32 [64][27]
-// (the tail weight; taps are flipped here); y bf16 NDHWC (the raw convolution output BatchNorm normalised); dconv bf16
-// NDHWC; dgamma / dbeta fp32 [64] (may be NULL).
-int tail_dgrad_bn_bwd(const float* dy1, const float* w, const void* y, const float* mean, const float* invstd,
-                      const float* gamma, const float* beta, float slope, void* dconv, float* dgamma, float* dbeta, int N,
-                      int D, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {
-  SIVAE_CHECK(ws && ws_bytes >= tail_dgrad_bn_bwd_workspace_bytes(), "tail_dgrad_bn_bwd: workspace too small");
-  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "tail_dgrad_bn_bwd: empty tensor");
-  SIVAE_CHECK(num_sms() <= 148, "tail_dgrad_bn_bwd: partial-sum workspace sized for <= 148 SMs");
-  __nv_bfloat16* wp = (__nv_bfloat16*)ws;
-  float* partial = (float*)((uint8_t*)ws + c1_to_c64_workspace_bytes());
-  float* coef = partial + kTailBnPartialFloats;
-  pack_c1_to_c64_weights_kernel<<<32, 256, 0, st>>>(w, 1, wp);
-  SIVAE_LAUNCH_OK("pack_c1_to_c64_weights_kernel");
-  CUtensorMap tmB, tmC;
-  {
-    uint64_t dims[3] = {64, 64, 2};
-    uint64_t strides[2] = {128, 64 * 128};
-    uint32_t box[3] = {64, 64, 1};
-    if (make_tmap_bf16(&tmB, wp, 3, dims, strides, box)) return -1;
-  }
-  if (make_act_tmap(&tmC, dconv, N, D, H, W, 64, kHW, kHH, 1)) return -1;
-  const int tiles_w = cdiv(W, kHW), tiles_h = cdiv(H, kHH);
-  const long long items = (long long)tiles_w * tiles_h * D * N;
-  SIVAE_CHECK(items < (1ll << 31), "tail_dgrad_bn_bwd: too many tiles");
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
-                   "cudaFuncSetAttribute(c1_to_c64_tc<1>)") ||
-        check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
-                   "cudaFuncSetAttribute(c1_to_c64_tc<2>)"))
-      return -1;
-    attr_set = true;
-  }
-  const long long cap = 2ll * num_sms();
-  const unsigned ctas = (unsigned)(items < cap ? items : cap);
-  const long long nvox = (long long)N * D * H * W;
-  C1BnBwd bn{(const __nv_bfloat16*)y, mean, invstd, gamma, beta, coef, slope};
-  c1_to_c64_tc_kernel<1><<<ctas, 288, kC1Smem, st>>>(dy1, tmB, tmC, nullptr, N, D, H, W, tiles_w, tiles_h, (int)items,
-                                                      partial, bn);
-  SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel<1>");
-  if (int rc = bn_bwd_finalize(partial, (int)ctas * 4, 64, nvox, coef, dgamma, dbeta, st)) return rc;
-  c1_to_c64_tc_kernel<2><<<ctas, 288, kC1Smem, st>>>(dy1, tmB, tmC, nullptr, N, D, H, W, tiles_w, tiles_h, (int)items,
-                                                      nullptr, bn);
-  SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel<2>");
   return 0;
 }
 

@@ -1226,15 +1226,6 @@ int bn_act_bwd(const void* g, const void* y, const void* res, const float* mean,
   return 0;
 }
 
-// finalize of a BatchNorm-backward reduction whose partial rows were produced elsewhere (conv3_tc.cu: tail_dgrad_bn_bwd)
-int bn_bwd_finalize(const float* partial, int nblocks, int C, long long nvox, float* coef, float* dgamma, float* dbeta,
-                    cudaStream_t st) {
-  SIVAE_CHECK(channels_ok(C) && nblocks > 0 && nvox > 0, "bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<cdiv(C, 8), kFinThreads, 0, st>>>(partial, nblocks, C, nvox, coef, dgamma, dbeta);
-  SIVAE_LAUNCH_OK("bn_bwd_finalize_kernel");
-  return 0;
-}
-
 int ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, long long vox, cudaStream_t st) {
   const long long total = (long long)N * C * vox;
   SIVAE_CHECK(total > 0, "layout: empty tensor");

@@ -353,73 +353,6 @@ def conv_bn_act(x, weight, gamma, beta, res, bn: BnState, slope: float, resample
     return _ConvBnAct.apply(x, weight, gamma, beta, res, bn, slope, resample, pre_up)
 
 
-class _ConvBnActTail(torch.autograd.Function):
-    """Decoder end as ONE autograd node: [Upsample ->] Conv3d(C,64,3) -> BatchNorm3d -> LeakyReLU (second unit of the last
-    UpsampleBuildingkBlock, models/models.py:58-60,78-79) followed by the tail Conv3d(64,1,3) -> ReLU -> Dropout
-    (models/models.py:137-140).  The forward pass runs the same kernels as ``conv_bn_act`` + ``tail_relu_drop``; the point is
-    the backward pass: the gradient entering the BatchNorm is a 27-tap function of the one-channel tail gradient, so
-    ``sivae_tail_dgrad_bn_bwd`` recomputes it on tensor cores inside the BatchNorm-backward reduce and apply passes
-    instead of writing a 64-channel tensor and reading it twice (1.9 GB instead of 3.8 GB per pass at batch 8)."""
-
-    @staticmethod
-    def forward(ctx, x, weight, gamma, beta, w_tail, b_tail, bn: BnState, slope: float, pre_up: bool, p_tail: float):
-        wf, wd = _packed(weight, pre_up)
-        conv_bn = K.upconv3_fprop_bn if pre_up else K.conv3_igemm_bn
-        y, mean, invstd, scale, shift = conv_bn(x, wf, gamma, beta, bn.running_mean, bn.running_var,
-                                                bn.num_batches_tracked, bn.momentum, bn.eps)
-        _note_bn(bn, mean, invstd, y.numel() // y.shape[-1])
-        a = K.bn_act_fwd(y, scale, shift, None, slope, K.RESAMPLE_NONE)
-        mask, seed = (None, 0)
-        if p_tail > 0.0:
-            mask, seed = dropout_state.next()
-        out = K.cn_to_c1(a, w_tail, b_tail, flip=False, act=1, mask=mask, p=p_tail, seed=seed)
-        tail_grads = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
-        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, y, mean, invstd, gamma, beta, wd,
-                              a if tail_grads else None, w_tail, out)
-        ctx.cfg = (slope, pre_up, p_tail)
-        ctx.wparam = weight if isinstance(weight, torch.nn.Parameter) else None
-        ctx.tparams = (_owning_param(w_tail), _owning_param(b_tail))
-        return out
-
-    @staticmethod
-    def backward(ctx, g_out):
-        x, y, mean, invstd, gamma, beta, wd, a, w_tail, out = ctx.saved_tensors
-        slope, pre_up, p_tail = ctx.cfg
-        need_x, need_w, need_g, need_b, need_wt, need_bt = ctx.needs_input_grad[:6]
-        dy = K.relu_drop_bwd(g_out.contiguous(), out, p_tail)
-        dwt = dbt = None
-        if need_wt or need_bt:
-            wp, bp = ctx.tparams
-            if wgrad_side.active and dy.is_cuda and wp is not None and bp is not None and need_wt and need_bt:
-                def _tail_wgrad():
-                    dw_, _, db_ = K.wgrad_c1(a, dy, w_tail.shape[1], flip=True)
-                    return dw_, db_
-                wgrad_side.launch((wp, bp), _tail_wgrad, (a, dy))
-            else:
-                dwt, _, dbt = K.wgrad_c1(a, dy, w_tail.shape[1], flip=True)
-        dconv, dgamma, dbeta = K.tail_dgrad_bn_bwd(dy, w_tail, y, mean, invstd, gamma, beta, slope,
-                                                   need_affine=bool(need_g or need_b))
-        dx = dw = None
-        if need_x:
-            dx = K.upconv3_dgrad(dconv, wd) if pre_up else K.conv3_igemm(dconv, wd)
-        if need_w:
-            if wgrad_side.active and ctx.wparam is not None and dconv.is_cuda:
-                wgrad_side.launch(ctx.wparam, (lambda: K.upconv3_wgrad(x, dconv)) if pre_up
-                                  else (lambda: K.conv3_wgrad(x, dconv)), (x, dconv))
-            else:
-                dw = K.upconv3_wgrad(x, dconv) if pre_up else K.conv3_wgrad(x, dconv)
-        return (dx, dw, (dgamma if need_g else None), (dbeta if need_b else None), (dwt if need_wt else None),
-                (dbt if need_bt else None), None, None, None, None)
-
-
-# default off until validated on hardware (SIVAE_FUSE_TAIL=1 enables)
-FUSE_TAIL = os.environ.get("SIVAE_FUSE_TAIL", "0") == "1"
-
-
-def conv_bn_act_tail(x, weight, gamma, beta, w_tail, b_tail, bn: BnState, slope: float, pre_up: bool, p_tail: float):
-    return _ConvBnActTail.apply(x, weight, gamma, beta, w_tail, b_tail, bn, slope, pre_up, p_tail)
-
-
 class _Conv3(torch.autograd.Function):
     """Plain 3x3x3 convolution (no BatchNorm): y = conv3(x, weight).  Only used for the 1x1 projection shortcut of a
     stride-1 block that changes its channel count (models/models.py:28-43), which runs as the centre tap of a 3x3x3

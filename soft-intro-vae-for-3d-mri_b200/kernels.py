@@ -69,8 +69,6 @@ _SIGNATURES = {
     "sivae_reparam_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _ll, _vp]),
     "sivae_reparam_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
     "sivae_reparam_draw_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _u64, _vp]),
-    "sivae_tail_dgrad_bn_bwd_workspace_bytes": (_sz, []),
-    "sivae_tail_dgrad_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_kl_persample_fwd": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "sivae_kl_persample_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "sivae_mse_workspace_bytes": (_sz, [_i, _ll]),
@@ -820,25 +818,6 @@ def wgrad_c1(xc, x1, taps: int, flip: bool = False):
     _check(lib.sivae_wgrad_c1(_p(xc), _p(x1), _p(dw), _p(sum_c), _p(sum_1), n, d, h, ww, c, taps, int(flip), _p(ws),
                               ws.numel(), _stream(xc)), "sivae_wgrad_c1")
     return dw, sum_c, sum_1
-
-
-def tail_dgrad_bn_bwd(dy1, w, y, mean, invstd, gamma, beta, slope: float, need_affine: bool = True):
-    """BatchNorm(train)+activation backward of the tail convolution's input gradient without materialising it:
-    == bn_act_bwd(c1_to_cn(dy1, w, None, flip=True), y, None, mean, invstd, gamma, beta, slope, RESAMPLE_NONE).
-    dy1 fp32 [N,D,H,W], w fp32 [64,27], y bf16 NDHWC (C = 64).  -> (dconv bf16 like y, dgamma or None, dbeta or None)."""
-    _req(dy1, torch.float32, "dy1")
-    _req(w, torch.float32, "w")
-    _req(y, torch.bfloat16, "y")
-    n, d, h, ww, c = y.shape
-    assert c == 64 and tuple(w.shape) == (64, 27) and tuple(dy1.shape) == (n, d, h, ww)
-    lib = _L()
-    ws = _workspace(y.device, lib.sivae_tail_dgrad_bn_bwd_workspace_bytes(), "tail_bn")
-    dconv = torch.empty_like(y)
-    aff = torch.empty(2, c, dtype=torch.float32, device=y.device) if need_affine else None
-    _check(lib.sivae_tail_dgrad_bn_bwd(_p(dy1), _p(w), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, _p(dconv),
-                                       _p(aff[0]) if need_affine else None, _p(aff[1]) if need_affine else None,
-                                       n, d, h, ww, _p(ws), ws.numel(), _stream(y)), "sivae_tail_dgrad_bn_bwd")
-    return dconv, (aff[0] if need_affine else None), (aff[1] if need_affine else None)
 
 
 def relu_drop_bwd(g, out, p: float):

@@ -161,15 +161,12 @@ class BuildingBlock(nn.Module):
                 res = res + _pad_dim(sc.bias, 0, _cpad(sc.out_channels)).to(res.dtype)
         else:
             res = None
-        a = self.first_unit(x)
+        # AvgPool3d(2) is fused behind the first convolution's BN/activation; Upsample(2) is folded into the
+        # second convolution itself (never materialised)
+        mode = K.RESAMPLE_AVGPOOL2 if (self.stride == 2 and not self._upsample) else K.RESAMPLE_NONE
+        a = _fused_conv_bn_act(x, self.block[0], self.block[1], None, self.slope, mode)
         return _fused_conv_bn_act(a, self.block[4], self.block[5], res, self.slope, K.RESAMPLE_NONE,
                                   pre_up=(self.stride == 2 and self._upsample))
-
-    def first_unit(self, x):
-        """conv3 -> BN -> act (-> AvgPool): AvgPool3d(2) is fused behind the first convolution's BN/activation; Upsample(2)
-        is folded into the second convolution itself (never materialised)."""
-        mode = K.RESAMPLE_AVGPOOL2 if (self.stride == 2 and not self._upsample) else K.RESAMPLE_NONE
-        return _fused_conv_bn_act(x, self.block[0], self.block[1], None, self.slope, mode)
 
 
 class UpsampleBuildingkBlock(BuildingBlock):
@@ -289,28 +286,13 @@ class ResNetDecoder(nn.Module):
         h = F.stem_bn_act(z1, _pad_dim(conv.weight.reshape(c, 1), 0, cp), _pad_dim(conv.bias, 0, cp), gamma, beta,
                           b.state(), self._slope, p)
         b.commit()
+        for blk in mods[1:-1]:
+            h = blk[0](h)
         tconv = tail[0]
         ci = tconv.in_channels
         p_tail = tail[2].p if len(tail) > 2 else 0.0
         training = tail[2].training if len(tail) > 2 else False
-        w_tail = _pad_dim(tconv.weight.reshape(ci, 27), 0, _cpad(ci))
-        last = mods[-2][0] if len(mods) > 2 else None
-        fuse = (F.FUSE_TAIL and last is not None and not last.res and last.block[5].training and self.training
-                and _cpad(last.block[4].out_channels) == 64 and _cpad(ci) == 64)
-        for blk in mods[1:-1]:
-            if fuse and blk[0] is last:
-                break
-            h = blk[0](h)
-        if fuse:
-            # decoder end as one autograd node (functional._ConvBnActTail): same forward kernels, fused backward
-            a = last.first_unit(h)
-            b = _BnBinding(last.block[5])
-            gamma, beta = b.params()
-            out = F.conv_bn_act_tail(a, _conv3_weight(last.block[4]), gamma, beta, w_tail, tconv.bias, b.state(), last.slope,
-                                     last.stride == 2 and last._upsample, p_tail if training else 0.0)
-            b.commit()
-            return out.unsqueeze(1)
-        out = F.tail_relu_drop(h, w_tail, tconv.bias, p_tail, training)
+        out = F.tail_relu_drop(h, _pad_dim(tconv.weight.reshape(ci, 27), 0, _cpad(ci)), tconv.bias, p_tail, training)
         return out.unsqueeze(1)
 
 

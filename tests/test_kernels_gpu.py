@@ -226,32 +226,6 @@ def test_wgrad_c1(C, T, flip):
         assert_f32_close(g, r, n, 1e-4)
 
 
-@pytest.mark.parametrize("shape", [(1, 4, 8, 16), (2, 5, 19, 13), (1, 1, 1, 1), (2, 3, 16, 32), (1, 6, 40, 24)])
-def test_tail_dgrad_bn_bwd_fused(shape):
-    """sivae_tail_dgrad_bn_bwd (BatchNorm + LeakyReLU backward of the tail convolution's input gradient, recomputed on
-    tensor cores in the reduce and apply passes) vs its specification, and vs the two-call path it replaces
-    (c1_to_cn(flip) -> bn_act_bwd; that one rounds the 64-channel gradient to bf16 in between)."""
-    n, d, h, w = shape
-    y = bf(n, d, h, w, 64)
-    dy1 = torch.randn(n, d, h, w, device=DEV)
-    wt = torch.randn(64, 27, device=DEV) * 0.2
-    gamma, beta = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV) * 0.3
-    mean, invstd, _, _ = S.bn_train_coeffs(y, gamma, beta, None, None, None, 0.1, 1e-5)
-    got = K.tail_dgrad_bn_bwd(dy1, wt, y, mean, invstd, gamma, beta, 0.2)
-    exp = S.tail_dgrad_bn_bwd(dy1, wt, y, mean, invstd, gamma, beta, 0.2)
-    slack = 0.02 * float(exp[0].float().abs().mean()) + 1e-6
-    assert_bf16_close(got[0], exp[0], "dconv", slack=slack)
-    assert_f32_close(got[1], exp[1], "dgamma", 2e-3)
-    assert_f32_close(got[2], exp[2], "dbeta", 2e-3)
-    g64 = K.c1_to_cn(dy1, wt, None, flip=True)
-    old = K.bn_act_bwd(g64, y, None, mean, invstd, gamma, beta, 0.2, 0)
-    assert_bf16_close(got[0], old[0], "dconv vs unfused", rel=2 ** -6, slack=2 * slack)
-    assert_f32_close(got[1], old[2], "dgamma vs unfused", 1e-2)
-    assert_f32_close(got[2], old[3], "dbeta vs unfused", 1e-2)
-    none = K.tail_dgrad_bn_bwd(dy1, wt, y, mean, invstd, gamma, beta, 0.2, need_affine=False)
-    assert none[1] is None and none[2] is None and torch.equal(none[0], got[0])
-
-
 def test_relu_drop_bwd():
     g, out = torch.randn(1000, device=DEV), torch.relu(torch.randn(1000, device=DEV))
     assert torch.equal(K.relu_drop_bwd(g, out, 0.35), S.relu_drop_bwd(g, out, 0.35))

@@ -647,29 +647,3 @@ def test_stride1_block_with_projection_shortcut_gpu():
         assert (p.grad is None) == (ps[k].grad is None), k
         if p.grad is not None and p.numel() >= 16:
             assert _cos(p.grad, ps[k].grad) > 0.995, (k, _cos(p.grad, ps[k].grad))
-
-
-def test_fused_decoder_end_matches_unfused():
-    """functional._ConvBnActTail (SIVAE_FUSE_TAIL): same forward kernels -> identical loss terms; the backward keeps the
-    tail convolution's 64-channel input gradient in fp32 instead of rounding it to bf16 -> gradients agree to bf16
-    rounding (cosine > 0.9999 per parameter), eagerly and through the whole-step graph."""
-    def run(fuse, graphed):
-        old = F.FUSE_TAIL
-        F.FUSE_TAIL = fuse
-        try:
-            return _one_step_terms_and_grads(True, graphed, wgrad_stream=True)
-        finally:
-            F.FUSE_TAIL = old
-    t0, g0, _ = run(False, False)
-    t1, g1, _ = run(True, False)
-    assert t0 == t1, (t0, t1)                       # forward is unchanged
-    assert set(g0) == set(g1)
-    for k in g0:
-        if g0[k].numel() >= 16 and not k.endswith("blocks.0.0.bias") and k != "decoder.blocks.0.0.weight":
-            assert _cos(g0[k], g1[k]) > 0.9999, (k, _cos(g0[k], g1[k]))
-    t2, _, s2 = run(False, True)
-    t3, _, s3 = run(True, True)
-    assert t2[0] == t3[0]                            # first replay: same weights -> same forward
-    for a, b in zip(t2[1:], t3[1:]):
-        for k in a:
-            assert a[k] == pytest.approx(b[k], rel=5e-2), (k, a[k], b[k])

@@ -76,11 +76,7 @@ def test_eval_forward_matches_golden(golden_dir):
         torch.testing.assert_close(a, g["eval"][b], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("fuse_tail", [False, True])
-def test_soft_intro_step_matches_golden(golden_dir, fuse_tail, monkeypatch):
-    """``fuse_tail``: the decoder end as one autograd node (functional._ConvBnActTail: the BatchNorm backward behind the
-    tail convolution's input gradient through sivae_tail_dgrad_bn_bwd) must reproduce the same golden step."""
-    monkeypatch.setattr(F, "FUSE_TAIL", fuse_tail)
+def test_soft_intro_step_matches_golden(golden_dir):
     g = _load(golden_dir, "sivae_small.pt")
     st = g["step"]
     net = sivae_b200.SoftIntroVAE(g["in_ch"], g["block_setting"])
