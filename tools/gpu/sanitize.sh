@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: this GPU pool refuses compute-sanitizer ("closed on this pool": runs under it have left GPUs needing a reset), so this
+# script has not produced a log here; tests/test_guard_bands_gpu.py and tools/determinism_probe.py stand in for it.
 # compute-sanitizer over the small-shape kernel parity tests: memcheck on every kernel family, racecheck
 # on the hand-rolled mbarrier / TMA / TMEM pipelines.  Each pass under its own timeout (the tools slow kernels 10-100x);
 # summaries go to gpurun_out/sanitize_*.log -> profiles/.

@@ -1,5 +1,6 @@
 #!/bin/bash
-# 2 GPUs: NCCL equivalence test, N=1 vs N=2 bench (three graphs + NCCL between replays vs NCCL captured in one graph)
+# 2 GPUs (gpurun --gpus 2 -- bash tools/gpu/two_gpu.sh): NCCL equivalence test, N=1 vs N=2 bench (three graphs + NCCL between
+# replays vs NCCL captured in one graph), --global-batch 64
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
