@@ -368,18 +368,6 @@ int sivae_flat_to_ndhwc(const float* src, void* dst, int B, int S, int C, int Cp
 int sivae_add_act_fwd(const void* a, const void* b, void* out, long long n, float slope, void* stream);
 int sivae_add_act_bwd(const void* g, const void* out, void* dz, long long n, float slope, void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * sivae_conv3_igemm with a caller-owned workspace: for shapes whose voxel tiles x N blocks give at most 40 CTAs (the
- * 5x6x5 layers of the FC-latent variant, models/mymodel.py:95-117) the 27 taps are split over up to 9 CTAs per tile, the
- * fp32 partial accumulators go to the workspace and a reduce kernel writes the bf16 output; every other shape, or a
- * workspace smaller than sivae_conv3_igemm_splitk_workspace_bytes(...) (0 = no split for this shape), runs
- * sivae_conv3_igemm unchanged.  Same operands and result as sivae_conv3_igemm (nn.Conv3d k=3 p=1 forward / data
- * gradient, models/models.py:17,21,55,59).  SIVAE_SPLITK=0 / force: never / every shape that fits.
- * ---------------------------------------------------------------------------------------------- */
-size_t sivae_conv3_igemm_splitk_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
-int sivae_conv3_igemm_ws(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout,
-                         void* workspace, size_t workspace_bytes, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

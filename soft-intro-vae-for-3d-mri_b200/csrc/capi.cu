@@ -118,8 +118,6 @@ int preprocess_clip_minmax(const float*, float*, int, long long, float, float*, 
 int affine_resample(const float*, float*, int, int, int, int, const float*, const float*, const float*, cudaStream_t);
 int upconv3_fprop_bn(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*, float*,
                      float*, long long*, float, float, float*, float*, float*, float*, void*, size_t, cudaStream_t);
-size_t conv3_igemm_splitk_workspace_bytes(int, int, int, int, int, int);
-int conv3_igemm_ws(const void*, const void*, void*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t linear_workspace_bytes(int, int, int);
 int linear_fwd(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 int linear_dgrad(const float*, const float*, float*, int, int, int, void*, size_t, cudaStream_t);
@@ -299,13 +297,6 @@ int sivae_c1_to_c64_bn(const float* x1, const float* w, const float* bias, void*
                        size_t ws_pack_bytes, void* ws_bn, size_t ws_bn_bytes, void* stream) {
   return c1_to_c64_bn(x1, w, bias, y, N, D, H, W, flip, gamma, beta, rm, rv, nbt, momentum, eps, mean, invstd, scale, shift,
                       ws_pack, ws_pack_bytes, ws_bn, ws_bn_bytes, ST(stream));
-}
-size_t sivae_conv3_igemm_splitk_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
-  return conv3_igemm_splitk_workspace_bytes(N, D, H, W, Cin, Cout);
-}
-int sivae_conv3_igemm_ws(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout, void* ws,
-                         size_t ws_bytes, void* stream) {
-  return conv3_igemm_ws(x, wpack, y, N, D, H, W, Cin, Cout, ws, ws_bytes, ST(stream));
 }
 size_t sivae_linear_workspace_bytes(int B, int K, int J) { return linear_workspace_bytes(B, K, J); }
 int sivae_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int J, int act, void* ws,

@@ -2924,213 +2924,4 @@ int pack_conv3_weights(const float* w, int Cout, int Cin, void* wf, void* wd, cu
   return 0;
 }
 
-// =================================================================================================
-// Split-K variant of the tap-by-tap fprop / dgrad kernel for grids that leave most of the GPU idle.
-//
-// A convolution whose voxel tiles x N blocks give only a handful of CTAs runs as that many serial chains of 27 taps x
-// Cin/64 K steps: the 5 x 6 x 5 layers of the FC-latent variant (models/mymodel.py, batch 4: 5 tiles, 10 CTAs, 108 K
-// steps = 34 us at 62 TFLOP/s).  Measured: for grids of >= 80 CTAs (the headline net's 10 x 12 x 10 layers at batch 8,
-// 160 CTAs) splitting is SLOWER -- the fp32 partials and the reduce launch cost more than the halved chain
-// (profiles/r02a_ab_splitk_keepbits.md) -- so the plan below only splits grids of at most kSplitKMaxCtas CTAs
-// (SIVAE_SPLITK=0 never, =force every shape that fits: the parity tests use both).
-// Here blockIdx.z = split s takes the taps [s*27/S, (s+1)*27/S) of a
-// tile, writes its fp32 accumulator to partial[s][tile][row][Cout] and a small kernel sums the S partials, converts to
-// bf16 and scatters the rows of the (wt x ht x dt) voxel box to the NDHWC output (rows beyond the box or the volume
-// are dropped), exactly as the weight-gradient kernels reduce their K splits.
-// =================================================================================================
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192)
-conv3_igemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const ConvGeom g, const int ksplits, float* __restrict__ partial, const int ld,
-                          const long long tiles) {
-  constexpr int B_BYTES = BLOCK_N * 128;
-  constexpr int STAGE_BYTES = kTileBytes + B_BYTES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp_id = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  int w0, h0, d0, n;
-  decode_tile(g, blockIdx.x, w0, h0, d0, n);
-  const int nb = blockIdx.y;
-  const int split = blockIdx.z;
-  const int tap_lo = split * 27 / ksplits, tap_hi = (split + 1) * 27 / ksplits;   // ksplits <= 27: never empty
-  const int num_kb = (tap_hi - tap_lo) * g.cin_blocks;
-
-  if (warp_id == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp_id == 1) tmem_alloc(tmem_ptr_smem, BLOCK_N);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp_id == 0) {
-    // ===== TMA producer =====
-    if (elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)g.rows * 128u + (uint32_t)B_BYTES;
-      uint32_t s = 0, ph = 0;
-      for (int tap = tap_lo; tap < tap_hi; ++tap) {
-        const int od = tap / 9 - 1, oh = (tap / 3) % 3 - 1, ow = tap % 3 - 1;
-        for (int cb = 0; cb < g.cin_blocks; ++cb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], tx_bytes);
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
-          tma_load_5d(a_dst, &tmA, &full_bar[s], cb * 64, w0 + ow, h0 + oh, d0 + od, n);
-          tma_load_3d(a_dst + kTileBytes, &tmB, &full_bar[s], cb * 64, nb * BLOCK_N, tap);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp_id == 1) {
-    // ===== MMA issuer (one elected thread) =====
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-      const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, 1024);
-      uint32_t s = 0, ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint64_t adesc = desc0 + (uint64_t)(s * (uint32_t)(STAGE_BYTES >> 4));
-        const uint64_t bdesc = adesc + (uint64_t)(kTileBytes >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else {
-    // ===== epilogue: TMEM -> fp32 partial rows (every row of the tile is written; the reduce kernel drops the padding) =====
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp_id & 3;
-    const int row = q * 32 + lane;
-    float* dst = partial + (((size_t)split * (size_t)tiles + blockIdx.x) * 128 + row) * (size_t)ld + (size_t)nb * BLOCK_N;
-#pragma unroll 1
-    for (int j = 0; j < BLOCK_N / 32; ++j) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(dst + j * 32 + c * 4) = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp_id == 1) tmem_dealloc(tmem_base, BLOCK_N);
-}
-
-// y[vox][c] = bf16( sum_s partial[s][tile][row][c] ) for the rows of each tile that lie inside the box and the volume
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplits, const ConvGeom g, long long tiles,
-                                     int Cout, __nv_bfloat16* __restrict__ y) {
-  const int c8s = Cout / 8;
-  const long long total = tiles * 128 * c8s;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % c8s);
-    const int row = (int)((idx / c8s) % 128);
-    const long long tile = idx / ((long long)c8s * 128);
-    int w0, h0, d0, n;
-    decode_tile(g, tile, w0, h0, d0, n);
-    const int w = w0 + row % g.wt, h = h0 + (row / g.wt) % g.ht, d = d0 + row / (g.wt * g.ht);
-    if (row >= g.rows || w >= g.W || h >= g.H || d >= g.D) continue;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < ksplits; ++s) {
-      const float* src = partial + (((size_t)s * (size_t)tiles + (size_t)tile) * 128 + row) * (size_t)Cout + (size_t)c8 * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-    }
-    const long long vox = (((long long)n * g.D + d) * g.H + h) * g.W + w;
-    uint4 pk;
-    pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-    pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(y + (size_t)vox * Cout + (size_t)c8 * 8) = pk;
-  }
-}
-
-// number of K splits for this shape (1 = the plain kernel runs)
-static constexpr long long kSplitKMaxCtas = 40;
-static int splitk_plan(int N, int D, int H, int W, int Cin, int Cout, ConvGeom& g, long long& tiles, int& block_n) {
-  fill_geom(g, N, D, H, W, Cin, kTapsPlain);
-  tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * N;
-  block_n = (Cout % 128 == 0) ? 128 : 64;
-  const long long ctas = tiles * (Cout / block_n);
-  const char* e = getenv("SIVAE_SPLITK");
-  if (e != nullptr && e[0] == '0') return 1;
-  const bool force = e != nullptr && e[0] == 'f';
-  if (!force && ctas > kSplitKMaxCtas) return 1;
-  if (ctas >= 2ll * num_sms()) return 1;                       // already two waves of CTAs: nothing to gain
-  long long ks = (2ll * num_sms() + ctas - 1) / ctas;          // aim at two CTAs per SM (the 3-stage kernel fits two)
-  if (ks > 9) ks = 9;                                          // at least three taps per split
-  return (int)(ks < 1 ? 1 : ks);
-}
-
-size_t conv3_igemm_splitk_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
-  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64) return 0;
-  ConvGeom g; long long tiles; int block_n;
-  const int ks = splitk_plan(N, D, H, W, Cin, Cout, g, tiles, block_n);
-  return ks > 1 ? (size_t)ks * (size_t)tiles * 128 * (size_t)Cout * sizeof(float) : 0;
-}
-
-template <int BLOCK_N>
-static int launch_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGeom& g, long long tiles, int nblocks,
-                         int ks, float* partial, int Cout, cudaStream_t st) {
-  constexpr int STAGES = 3;
-  constexpr int smem = STAGES * (kTileBytes + BLOCK_N * 128) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(conv3_igemm_splitk_kernel<BLOCK_N, STAGES>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-                   "cudaFuncSetAttribute(conv3_igemm_splitk)"))
-      return -1;
-    attr_set = true;
-  }
-  dim3 grid((unsigned)tiles, (unsigned)nblocks, (unsigned)ks);
-  conv3_igemm_splitk_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, g, ks, partial, Cout, tiles);
-  SIVAE_LAUNCH_OK("conv3_igemm_splitk_kernel");
-  return 0;
-}
-
-// conv3_igemm with a caller-owned workspace: takes the split-K path when splitk_plan says so and the workspace is large
-// enough, else the plain path (sivae_conv3_igemm unchanged).
-int conv3_igemm_ws(const void* x, const void* wpack, void* y, int N, int D, int H, int W, int Cin, int Cout, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
-  SIVAE_CHECK(Cin % 64 == 0 && Cin >= 64 && Cout % 64 == 0 && Cout >= 64,
-              "conv3_igemm_ws: Cin=%d, Cout=%d must be multiples of 64", Cin, Cout);
-  SIVAE_CHECK(N > 0 && D > 0 && H > 0 && W > 0, "conv3_igemm_ws: empty tensor");
-  ConvGeom g; long long tiles; int block_n;
-  const int ks = splitk_plan(N, D, H, W, Cin, Cout, g, tiles, block_n);
-  const size_t need = ks > 1 ? (size_t)ks * (size_t)tiles * 128 * (size_t)Cout * sizeof(float) : 0;
-  if (ks <= 1 || ws == nullptr || ws_bytes < need || tiles >= (1ll << 31))
-    return conv3_igemm(x, wpack, y, N, D, H, W, Cin, Cout, st);
-  CUtensorMap tmA, tmB;
-  if (make_act_tmap(&tmA, x, N, D, H, W, Cin, g.wt, g.ht, g.dt)) return -1;
-  if (make_weight_tmap(&tmB, wpack, 27, Cout, Cin, block_n)) return -1;
-  int rc = block_n == 128 ? launch_splitk<128>(tmA, tmB, g, tiles, Cout / 128, ks, (float*)ws, Cout, st)
-                          : launch_splitk<64>(tmA, tmB, g, tiles, Cout / 64, ks, (float*)ws, Cout, st);
-  if (rc) return rc;
-  const long long total = tiles * 128 * (Cout / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)ws, ks, g, tiles, Cout, (__nv_bfloat16*)y);
-  SIVAE_LAUNCH_OK("splitk_reduce_kernel");
-  return 0;
-}
-
 }  // namespace sivae

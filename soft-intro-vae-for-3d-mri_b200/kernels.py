@@ -83,8 +83,6 @@ _SIGNATURES = {
     "sivae_volume_stats": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sivae_preprocess_clip_minmax": (_i, [_vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
     "sivae_affine_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "sivae_conv3_igemm_splitk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "sivae_conv3_igemm_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "sivae_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sivae_linear_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
@@ -255,14 +253,6 @@ def conv3_igemm(x: torch.Tensor, wpack: torch.Tensor) -> torch.Tensor:
     y = torch.empty(n, d, h, w, co, dtype=torch.bfloat16, device=x.device)
     flops = 2.0 * 27 * ci * co * n * d * h * w
     lib = _L()
-    # tiny grids (<= 40 CTAs: the 5x6x5 layers of the FC-latent variant) split the 27 taps over several CTAs
-    nbytes = lib.sivae_conv3_igemm_splitk_workspace_bytes(n, d, h, w, ci, co)
-    if nbytes > 0:
-        ws = _workspace(x.device, nbytes, "splitk")
-        _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
-               lambda: _check(lib.sivae_conv3_igemm_ws(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _p(ws), ws.numel(),
-                                                       _stream(x)), "sivae_conv3_igemm_ws"))
-        return y
     _timed("conv3_igemm", (flops, (n, d, h, w, ci, co)),
            lambda: _check(lib.sivae_conv3_igemm(_p(x), _p(wpack), _p(y), n, d, h, w, ci, co, _stream(x)),
                           "sivae_conv3_igemm"))

@@ -39,17 +39,14 @@ CONV_MODES = {"auto": {}, "kd_force": {"SIVAE_CONV_KD": "force"}, "tapwise": {"S
               # N = 256 tiles with the 4-stage ring (the library's choice for Cout % 256 == 0 grids of more than one wave
               # of N = 128 CTAs) forced for every Cout % 256 == 0 shape, and the legacy 3-stage form
               "n256_ring4": {"SIVAE_CONV_KD": "0", "SIVAE_N256": "4"},
-              "n256_ring3": {"SIVAE_CONV_KD": "0", "SIVAE_N256": "1"},
-              # split-K over the taps (the library takes it by itself for grids of <= 40 CTAs) forced for every shape
-              "splitk": {"SIVAE_CONV_KD": "0", "SIVAE_SPLITK": "force"},
-              "splitk_off": {"SIVAE_CONV_KD": "0", "SIVAE_SPLITK": "0"}}
+              "n256_ring3": {"SIVAE_CONV_KD": "0", "SIVAE_N256": "1"}}
 
 
 
 @pytest.fixture(params=list(CONV_MODES))
 def kwmode(request):
     import os
-    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW", "SIVAE_DEEP_RING", "SIVAE_N256", "SIVAE_SPLITK")
+    keys = ("SIVAE_CONV_KD", "SIVAE_CONV_KW", "SIVAE_DEEP_RING", "SIVAE_N256")
     old = {k: os.environ.get(k) for k in keys}
     for k in keys:
         os.environ.pop(k, None)
