@@ -120,7 +120,17 @@ def deferred_bn():
 
 def _note_bn(bn: BnState, mean, invstd, nvox: int):
     if bn.defer is not None and bn.training:
-        bn_defer.records.append((bn.defer, mean, invstd, int(nvox), float(bn.momentum), float(bn.eps)))
+        c = bn.defer[0].numel()                         # the holder's channel count (the kernels may run zero-padded)
+        if mean.numel() != c:
+            mean, invstd = mean[:c], invstd[:c]
+        bn_defer.records.append([bn.defer, mean, invstd, int(nvox), float(bn.momentum), float(bn.eps), None])
+
+
+def note_bias_into_running_mean(bias):
+    """FC-latent variant (mymodel.py): a convolution bias in front of a train-mode BatchNorm only shifts the batch mean;
+    the fused units run the bias-free convolution, so the deferred running-mean update of the record just logged gets
+    ``+ momentum * bias`` (the non-deferred path adds it through mymodel._BiasIntoRunningMean)."""
+    bn_defer.records[-1][6] = bias.detach()
 
 
 def apply_deferred_bn(records):
@@ -146,6 +156,9 @@ def apply_deferred_bn(records):
                 rms, rvs = [r[0][0] for r in rs], [r[0][1] for r in rs]
                 torch._foreach_mul_(rms, 1.0 - m)
                 torch._foreach_add_(rms, [r[1] for r in rs], alpha=m)
+                with_bias = [r for r in rs if r[6] is not None]
+                if with_bias:
+                    torch._foreach_add_([r[0][0] for r in with_bias], [r[6] for r in with_bias], alpha=m)
                 torch._foreach_mul_(rvs, 1.0 - m)
                 torch._foreach_add_(rvs, var)
             nbts = [r[0][2] for r in wave if r[0][2] is not None]

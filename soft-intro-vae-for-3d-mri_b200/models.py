@@ -62,8 +62,6 @@ class _BnBinding:
         mom = 0.1 if bn.momentum is None else bn.momentum
         if F.bn_defer.records is not None and bn.training:
             # side-stream pass (trainer._fork_join): the running statistics are updated after the streams have joined
-            if self.c != self.cp:
-                raise RuntimeError("two-stream execution needs channel counts that are multiples of 64")
             return F.BnState(None, None, None, True, mom, bn.eps,
                              defer=(bn.running_mean, bn.running_var, bn.num_batches_tracked))
         if self.c == self.cp:
@@ -142,8 +140,10 @@ class BuildingBlock(nn.Module):
     def prepack(self):
         """Make sure the bf16 weight packs of both convolutions exist (on the CURRENT stream) -- called before two passes
         through this block are issued on two streams, so neither of them launches a pack kernel the other one needs."""
-        F._packed(_conv3_weight(self.block[0]), False)
-        F._packed(_conv3_weight(self.block[4]), self.stride == 2 and self._upsample)
+        for conv, pre_up in ((self.block[0], False), (self.block[4], self.stride == 2 and self._upsample)):
+            w = _conv3_weight(conv)
+            if w is conv.weight:          # channel-padded weights are re-packed per call from their temporaries
+                F._packed(w, pre_up)
 
     def forward(self, x):
         """x, result: NDHWC activations (bf16 on the CUDA path)."""
@@ -409,8 +409,8 @@ class SoftIntroVAE(nn.Module):
         self.decoder = ResNetDecoder(self.encoder)
 
     def two_stream_ok(self) -> bool:
-        """Independent passes may run on two CUDA streams (trainer._fork_join) when no layer needs channel padding."""
-        return all(m.num_features % CH_ALIGN == 0 for m in self.modules() if isinstance(m, nn.BatchNorm3d))
+        """Independent passes of a training iteration may run on two CUDA streams (trainer._fork_join)."""
+        return True
 
     def prepack(self):
         for m in self.modules():

@@ -78,7 +78,10 @@ def _conv_bn_act(x, conv: nn.Conv3d, bn: nn.BatchNorm3d, pend: _BiasIntoRunningM
     out = F.conv_bn_act(x, _conv3_weight(conv), gamma, beta, res, state, slope, resample, pre_up)
     b.commit()
     if conv.bias is not None and bn.training:
-        pend.add(bn, conv.bias)
+        if state.defer is not None:
+            F.note_bias_into_running_mean(conv.bias)     # side-stream pass: rides on the deferred running-mean update
+        else:
+            pend.add(bn, conv.bias)
     return out
 
 
@@ -205,6 +208,23 @@ class SoftIntroVAE(nn.Module):
         self.encoder = ResNetVAEencoder(first_ch, second_ch, third_ch, forth_ch, z_ch, latent_grid)
         self.decoder = ResNetDecoder(first_ch, second_ch, third_ch, forth_ch, z_ch, latent_grid)
         self.z_ch = z_ch
+
+    def two_stream_ok(self) -> bool:
+        """Independent passes of a training iteration may run on two CUDA streams (trainer._fork_join)."""
+        return True
+
+    def prepack(self):
+        """bf16 packs of every unpadded 3x3x3 weight on the current stream before two passes fork (padded weights are
+        re-packed per call from their temporaries, each pass its own)."""
+        e, d = self.encoder, self.decoder
+        plain = [e.block1[3], e.block2[0], e.block2[3], e.block3[0], e.block3[3], e.block4short[0], e.block5[0],
+                 e.block6[0], e.block6[4], e.block7[0], e.block7[3], d.block1[0], d.block1[3], d.block2u[0], d.block3[0],
+                 d.block3[3], d.block4u[0], d.block5u[0], d.block6u[0]]
+        up = [d.block2u[4], d.block4u[4], d.block5u[4], d.block6u[4]]
+        for conv, pre_up in [(c, False) for c in plain] + [(c, True) for c in up]:
+            w = _conv3_weight(conv)
+            if w is conv.weight:
+                F._packed(w, pre_up)
 
     def reparameterize(self, mu, logvar):
         return F.reparameterize(mu, logvar, F.draw_eps(mu))

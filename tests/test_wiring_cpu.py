@@ -255,16 +255,17 @@ def test_fc_eval_forward_matches_oracle_small_grid():
     torch.testing.assert_close(x_re, x_r, rtol=1e-4, atol=1e-5)
 
 
-def test_deferred_bn_updates_match_direct():
+@pytest.mark.parametrize("width", [64, 4])
+def test_deferred_bn_updates_match_direct(width):
     """trainer._fork_join issues the second pass of an independent pair on a side stream with its BatchNorm
     running-statistic updates deferred (functional.deferred_bn / apply_deferred_bn).  Two passes through the same
     layers, deferred and applied afterwards, must leave exactly the buffers that two direct passes leave
     (running <- 0.9 running + 0.1 batch composes in call order; num_batches_tracked += 2)."""
     torch.manual_seed(5)
-    bs = [[64, 1, 2], [64, 1, 2], [64, 2, 2]]
-    a = sivae_b200.SoftIntroVAE(64, bs)
+    bs = [[width, 1, 2], [width, 1, 2], [width, 2, 2]]      # width 4: the kernels run zero-padded to 64 channels
+    a = sivae_b200.SoftIntroVAE(width, bs)
     a.apply(T.init_weights_he)
-    b = sivae_b200.SoftIntroVAE(64, bs)
+    b = sivae_b200.SoftIntroVAE(width, bs)
     b.load_state_dict(a.state_dict())
     a.train(), b.train()
     assert a.two_stream_ok()
@@ -292,7 +293,6 @@ def test_deferred_bn_updates_match_direct():
             assert int(sa[k]) == int(sb[k]) and int(sa[k]) in (0, 2), k
         elif "running" in k:
             torch.testing.assert_close(sb[k], sa[k], rtol=2e-5, atol=1e-6, msg=k)
-    assert not sivae_b200.SoftIntroVAE(4, [[4, 1, 2], [8, 1, 2], [8, 2, 2]]).two_stream_ok()   # padded widths: no
 
 
 def test_stride1_block_with_channel_change_runs_the_projection_shortcut():
@@ -331,3 +331,36 @@ def test_stride1_block_with_channel_change_runs_the_projection_shortcut():
     assert set(got) == {k for k, p in ps.items() if p.grad is not None}
     for k, v in got.items():
         torch.testing.assert_close(v, ps[k].grad, rtol=2e-3, atol=1e-3 * float(ps[k].grad.abs().max()) + 1e-6, msg=k)
+
+
+def test_fc_variant_deferred_bn_and_bias_match_direct():
+    """FC-latent variant (mymodel.py): every convolution carries a bias in front of its train-mode BatchNorm, which the
+    fused units move into the running mean.  A deferred pass (side stream of trainer._fork_join) must leave the same
+    buffers as a direct one, incl. that bias term, over two passes through the same layers."""
+    torch.manual_seed(6)
+    a = sivae_b200.mymodel.SoftIntroVAE(4, 4, 8, 8, 6, latent_grid=(1, 1, 1))
+    a.apply(T.init_weights_he)
+    b = sivae_b200.mymodel.SoftIntroVAE(4, 4, 8, 8, 6, latent_grid=(1, 1, 1))
+    b.load_state_dict(a.state_dict())
+    a.train(), b.train()
+    assert a.two_stream_ok()
+    x1, x2 = torch.rand(3, 1, 16, 16, 16), torch.rand(3, 1, 16, 16, 16) * 2.0
+    F.noise_state.eps_feed = iter([torch.zeros(3, 6)] * 4)
+    try:
+        with emulated_kernels(), torch.no_grad():
+            ra = [a.forward(x1)[3], a.forward(x2)[3]]
+            with F.deferred_bn() as log:
+                rb = [b.forward(x1)[3], b.forward(x2)[3]]
+            assert int(b.state_dict()["encoder.block1.1.num_batches_tracked"]) == 0
+            F.apply_deferred_bn(log)
+    finally:
+        F.noise_state.eps_feed = None
+    for u, v in zip(ra, rb):
+        torch.testing.assert_close(u, v, rtol=0, atol=0)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]), k
+        elif "running" in k:
+            torch.testing.assert_close(sb[k], sa[k], rtol=2e-5, atol=1e-6, msg=k)
+    assert float(sa["encoder.block2.1.running_mean"].abs().max()) > 0
