@@ -702,7 +702,7 @@ struct UpGeom {
   int cin_blocks;
   long long items;                 // tiles_w * tiles_h * D * 2 * N
 };
-static constexpr int kUpAStages = 5, kUpBStages = 7;
+static constexpr int kUpAStages = 5, kUpBStages = 7;   // (6 B stages would leave room for a co-resident BatchNorm block: A/B neutral)
 static constexpr int kUpBSlot = 2 * 64 * 128;       // up to two stacked 64 x 64 slabs
 static constexpr int kUpSmem = kUpAStages * kTileBytes + kUpBStages * kUpBSlot + 2 * kTileBytes + 1024 + 256;
 static constexpr int kUpSteps = 10;
@@ -1894,8 +1894,11 @@ int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wup
 // 180 x 27 floats of P traffic -- the first version of this kernel (one 18 x 10 x 3 box per output plane) moved 3x that
 // and was bound by shared-memory bandwidth (ncu: every pipe < 30 % busy, profiles/r01c).
 // Persistent CTA, one per SM: resident weights, 4-deep input ring, ring of eight 64-column TMEM slots handed over per
-// M-tile, 4-deep P ring.  6 warps: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> P -> gather -> bias / ReLU /
-// dropout -> fp32 store).
+// M-tile, 5-deep P ring.  10 warps: TMA producer, MMA issuer, 4 converter warps (TMEM -> hi + lo -> P) and 4 gather
+// warps (27-term gather -> bias / ReLU / dropout -> fp32 store), handing P planes over through mbarriers.  With ONE
+// warp group doing both halves the kernel ran at the length of that group's dependency chain (ncu source view of the
+// round-2 build: 39 % of its samples in TMEM -> P, 44 % in gather / Philox / store, 17 % at the barrier between them,
+// every pipe < 30 % busy, 300 us against 100 us of HBM time); the two halves now overlap plane by plane.
 // =================================================================================================
 static constexpr int kHW = 16, kHH = 8;                        // outputs per patch (w, h)
 static constexpr int kHBW = kHW + 2, kHBH = kHH + 2, kHBD = 3; // input halo (kHBD only used by the c1 kernels' 3-plane halo)
@@ -1906,11 +1909,12 @@ static constexpr int kSASlot = ((kSPRows * 128 + 1023) / 1024) * 1024;     // 23
 static constexpr int kSASlots = 4;
 static constexpr int kSARegion = (kSASlots - 1) * kSASlot + 2 * kTileBytes;  // the 2nd M-tile reads 76 rows past a plane
 static constexpr int kHBBytes = 64 * 128;                                   // [hi 32 taps | lo 32 taps] x 64 channels
-static constexpr int kSPSlots = 4;
+static constexpr int kSPSlots = 5;
 static constexpr int kSPSlotFloats = kSPRows * kPStride;                    // 4,860
-static constexpr int kSPBytes = kSPSlots * kSPSlotFloats * 4;               // 77,760
+static constexpr int kSPBytes = kSPSlots * kSPSlotFloats * 4;               // 97,200
 static constexpr int kHSlots = 8;
-static constexpr int kTo1Smem = kSARegion + kHBBytes + kSPBytes + 1024 + 256;
+static constexpr int kTo1Threads = 320;
+static constexpr int kTo1Smem = kSARegion + kHBBytes + kSPBytes + 1024 + 512;
 
 struct To1Geom {
   int N, D, H, W;
@@ -1919,7 +1923,7 @@ struct To1Geom {
   int items;             // tiles_w * tiles_h * chunks * N
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTo1Threads, 1)
 conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const To1Geom g,
                       const ToOneEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -1930,7 +1934,9 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* a_empty = a_full + kSASlots;
   uint64_t* slot_full = a_empty + kSASlots;
   uint64_t* slot_empty = slot_full + kHSlots;
-  uint64_t* b_full = slot_empty + kHSlots;
+  uint64_t* p_full = slot_empty + kHSlots;
+  uint64_t* p_empty = p_full + kSPSlots;
+  uint64_t* b_full = p_empty + kSPSlots;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1940,6 +1946,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSASlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kHSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
+    for (int s = 0; s < kSPSlots; ++s) { mbar_init(&p_full[s], 128); mbar_init(&p_empty[s], 128); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -2010,23 +2017,20 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
-  } else {
-    // ===== epilogue (warps 2..5 <-> TMEM lane quadrants 2,3,0,1) =====
+  } else if (warp_id < 6) {
+    // ===== converters (warps 2..5 <-> TMEM lane quadrants 2,3,0,1): P[plane][row][tap] = hi + lo partial =====
+    // P plane `pc` (counted over the CTA's whole run) lives in ring slot pc % kSPSlots; the gather warps release the slot
+    // of plane pc - 2 after their step pc, so a converter may run two planes ahead of them.
     const int q = warp_id & 3;
-    const int t128 = (warp_id - 2) * 32 + lane;          // one output voxel of the patch per epilogue thread
-    const int ow = t128 % kHW, oh = t128 / kHW;
-    const float bias = ep.bias ? ep.bias[0] : 0.f;
-    const float inv_keep = 1.f / (1.f - ep.p);
-    const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: STS / LDS below
-    uint32_t sl = 0;
+    const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: STS below
+    uint32_t sl = 0, pslot = 0, pfree = 1;                // pfree: parity to wait for on p_empty (starts "free")
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
       int w0, h0, d_lo, d_hi, n;
       decode(item, w0, h0, d_lo, d_hi, n);
-      const int w = w0 + ow, h = h0 + oh;
-      const bool inside = (w < g.W && h < g.H);
       const int planes = d_hi - d_lo + 2;
       for (int zi = 0; zi < planes; ++zi) {
-        const uint32_t Pz = p_addr + (uint32_t)(zi & (kSPSlots - 1)) * (kSPSlotFloats * 4u);
+        mbar_wait(&p_empty[pslot], pfree);
+        const uint32_t Pz = p_addr + pslot * (kSPSlotFloats * 4u);
 #pragma unroll 1
         for (int m = 0; m < 2; ++m, ++sl) {
           const uint32_t slot = sl % kHSlots;
@@ -2053,13 +2057,33 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (lane == 0) mbar_arrive(&slot_empty[slot]);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // P of input plane zi is complete
+        mbar_arrive(&p_full[pslot]);                       // every converter thread: its rows of plane zi are in P
+        if (++pslot == kSPSlots) { pslot = 0; pfree ^= 1u; }
+      }
+    }
+  } else {
+    // ===== gather warps (6..9): one output voxel of the patch per thread and output plane =====
+    const int t128 = (warp_id - 6) * 32 + lane;
+    const int ow = t128 % kHW, oh = t128 / kHW;
+    const float bias = ep.bias ? ep.bias[0] : 0.f;
+    const float inv_keep = 1.f / (1.f - ep.p);
+    const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: LDS below
+    uint32_t pslot = 0, pfull = 0;                        // slot of the newest plane, parity to wait for on p_full
+    uint32_t s1 = 0, s2 = 0, seen = 0;                    // slots of the two planes before it
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+      int w0, h0, d_lo, d_hi, n;
+      decode(item, w0, h0, d_lo, d_hi, n);
+      const int w = w0 + ow, h = h0 + oh;
+      const bool inside = (w < g.W && h < g.H);
+      const int planes = d_hi - d_lo + 2;
+      for (int zi = 0; zi < planes; ++zi) {
+        mbar_wait(&p_full[pslot], pfull);                  // P of input plane zi is complete (zi-1, zi-2 seen earlier)
         if (zi >= 2 && inside) {
           // output plane d = d_lo + zi - 2 gathers tap kd from input plane (zi - 2 + kd)
           float acc = 0.f;
 #pragma unroll
           for (int kd = 0; kd < 3; ++kd) {
-            const uint32_t Pk = p_addr + (uint32_t)((zi - 2 + kd) & (kSPSlots - 1)) * (kSPSlotFloats * 4u);
+            const uint32_t Pk = p_addr + (kd == 0 ? s2 : kd == 1 ? s1 : pslot) * (kSPSlotFloats * 4u);
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
               const int row = (oh + t9 / 3) * kHBW + ow + t9 % 3;
@@ -2076,8 +2100,13 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           ep.y[vox] = r;
         }
+        // the plane two steps back has served its last output plane (across an item boundary: it was the previous
+        // item's, whose last gather ran at least one step ago)
+        if (seen >= 2) mbar_arrive(&p_empty[s2]);
+        else ++seen;
+        s2 = s1; s1 = pslot;
+        if (++pslot == kSPSlots) { pslot = 0; pfull ^= 1u; }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // the P ring is free for the next item
     }
   }
   tc_fence_before();
@@ -2122,7 +2151,7 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
   uint8_t* smem_b = smem + 2 * kC1ABytes;
   uint8_t* smem_o = smem_b + kC1BBytes;
   float* xs = reinterpret_cast<float*>(smem_o + kTileBytes);       // [2][kC1Halo]
-  float* bias_s = xs + 2 * kC1Halo;                                // [64]
+  float* bias_s = xs + 2 * kC1Halo;                                // [64], 16-byte aligned (kC1Halo % 4 == 0)
   uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint64_t* a_empty = a_full + 2;
   uint64_t* acc_full = a_empty + 2;
@@ -2198,17 +2227,25 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
     const int ow = row % kHW, oh = row / kHW;
     constexpr int kPer = (kHRows + 127) / 128;            // halo floats per thread (5)
     float pre[kPer];
+    // this thread's halo cells never change: offsets from the halo origin and packed (wx, hy, dz) for the bounds tests
+    int off[kPer], cell[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = row + j * 128;
+      const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
+      off[j] = (dz * H + hy) * W + wx;
+      cell[j] = i < kHRows ? (wx | (hy << 8) | (dz << 16)) : -1;
+    }
     auto fetch = [&](int item) {
       int w0, h0, d0; long long n;
       decode(item, w0, h0, d0, n);
+      const float* origin = x1 + (((n * D + (d0 - 1)) * H + (h0 - 1)) * W + (w0 - 1));
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
-        const int i = row + j * 128;
-        const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
-        const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+        const int d = d0 - 1 + (cell[j] >> 16), h = h0 - 1 + ((cell[j] >> 8) & 255), w = w0 - 1 + (cell[j] & 255);
         float v = 0.f;
-        if (i < kHRows && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-          v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+        if (cell[j] >= 0 && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+          v = __ldg(origin + off[j]);
         pre[j] = v;
       }
     };
@@ -2277,9 +2314,17 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
       for (int c = 0; c < 4; ++c) {
         float f[8], g8[8];
 #pragma unroll
+        // bias: 128-bit broadcast reads (4 per 8 channels instead of 16 scalar ones).  Folding it into a free K slot of
+        // the GEMM was tried: faster still, but a bf16 hi + lo bias moves single roundings of the output (0.07 % of
+        // the elements), and the fp32 add keeps this kernel bit-identical to the build the parity evidence was taken on
+        const float4 b0 = lds128_f32(bias_addr + (uint32_t)(c * 8) * 4u), b1 = lds128_f32(bias_addr + (uint32_t)(c * 8 + 4) * 4u);
+        const float4 b2 = lds128_f32(bias_addr + (uint32_t)(32 + c * 8) * 4u), b3 = lds128_f32(bias_addr + (uint32_t)(36 + c * 8) * 4u);
+        const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float bh[8] = {b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
         for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(v0[c * 8 + e]) + lds_f32(bias_addr + (uint32_t)(c * 8 + e) * 4u);          // broadcast reads
-          g8[e] = __uint_as_float(v1[c * 8 + e]) + lds_f32(bias_addr + (uint32_t)(32 + c * 8 + e) * 4u);
+          f[e] = __uint_as_float(v0[c * 8 + e]) + bl[e];
+          g8[e] = __uint_as_float(v1[c * 8 + e]) + bh[e];
         }
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
@@ -2481,17 +2526,25 @@ wgrad_c1_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtenso
     float pre[kPer];
     // the fp32 halo of the NEXT tile is fetched into registers while the current A tile is built, so the global-load
     // latency is off the per-tile critical path
+    // this thread's halo cells never change: offsets from the halo origin and packed (wx, hy, dz) for the bounds tests
+    int off[kPer], cell[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = row + j * 128;
+      const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
+      off[j] = (dz * H + hy) * W + wx;
+      cell[j] = i < kHRows ? (wx | (hy << 8) | (dz << 16)) : -1;
+    }
     auto fetch = [&](long long id) {
       int w0, h0, d0; long long n;
       decode(id, w0, h0, d0, n);
+      const float* origin = x1 + (((n * D + (d0 - 1)) * H + (h0 - 1)) * W + (w0 - 1));
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
-        const int i = row + j * 128;
-        const int wx = i % kHBW, hy = (i / kHBW) % kHBH, dz = i / (kHBW * kHBH);
-        const int d = d0 - 1 + dz, h = h0 - 1 + hy, w = w0 - 1 + wx;
+        const int d = d0 - 1 + (cell[j] >> 16), h = h0 - 1 + ((cell[j] >> 8) & 255), w = w0 - 1 + (cell[j] & 255);
         float v = 0.f;
-        if (i < kHRows && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-          v = __ldg(x1 + ((n * D + d) * H + h) * W + w);
+        if (cell[j] >= 0 && (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+          v = __ldg(origin + off[j]);
         pre[j] = v;
       }
     };
@@ -2668,7 +2721,7 @@ int conv3_to1(const void* x, const float* w, const float* bias, float* y, int N,
       attr_set = true;
     }
     const unsigned ctas = (unsigned)(tg.items < num_sms() ? tg.items : num_sms());
-    conv3_to1_halo_kernel<<<ctas, 192, kTo1Smem, st>>>(tmA, tmB, tg, ep);
+    conv3_to1_halo_kernel<<<ctas, kTo1Threads, kTo1Smem, st>>>(tmA, tmB, tg, ep);
     SIVAE_LAUNCH_OK("conv3_to1_halo_kernel");
     return 0;
   }

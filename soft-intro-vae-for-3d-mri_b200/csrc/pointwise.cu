@@ -81,26 +81,26 @@ __device__ __forceinline__ void keep_scale_from_byte(uint32_t byte, float p, flo
 }
 
 // Block-level reduction of per-thread (s1[8], s2[8]) for threads sharing a channel chunk; result to
-// partial[(blockIdx.x*2 + {0,1})*C + c].
+// partial[(blockIdx.x*2 + {0,1})*C + c].  Two passes over one 9 KB staging array (first the s1 sums, then the s2 sums;
+// the additions and their order are those of a single 17 KB pass): a reduce block must fit into the ~16 KB of shared
+// memory a persistent convolution CTA (209 KB) leaves on its SM, otherwise the BatchNorm-backward of one pass cannot
+// run under the convolutions of the pass issued on the other stream (tools/overlap_probe.py: 0.6 % -> see profiles/).
 __device__ __forceinline__ void block_reduce_channels(const float (&s1)[8], const float (&s2)[8], int C, int cpc,
                                                       float* __restrict__ partial) {
-  __shared__ float sh[kBnThreads][17];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    sh[threadIdx.x][k] = s1[k];
-    sh[threadIdx.x][8 + k] = s2[k];
-  }
-  __syncthreads();
+  __shared__ float sh[kBnThreads][9];
   const int lanes_v = kBnThreads / cpc;
-  for (int j = threadIdx.x; j < C; j += kBnThreads) {
-    const int chunk = j >> 3, k = j & 7;
-    float a = 0.f, b = 0.f;
-    for (int lv = 0; lv < lanes_v; ++lv) {
-      a += sh[lv * cpc + chunk][k];
-      b += sh[lv * cpc + chunk][8 + k];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (half) __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = half ? s2[k] : s1[k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < C; j += kBnThreads) {
+      const int chunk = j >> 3, k = j & 7;
+      float a = 0.f;
+      for (int lv = 0; lv < lanes_v; ++lv) a += sh[lv * cpc + chunk][k];
+      partial[((long long)blockIdx.x * 2 + half) * C + j] = a;
     }
-    partial[((long long)blockIdx.x * 2 + 0) * C + j] = a;
-    partial[((long long)blockIdx.x * 2 + 1) * C + j] = b;
   }
 }
 

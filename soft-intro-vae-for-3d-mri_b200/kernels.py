@@ -17,7 +17,7 @@ from typing import Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsivae.so")
+LIB_PATH = os.environ.get("SIVAE_LIB") or os.path.join(_HERE, "libsivae.so")   # SIVAE_LIB: A/B another build
 
 RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_UPSAMPLE2 = 0, 1, 2
 
