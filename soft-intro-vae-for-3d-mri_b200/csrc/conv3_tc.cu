@@ -1894,8 +1894,9 @@ int pack_upconv3_weights(const float* w, int Cout, int Cin, void* wup, void* wup
 // 180 x 27 floats of P traffic -- the first version of this kernel (one 18 x 10 x 3 box per output plane) moved 3x that
 // and was bound by shared-memory bandwidth (ncu: every pipe < 30 % busy, profiles/r01c).
 // Persistent CTA, one per SM: resident weights, 4-deep input ring, ring of eight 64-column TMEM slots handed over per
-// M-tile, 5-deep P ring.  10 warps: TMA producer, MMA issuer, 4 converter warps (TMEM -> hi + lo -> P) and 4 gather
-// warps (27-term gather -> bias / ReLU / dropout -> fp32 store), handing P planes over through mbarriers.  With ONE
+// M-tile, 5-deep P ring.  18 warps: TMA producer, MMA issuer, 2 x 4 converter warps (TMEM -> hi + lo -> P) and 2 x 4
+// gather warps (27-term gather -> bias / ReLU / dropout -> fp32 store), handing P planes over through mbarriers; the
+// two groups of a kind take alternate planes (each is one warp per scheduler running a dependent chain).  With ONE
 // warp group doing both halves the kernel ran at the length of that group's dependency chain (ncu source view of the
 // round-2 build: 39 % of its samples in TMEM -> P, 44 % in gather / Philox / store, 17 % at the barrier between them,
 // every pipe < 30 % busy, 300 us against 100 us of HBM time); the two halves now overlap plane by plane.
@@ -1913,7 +1914,8 @@ static constexpr int kSPSlots = 5;
 static constexpr int kSPSlotFloats = kSPRows * kPStride;                    // 4,860
 static constexpr int kSPBytes = kSPSlots * kSPSlotFloats * 4;               // 97,200
 static constexpr int kHSlots = 8;
-static constexpr int kTo1Threads = 320;
+static constexpr int kTo1Groups = 2;                           // converter groups = gather groups (4 warps each)
+static constexpr int kTo1Threads = 64 + 2 * kTo1Groups * 128;
 static constexpr int kTo1Smem = kSARegion + kHBBytes + kSPBytes + 1024 + 512;
 
 struct To1Geom {
@@ -1946,7 +1948,7 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSASlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kHSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
-    for (int s = 0; s < kSPSlots; ++s) { mbar_init(&p_full[s], 128); mbar_init(&p_empty[s], 128); }
+    for (int s = 0; s < kSPSlots; ++s) { mbar_init(&p_full[s], 128); mbar_init(&p_empty[s], 3 * 128); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -2017,22 +2019,26 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
-  } else if (warp_id < 6) {
-    // ===== converters (warps 2..5 <-> TMEM lane quadrants 2,3,0,1): P[plane][row][tap] = hi + lo partial =====
-    // P plane `pc` (counted over the CTA's whole run) lives in ring slot pc % kSPSlots; the gather warps release the slot
-    // of plane pc - 2 after their step pc, so a converter may run two planes ahead of them.
+  } else if (warp_id < 2 + 4 * kTo1Groups) {
+    // ===== converters (kTo1Groups x 4 warps <-> TMEM lane quadrants by warp_id % 4): P[plane][row][tap] = hi + lo =====
+    // P plane `pc` (counted over the CTA's whole run) lives in ring slot pc % kSPSlots and is converted by group
+    // pc % kTo1Groups; its slot is free again once the gather steps pc, pc+1, pc+2 have arrived on p_empty.
     const int q = warp_id & 3;
+    const uint32_t grp = (uint32_t)(warp_id - 2) >> 2;
     const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: STS below
-    uint32_t sl = 0, pslot = 0, pfree = 1;                // pfree: parity to wait for on p_empty (starts "free")
+    uint32_t pc = 0;
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
       int w0, h0, d_lo, d_hi, n;
       decode(item, w0, h0, d_lo, d_hi, n);
       const int planes = d_hi - d_lo + 2;
-      for (int zi = 0; zi < planes; ++zi) {
-        mbar_wait(&p_empty[pslot], pfree);
+      for (int zi = 0; zi < planes; ++zi, ++pc) {
+        if (pc % kTo1Groups != grp) continue;
+        const uint32_t pslot = pc % kSPSlots;
+        mbar_wait(&p_empty[pslot], ((pc / kSPSlots) & 1u) ^ 1u);
         const uint32_t Pz = p_addr + pslot * (kSPSlotFloats * 4u);
 #pragma unroll 1
-        for (int m = 0; m < 2; ++m, ++sl) {
+        for (int m = 0; m < 2; ++m) {
+          const uint32_t sl = 2u * pc + (uint32_t)m;       // the MMA warp's M-tile counter
           const uint32_t slot = sl % kHSlots;
           const int prow = m * 128 + q * 32 + lane;
           mbar_wait(&slot_full[slot], (sl / kHSlots) & 1u);
@@ -2057,33 +2063,40 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (lane == 0) mbar_arrive(&slot_empty[slot]);
           }
         }
-        mbar_arrive(&p_full[pslot]);                       // every converter thread: its rows of plane zi are in P
-        if (++pslot == kSPSlots) { pslot = 0; pfree ^= 1u; }
+        mbar_arrive(&p_full[pslot]);                       // every converter thread: its rows of plane pc are in P
       }
     }
   } else {
-    // ===== gather warps (6..9): one output voxel of the patch per thread and output plane =====
-    const int t128 = (warp_id - 6) * 32 + lane;
+    // ===== gather warps (kTo1Groups x 4): one output voxel of the patch per thread; step pc by group pc % kTo1Groups =====
+    const uint32_t grp = (uint32_t)(warp_id - 2 - 4 * kTo1Groups) >> 2;
+    const int t128 = ((warp_id - 2) & 3) * 32 + lane;
     const int ow = t128 % kHW, oh = t128 / kHW;
     const float bias = ep.bias ? ep.bias[0] : 0.f;
     const float inv_keep = 1.f / (1.f - ep.p);
     const uint32_t p_addr = smem_u32(P);                  // shared-window address of the P ring: LDS below
-    uint32_t pslot = 0, pfull = 0;                        // slot of the newest plane, parity to wait for on p_full
-    uint32_t s1 = 0, s2 = 0, seen = 0;                    // slots of the two planes before it
+    uint32_t pc = 0;
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
       int w0, h0, d_lo, d_hi, n;
       decode(item, w0, h0, d_lo, d_hi, n);
       const int w = w0 + ow, h = h0 + oh;
       const bool inside = (w < g.W && h < g.H);
       const int planes = d_hi - d_lo + 2;
-      for (int zi = 0; zi < planes; ++zi) {
-        mbar_wait(&p_full[pslot], pfull);                  // P of input plane zi is complete (zi-1, zi-2 seen earlier)
+      for (int zi = 0; zi < planes; ++zi, ++pc) {
+        if (pc % kTo1Groups != grp) continue;
+        // slots of planes pc-2, pc-1, pc (the converters of the other group(s) filled some of them: wait for all three)
+        uint32_t sk[3];
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const uint32_t pk = pc + (uint32_t)kd - 2u;
+          sk[kd] = pk % kSPSlots;
+          if (pc + (uint32_t)kd >= 2u) mbar_wait(&p_full[sk[kd]], (pk / kSPSlots) & 1u);
+        }
         if (zi >= 2 && inside) {
           // output plane d = d_lo + zi - 2 gathers tap kd from input plane (zi - 2 + kd)
           float acc = 0.f;
 #pragma unroll
           for (int kd = 0; kd < 3; ++kd) {
-            const uint32_t Pk = p_addr + (kd == 0 ? s2 : kd == 1 ? s1 : pslot) * (kSPSlotFloats * 4u);
+            const uint32_t Pk = p_addr + sk[kd] * (kSPSlotFloats * 4u);
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
               const int row = (oh + t9 / 3) * kHBW + ow + t9 % 3;
@@ -2100,12 +2113,11 @@ conv3_to1_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           ep.y[vox] = r;
         }
-        // the plane two steps back has served its last output plane (across an item boundary: it was the previous
-        // item's, whose last gather ran at least one step ago)
-        if (seen >= 2) mbar_arrive(&p_empty[s2]);
-        else ++seen;
-        s2 = s1; s1 = pslot;
-        if (++pslot == kSPSlots) { pslot = 0; pfull ^= 1u; }
+        // every step (also the two that open an item and gather nothing) signs off the three planes of its window:
+        // plane q has collected all its arrivals when steps q, q+1 and q+2 are done, whichever group ran them
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+          if (pc + (uint32_t)kd >= 2u) mbar_arrive(&p_empty[sk[kd]]);
       }
     }
   }

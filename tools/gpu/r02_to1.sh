@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 300 python tools/lib_compare.py build_old/libsivae_old.so 2>&1 | tail -7
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_guard_bands_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 300 python tools/pointwise_bench.py 2>&1 | grep taps
+bash tools/gpu/r02_ab_lib.sh build_old/libsivae_old.so soft-intro-vae-for-3d-mri_b200/libsivae.so
