@@ -216,6 +216,45 @@ __device__ __forceinline__ void act_chunk(const __nv_bfloat16* __restrict__ y, c
   for (int k = 0; k < 8; ++k) a[k] = (f[k] > 0.f ? f[k] : slope * f[k]) * ks[k];
 }
 
+// The most frequent case on its own: no resampling, no residual, no dropout (first BatchNorm of every residual block).
+// One tensor in, one out -- the access pattern of a plain copy -- so the bytes in flight per SM are what sets the
+// bandwidth: 8 independent 16-byte loads per thread (the general kernel below issues 4 per tensor and carries the
+// registers of the residual / dropout paths: 5.0 TB/s where a copy reaches 6.5).  Same arithmetic, bitwise equal results.
+__global__ void __launch_bounds__(256, 2) bn_act_plain_fwd_kernel(const __nv_bfloat16* __restrict__ y,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift,
+                                                                  __nv_bfloat16* __restrict__ out, unsigned nitems, int C,
+                                                                  float slope) {
+  constexpr int U = 8;
+  const int chunk = (int)(threadIdx.x % (C >> 3));      // 256 threads and C/8 | 256: fixed across the grid-stride loop
+  float sc[8], sh[8];
+  ldf8(scale + chunk * 8, sc);
+  ldf8(shift + chunk * 8, sh);
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nitems; i0 += stride * U) {
+    uint4 ry[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nitems) ry[u] = *reinterpret_cast<const uint4*>(y + (size_t)i * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nitems) {
+        float f[8], a[8];
+        unpack8(ry[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          f[k] = fmaf(f[k], sc[k], sh[k]);
+          a[k] = f[k] > 0.f ? f[k] : slope * f[k];
+        }
+        st8(out + (size_t)i * 8, a);
+      }
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ y,
                                                          const float* __restrict__ scale,
@@ -1153,7 +1192,9 @@ int bn_act_fwd(const void* y, const float* scale, const float* shift, const void
     keep_bits = const_cast<uint8_t*>(mask);
     mask = nullptr;
   }
-  if (resample == 0)
+  if (resample == 0 && rr == nullptr && mask == nullptr && keep_bits == nullptr && p <= 0.f)
+    bn_act_plain_fwd_kernel<<<blocks, 256, 0, st>>>(yy, scale, shift, oo, (unsigned)items, C, slope);
+  else if (resample == 0)
     bn_act_fwd_kernel<0><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed), keep_bits);
   else if (resample == 1)
     bn_act_fwd_kernel<1><<<blocks, 256, 0, st>>>(yy, scale, shift, rr, oo, N, D, H, W, C, slope, mask, p, make_seed_ref(seed), nullptr);
