@@ -13,6 +13,8 @@
 //                   K loop = 27 taps x Cin/64;   A, B K-major.
 //   wgrad         : D[2 units x 64ci, NT co]  += A[voxels x 64ci]^T (tap-shifted box) * B[voxels x 64co] (dy box)
 //                   K loop = voxel boxes;        A, B MN-major (voxel rows are the K dimension).
+#include <utility>
+
 #include "sivae_common.cuh"
 
 namespace sivae {
@@ -29,6 +31,39 @@ static int num_sms() {
       n = 148;
   }
   return n;
+}
+
+// Optional (SIVAE_CONV_PRIORITY=1): launch the tensor-core convolution kernels at the highest stream priority (per-launch
+// attribute, kept by CUDA graph capture), so that when a BatchNorm grid of the pass on the other stream and a persistent
+// convolution are pending together the block scheduler places the convolution CTAs first and the BatchNorm blocks fill
+// what is left of each SM.  Measured neutral (4 A/B pairs: 59.44 vs 59.70 ms, inside the run-to-run spread): the step is
+// power-capped, more overlap mostly buys lower clocks.  Default off.
+static int conv_priority(bool* use) {
+  static int prio = 0, enabled = -1;
+  if (enabled < 0) {
+    int least = 0, greatest = 0;
+    const char* e = getenv("SIVAE_CONV_PRIORITY");
+    enabled = (e != nullptr && atoi(e) != 0) && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
+              greatest < least;
+    prio = greatest;
+  }
+  *use = enabled != 0;
+  return prio;
+}
+template <typename... KArgs, typename... Args>
+static void launch_conv(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  bool use = false;
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = conv_priority(&use);
+  cfg.attrs = attr;
+  cfg.numAttrs = use ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through SIVAE_LAUNCH_OK
 }
 
 static constexpr int kTileRows = 128;            // UMMA M (fprop) / max voxel rows per box
@@ -1547,7 +1582,7 @@ static int launch_igemm(const TmapPack& tmA, const CUtensorMap& tmB, const TmapP
     attr_set = true;
   }
   dim3 grid((unsigned)tiles, (unsigned)nblocks, g.mode == kTapsUpFprop ? 8u : 1u);
-  conv3_igemm_kernel<BLOCK_N, STAGES, EPI><<<grid, 192, smem, st>>>(tmA, tmB, tmC, g, ep);
+  launch_conv(conv3_igemm_kernel<BLOCK_N, STAGES, EPI>, grid, 192, smem, st, tmA, tmB, tmC, g, ep);
   SIVAE_LAUNCH_OK("conv3_igemm_kernel");
   return 0;
 }
@@ -1616,7 +1651,7 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
       }
       const unsigned ctas = (unsigned)(kg.items < (long long)num_sms() ? kg.items : (long long)num_sms());
       const bool fuse_stats = stats != nullptr && stats_blocks != nullptr;
-      conv3_kd3_kernel<<<ctas, 224, kKdSmem, st>>>(tA, tB, tC, kg, fuse_stats ? stats : nullptr);
+      launch_conv(conv3_kd3_kernel, dim3(ctas), 224, kKdSmem, st, tA, tB, tC, kg, fuse_stats ? stats : (float*)nullptr);
       SIVAE_LAUNCH_OK("conv3_kd3_kernel");
       if (fuse_stats) *stats_blocks = (int)ctas * 4;
       return 0;
@@ -1653,7 +1688,7 @@ static int conv3_igemm_impl(const void* x, const void* wpack, void* y, int N, in
         attr_set = true;
       }
       const unsigned ctas = (unsigned)(kg.items < (long long)num_sms() ? kg.items : (long long)num_sms());
-      conv3_kw64_kernel<<<ctas, 224, kKwSmem, st>>>(tA, tB, tC, kg);
+      launch_conv(conv3_kw64_kernel, dim3(ctas), 224, kKwSmem, st, tA, tB, tC, kg);
       SIVAE_LAUNCH_OK("conv3_kw64_kernel");
       return 0;
     }
@@ -1767,7 +1802,7 @@ static int upconv3_fprop_impl(const void* x_lo, const void* wup, void* y_hi, int
       }
       const unsigned ctas = (unsigned)(ug.items < (long long)num_sms() ? ug.items : (long long)num_sms());
       const bool fuse_stats = stats != nullptr && stats_blocks != nullptr;
-      upconv3_fused_kernel<<<ctas, 224, kUpSmem, st>>>(tA, tB, tC, ug, fuse_stats ? stats : nullptr);
+      launch_conv(upconv3_fused_kernel, dim3(ctas), 224, kUpSmem, st, tA, tB, tC, ug, fuse_stats ? stats : (float*)nullptr);
       SIVAE_LAUNCH_OK("upconv3_fused_kernel");
       if (fuse_stats) *stats_blocks = (int)ctas * 4;
       return 0;
@@ -2858,7 +2893,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const TmapPack& tmDY, const Wgra
     attr_set = true;
   }
   dim3 grid((unsigned)(g.groups_pc * g.nclasses * ntiles), (unsigned)splits);
-  conv3_wgrad_kernel<NT, A_STAGES><<<grid, 192, smem, st>>>(tmX, tmDY, g, partial);
+  launch_conv(conv3_wgrad_kernel<NT, A_STAGES>, grid, 192, smem, st, tmX, tmDY, g, partial);
   SIVAE_LAUNCH_OK("conv3_wgrad_kernel");
   return 0;
 }
@@ -2888,8 +2923,8 @@ static int wgrad_impl(const void* x, const void* dy, float* dw, void* ws, size_t
                                             kWgKwSmem), "cudaFuncSetAttribute(conv3_wgrad_kw64)")) return -1;
         attr_set = true;
       }
-      conv3_wgrad_kw64_kernel<<<dim3(3u * (unsigned)kg.ntiles, (unsigned)ksplits), 224, kWgKwSmem, st>>>(tX, tDY, kg,
-                                                                                                      (float*)ws);
+      launch_conv(conv3_wgrad_kw64_kernel, dim3(3u * (unsigned)kg.ntiles, (unsigned)ksplits), 224, kWgKwSmem, st, tX, tDY, kg,
+                  (float*)ws);
       SIVAE_LAUNCH_OK("conv3_wgrad_kw64_kernel");
       const long long total = 27ll * 64 * Cout;
       int blocks = (int)((total + 255) / 256);
@@ -2919,8 +2954,8 @@ static int wgrad_impl(const void* x, const void* dy, float* dw, void* ws, size_t
                                             kWgKwSmem), "cudaFuncSetAttribute(upconv3_wgrad_tall)")) return -1;
         attr_set = true;
       }
-      upconv3_wgrad_tall_kernel<<<dim3(8u * (unsigned)ug.ntiles, (unsigned)usplits), 224, kWgKwSmem, st>>>(tX, tDY, ug,
-                                                                                                         (float*)ws);
+      launch_conv(upconv3_wgrad_tall_kernel, dim3(8u * (unsigned)ug.ntiles, (unsigned)usplits), 224, kWgKwSmem, st, tX, tDY, ug,
+                  (float*)ws);
       SIVAE_LAUNCH_OK("upconv3_wgrad_tall_kernel");
       const long long total = 27ll * Cin * Cout;
       int blocks = (int)((total + 255) / 256);

@@ -215,6 +215,29 @@ def test_cn_to_c1(C, T, flip, act):
     assert_f32_close(y, S.cn_to_c1(x, w, b, flip, act, mask, 0.35 if act else 0.0, 0), "cn_to_c1 (SIMT)", 2e-5)
 
 
+@pytest.mark.parametrize("act", [0, 1])
+def test_cn_to_c1_many_planes_per_cta(act, monkeypatch):
+    """conv3_to1_halo_kernel over a geometry where every CTA walks several work items of 17 input planes each: the two
+    converter and the two gather warp groups alternate planes across item boundaries and the 5-deep P ring wraps dozens
+    of times.  Checked against the specification, against the tap-by-tap tcgen05 kernel (SIVAE_TO1_TAPWISE) including
+    the Philox keep pattern, and for run-to-run identity."""
+    x = bf(3, 44, 50, 70, 64)
+    w = torch.randn(64, 27, device=DEV) * 0.1
+    b = torch.randn(1, device=DEV)
+    p, seed = (0.35, 4242) if act else (0.0, 0)
+    got = K.cn_to_c1(x, w, b, False, act, None, p, seed)
+    again = K.cn_to_c1(x, w, b, False, act, None, p, seed)
+    assert torch.equal(got, again)
+    monkeypatch.setenv("SIVAE_TO1_TAPWISE", "1")
+    tap = K.cn_to_c1(x, w, b, False, act, None, p, seed)
+    monkeypatch.delenv("SIVAE_TO1_TAPWISE")
+    # same Philox keep pattern; only pre-activations within rounding of zero may differ in being clipped by the ReLU
+    assert float(((got == 0) != (tap == 0)).float().mean()) < 1e-4
+    assert_f32_close(got, tap, "cn_to_c1 halo vs tap-by-tap", 1e-4)
+    if act == 0:
+        assert_f32_close(got, S.cn_to_c1(x, w, b, False, 0, None, 0.0, 0), "cn_to_c1 vs spec", 1e-4)
+
+
 @pytest.mark.parametrize("C,T", [(64, 27), (64, 1), (128, 27), (256, 1)])
 @pytest.mark.parametrize("flip", [False, True])
 def test_wgrad_c1(C, T, flip):
