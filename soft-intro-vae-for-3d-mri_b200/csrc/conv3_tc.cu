@@ -2189,6 +2189,7 @@ static constexpr int kC1BBytes = 2 * 64 * 128;            // [2 K blocks][64 cha
 static constexpr int kC1Halo = (kHRows + 3) & ~3;         // floats per staged halo
 static constexpr int kC1Smem = 2 * kC1ABytes + kC1BBytes + kTileBytes + 2 * kC1Halo * 4 + 64 * 4 + 1024 + 256;
 
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(288, 2)
 c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int N, int D, int H, int W,
@@ -2363,15 +2364,25 @@ c1_to_c64_tc_kernel(const float* __restrict__ x1, const __grid_constant__ CUtens
 #pragma unroll
         // bias: 128-bit broadcast reads (4 per 8 channels instead of 16 scalar ones).  Folding it into a free K slot of
         // the GEMM was tried: faster still, but a bf16 hi + lo bias moves single roundings of the output (0.07 % of
-        // the elements), and the fp32 add keeps this kernel bit-identical to the build the parity evidence was taken on
-        const float4 b0 = lds128_f32(bias_addr + (uint32_t)(c * 8) * 4u), b1 = lds128_f32(bias_addr + (uint32_t)(c * 8 + 4) * 4u);
-        const float4 b2 = lds128_f32(bias_addr + (uint32_t)(32 + c * 8) * 4u), b3 = lds128_f32(bias_addr + (uint32_t)(36 + c * 8) * 4u);
-        const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const float bh[8] = {b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+        // the elements), and the fp32 add keeps this kernel bit-identical to the build the parity evidence was taken on.
+        // Without a bias (input gradient of the decoder tail, 7 of the 12 launches of a step) the add is skipped: the
+        // accumulator is never -0 (the zero K-padding slots contribute +0 products), so acc + 0.0f == acc bit for bit.
+        if constexpr (HAS_BIAS) {
+          const float4 b0 = lds128_f32(bias_addr + (uint32_t)(c * 8) * 4u), b1 = lds128_f32(bias_addr + (uint32_t)(c * 8 + 4) * 4u);
+          const float4 b2 = lds128_f32(bias_addr + (uint32_t)(32 + c * 8) * 4u), b3 = lds128_f32(bias_addr + (uint32_t)(36 + c * 8) * 4u);
+          const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float bh[8] = {b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(v0[c * 8 + e]) + bl[e];
-          g8[e] = __uint_as_float(v1[c * 8 + e]) + bh[e];
+          for (int e = 0; e < 8; ++e) {
+            f[e] = __uint_as_float(v0[c * 8 + e]) + bl[e];
+            g8[e] = __uint_as_float(v1[c * 8 + e]) + bh[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = __uint_as_float(v0[c * 8 + e]);
+            g8[e] = __uint_as_float(v1[c * 8 + e]);
+          }
         }
         uint4 pk;
         pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
@@ -2439,7 +2450,9 @@ static int c1_to_c64_tc_impl(const float* x1, const float* w, const float* bias,
   SIVAE_CHECK(items < (1ll << 31), "c1_to_c64: too many tiles");
   static bool attr_set = false;
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
+    if (check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
+                   "cudaFuncSetAttribute(c1_to_c64_tc)") ||
+        check_cuda(cudaFuncSetAttribute(c1_to_c64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem),
                    "cudaFuncSetAttribute(c1_to_c64_tc)"))
       return -1;
     attr_set = true;
@@ -2448,7 +2461,10 @@ static int c1_to_c64_tc_impl(const float* x1, const float* w, const float* bias,
   // role is a single warp per scheduler, so a second CTA is what hides the LDS / ALU latencies of the builders
   const long long cap = 2ll * num_sms();
   const unsigned ctas = (unsigned)(items < cap ? items : cap);
-  c1_to_c64_tc_kernel<<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
+  if (bias != nullptr)
+    c1_to_c64_tc_kernel<true><<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
+  else
+    c1_to_c64_tc_kernel<false><<<ctas, 288, kC1Smem, st>>>(x1, tmB, tmC, bias, N, D, H, W, tiles_w, tiles_h, (int)items, stats);
   SIVAE_LAUNCH_OK("c1_to_c64_tc_kernel");
   if (stats != nullptr && stats_blocks != nullptr) *stats_blocks = (int)ctas * 4;
   return 0;

@@ -22,6 +22,7 @@ x1 = torch.rand(N, D, H, W, device="cuda")
 w27 = torch.randn(C, 27, device="cuda") * 0.1
 b64 = torch.randn(C, device="cuda")
 b1 = torch.randn(1, device="cuda")
+x1_sparse = x1 * (torch.rand_like(x1) > 0.6)
 
 
 def both(fn):
@@ -39,6 +40,8 @@ cases = [("cn_to_c1 relu + philox dropout", lambda: K.cn_to_c1(x, w27, b1, False
          ("cn_to_c1 2x37x45x51", lambda: K.cn_to_c1(x[:2, :37, :45, :51].contiguous(), w27, b1, False, 1, None, 0.35, 99)),
          ("c1_to_cn with bias", lambda: K.c1_to_cn(x1, w27, b64)),
          ("c1_to_cn no bias, flipped taps", lambda: K.c1_to_cn(x1, w27, None, True)),
+         ("c1_to_cn no bias, 60 % zero input, negative filters",
+          lambda: K.c1_to_cn(x1_sparse, -w27.abs(), None, True)),
          ("wgrad_c1", lambda: K.wgrad_c1(x, x1, 27)[0])]
 for name, fn in cases:
     a, b = both(fn)
@@ -47,7 +50,7 @@ for name, fn in cases:
         torch.cuda.synchronize()
         assert torch.equal(b, c), f"{name}: new build not deterministic"
     af, bf = a.float(), b.float()
-    ne = af != bf
+    ne = a.view(torch.int16) != b.view(torch.int16) if a.dtype == torch.bfloat16 else af != bf   # -0 vs +0 counts
     worst = float(((af - bf).abs() / af.abs().clamp_min(1e-6))[ne].max()) if bool(ne.any()) else 0.0
     print(f"{name:34s} bitwise equal: {bool(torch.equal(a, b))!s:5s}  elements differing {100 * ne.float().mean().item():.4f} %  "
           f"worst relative difference {worst:.2e}")
