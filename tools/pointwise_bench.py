@@ -44,7 +44,10 @@ rows = [
     ("bn_act_fwd none + philox dropout", 2 * T, lambda: K.bn_act_fwd(y, scale, shift, None, 0.2, 0, None, 0.35, 1)),
     ("bn_act_fwd none + philox + keep-bit store", 2 * T + T / 16,
      lambda: K.bn_act_fwd(y, scale, shift, None, 0.2, 0, None, 0.35, 1, keep_bits=bits)),
+    ("bn_act_fwd + residual (2nd BN of a block)", 3 * T, lambda: K.bn_act_fwd(y, scale, shift, g, 0.2, 0)),
     ("bn_act_fwd avgpool", T + T / 8, lambda: K.bn_act_fwd(y, scale, shift, None, 0.2, 1)),
+    ("bn_act_bwd + residual gradient", 6 * T,
+     lambda: K.bn_act_bwd(g, y, g, mean, invstd, gamma, beta, 0.2, 0, need_dres=True)),
     ("bn_act_bwd none (reduce+apply)", 5 * T, lambda: K.bn_act_bwd(g, y, None, mean, invstd, gamma, beta, 0.2, 0)),
     ("bn_act_bwd none + philox", 5 * T, lambda: K.bn_act_bwd(g, y, None, mean, invstd, gamma, beta, 0.2, 0, None, 0.35, 1)),
     ("bn_act_bwd none + keep bits (as the step runs it)", 5 * T + 2 * T / 16,
