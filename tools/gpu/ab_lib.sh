@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B/A/B of two builds of the library on the headline bench:  r02_ab_lib.sh <libA> <libB> [pytest -k expression]
+# A/B/A/B of two builds of the library on the headline bench:  ab_lib.sh <libA> <libB> [pytest -k expression]
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 if [ -n "$3" ]; then timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "$3" 2>&1 | tail -3; fi
