@@ -90,6 +90,19 @@ def test_bn_act_fwd_bwd(resample, with_res, with_mask):
     assert_f32_close(got[3], exp[3], "dbeta", 1e-3)
 
 
+@pytest.mark.parametrize("shape,C", [((2, 4, 6, 8), 64), ((3, 17, 19, 23), 64), ((1, 9, 10, 11), 256), ((4, 40, 48, 40), 64)])
+def test_bn_act_plain_fwd_equals_general_kernel(shape, C):
+    """The streaming kernel taken when there is no residual / dropout / resampling (bn_act_plain_fwd_kernel, 8 loads in
+    flight per thread) must return exactly what the general kernel returns: the general kernel is forced by a zero
+    residual, which adds +0.0 to every value (only the sign of an exact zero can differ, and compares equal)."""
+    y = bf(*shape, C, scale=1.5)
+    scale, shift = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.4
+    plain = K.bn_act_fwd(y, scale, shift, None, 0.2, 0)
+    general = K.bn_act_fwd(y, scale, shift, torch.zeros_like(y), 0.2, 0)
+    assert torch.equal(plain, general)
+    assert_bf16_close(plain, S.bn_act_fwd(y, scale, shift, None, 0.2, 0, None, 0.0, 0), "bn_act_plain_fwd vs spec")
+
+
 def test_bn_act_relu_slope_zero():
     C = 128
     y = bf(1, 4, 4, 4, C)
