@@ -34,7 +34,10 @@ UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nseco
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):       # the raw page exported on the GPU box (ncu -i X.ncu-rep --page raw --csv)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     rows = [r for r in rows if r and not r[0].startswith("==")]
     head, units, body = rows[0], rows[1], rows[2:]
@@ -71,6 +74,7 @@ def main():
     ap.add_argument("--command", default="")
     ap.add_argument("--top-kernel", default="conv3_kd3_kernel")
     ap.add_argument("--top-shape", default="64->64 @ 8x80x96x80")
+    ap.add_argument("--no-top", action="store_true", help="do not rewrite profiles/top_kernel_ncu.json")
     a = ap.parse_args()
     rows = load(a.rep)
     lines = [f"# ncu --set full --clock-control none, source commit {a.commit}", "",
@@ -88,7 +92,7 @@ def main():
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
     top = [d for d in rows if d["kernel"].startswith(a.top_kernel)]
-    if top:
+    if top and not a.no_top:
         d = max(top, key=lambda r: r.get("dur_us", 0.0))
         js = {"kernel": a.top_kernel, "shape": a.top_shape, "duration_us": round(d.get("dur_us", 0.0), 1),
               "dram_bytes_per_launch": d.get("dram_rd", 0.0) + d.get("dram_wr", 0.0),
